@@ -1,0 +1,384 @@
+"""ctypes mirror of include/dynprog_cuda.h plus the synthetic workload generator.
+
+Host-side plumbing only: loads libdynprog_cuda.so (the product), and builds
+problem arrays as numpy structured arrays laid out exactly like dpc_problem_t.
+The reference interface this mirrors is src/dynprog.h (Dynprog_single_gap 71-82,
+Dynprog_cdna_gap 84-97, Dynprog_genome_gap 99-117, Dynprog_end5_gap 119-132,
+Dynprog_end3_gap 148-161).  Nothing here falls back to a CPU solver: if the
+CUDA library is missing, loading raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+DPC_UNSET = -2000000001
+SINGLE_GAP, GENOME_GAP, CDNA_GAP, END5_GAP, END3_GAP = range(5)
+QUERYEND_GAP, QUERYEND_INDELS, QUERYEND_NOGAPS, BEST_LOCAL = range(4)
+KIND_NAMES = ["single_gap", "genome_gap", "cdna_gap", "end5_gap", "end3_gap"]
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("seq1", C.c_void_p), ("seq1R", C.c_void_p),
+        ("kind", C.c_int32), ("endalign", C.c_int32),
+        ("length1", C.c_int32), ("length1R", C.c_int32), ("length2", C.c_int32), ("length2R", C.c_int32),
+        ("offset1", C.c_int32), ("offset1R", C.c_int32), ("offset2", C.c_int32), ("offset2R", C.c_int32),
+        ("chroffset", C.c_uint32), ("chrhigh", C.c_uint32), ("chrpos", C.c_uint32), ("genomiclength", C.c_uint32),
+        ("chrnum", C.c_int32), ("cdna_direction", C.c_int32), ("extraband", C.c_int32),
+        ("maxpeelback", C.c_int32), ("score_threshold", C.c_int32), ("dynprogindex", C.c_int32),
+        ("watsonp", C.c_uint8), ("jump_late_p", C.c_uint8), ("widebandp", C.c_uint8), ("halfp", C.c_uint8),
+        ("finalp", C.c_uint8), ("use_probabilities_p", C.c_uint8), ("splicingp", C.c_uint8), ("reserved", C.c_uint8),
+        ("defect_rate", C.c_double),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("null_list", C.c_int32), ("dynprogindex_out", C.c_int32), ("finalscore", C.c_int32),
+        ("nmatches", C.c_int32), ("nmismatches", C.c_int32), ("nopens", C.c_int32), ("nindels", C.c_int32),
+        ("new_leftgenomepos", C.c_int32), ("new_rightgenomepos", C.c_int32),
+        ("exonhead", C.c_int32), ("introntype", C.c_int32), ("incompletep", C.c_int32),
+        ("npairs", C.c_int32), ("reserved", C.c_int32),
+        ("left_prob", C.c_double), ("right_prob", C.c_double),
+    ]
+
+
+class Pair(C.Structure):
+    _fields_ = [
+        ("querypos", C.c_int32), ("genomepos", C.c_int32), ("dynprogindex", C.c_int32),
+        ("cdna", C.c_char), ("comp", C.c_char), ("genome", C.c_char), ("gapp", C.c_uint8),
+    ]
+
+
+PROB_FN = C.CFUNCTYPE(C.c_double, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p)
+KNOWN_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p)
+
+
+class Setup(C.Structure):
+    _fields_ = [
+        ("genome_blocks", C.c_void_p), ("genome_nwords", C.c_uint64),
+        ("novelsplicingp", C.c_int32), ("reserved", C.c_int32),
+        ("splice_prob", C.c_void_p), ("splice_known", C.c_void_p), ("user", C.c_void_p),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("nproblems", C.c_int64), ("nmatrices", C.c_int64), ("cells", C.c_int64),
+        ("fill_bytes", C.c_int64), ("traceback_bytes", C.c_int64),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("launches", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("genome_nbases", C.c_uint64),
+        ("nchr", C.c_int32), ("extraband", C.c_int32), ("len_lo", C.c_int32), ("len_hi", C.c_int32),
+        ("intron_lo", C.c_int32), ("intron_hi", C.c_int32),
+        ("p_sub", C.c_double), ("p_del", C.c_double), ("p_ins", C.c_double),
+        ("long_frac", C.c_double), ("long_hi", C.c_int32), ("edge_frac_pm", C.c_int32),
+        ("finalp_mode", C.c_int32), ("prob_mode_pm", C.c_int32), ("lower_case", C.c_int32),
+        ("iupac_pm", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+PROBLEM_DT = np.dtype(Problem)
+RESULT_DT = np.dtype(Result)
+PAIR_DT = np.dtype(Pair)
+assert PROBLEM_DT.itemsize == 112 and RESULT_DT.itemsize == 72 and PAIR_DT.itemsize == 16
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# --------------------------------------------------------------------------- synth
+_synth = None
+
+
+def synth_lib():
+    global _synth
+    if _synth is None:
+        _synth = C.CDLL(os.path.join(HERE, "host", "libdpc_synth.so"))
+        _synth.synth_genome_nwords.restype = C.c_uint64
+        _synth.synth_genome_nwords.argtypes = [C.c_uint64]
+        _synth.synth_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double]
+        _synth.synth_genome_from_ascii.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        _synth.synth_genome_char.restype = C.c_char
+        _synth.synth_genome_char.argtypes = [C.c_void_p, C.c_uint32]
+        for name in ("synth_single_gaps", "synth_end_gaps", "synth_genome_gaps", "synth_cdna_gaps"):
+            f = getattr(_synth, name)
+            f.restype = C.c_int64
+            f.argtypes = [C.POINTER(SynthParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+    return _synth
+
+
+class Workload:
+    """A genome plus problem arrays.  Keeps the query buffers alive (the problems point into them)."""
+
+    def __init__(self, nbases, seed=1, n_frac=0.0, nchr=4):
+        lib = synth_lib()
+        self.nbases = int(nbases)
+        self.nchr = nchr
+        self.seed = seed
+        self.blocks = np.zeros(int(lib.synth_genome_nwords(self.nbases)), dtype=np.uint32)
+        lib.synth_genome(_ptr(self.blocks), self.nbases, seed, n_frac)
+        self._keep = []
+
+    @classmethod
+    def from_ascii(cls, seq):
+        lib = synth_lib()
+        self = cls.__new__(cls)
+        self.nbases = len(seq)
+        self.nchr = 1
+        self.seed = 0
+        self.blocks = np.zeros(int(lib.synth_genome_nwords(self.nbases)), dtype=np.uint32)
+        lib.synth_genome_from_ascii(_ptr(self.blocks), seq.encode(), self.nbases)
+        self._keep = []
+        return self
+
+    def params(self, **kw):
+        sp = SynthParams()
+        sp.seed = self.seed
+        sp.genome_nbases = self.nbases
+        sp.nchr = self.nchr
+        sp.extraband = 3
+        sp.len_lo, sp.len_hi = 10, 100
+        sp.intron_lo, sp.intron_hi = 50, 20000
+        sp.p_sub, sp.p_del, sp.p_ins = 0.05, 0.03, 0.03
+        sp.long_frac, sp.long_hi = 0.0, 600
+        for k, v in kw.items():
+            setattr(sp, k, v)
+        return sp
+
+    def _gen(self, fname, n, qbytes_per, sp):
+        lib = synth_lib()
+        probs = np.zeros(n, dtype=PROBLEM_DT)
+        qbuf = np.zeros(int(n) * int(qbytes_per) + 4096, dtype=np.uint8)
+        used = getattr(lib, fname)(C.byref(sp), _ptr(self.blocks), n, _ptr(probs), _ptr(qbuf), qbuf.size)
+        if used < 0:
+            raise RuntimeError("%s: query buffer too small" % fname)
+        self._keep.append(qbuf)
+        return probs
+
+    def single_gaps(self, n, extraband=30, **kw):
+        sp = self.params(extraband=extraband, len_lo=10, len_hi=100, p_sub=0.05, p_del=0.03, p_ins=0.03, **kw)
+        return self._gen("synth_single_gaps", n, 2 * sp.len_hi + 16, sp)
+
+    def end_gaps(self, n, extraband=3, **kw):
+        sp = self.params(extraband=extraband, len_lo=1, len_hi=40, p_sub=0.03, p_del=0.0025, p_ins=0.0025, **kw)
+        return self._gen("synth_end_gaps", n, 2 * (sp.len_hi + 11) + 16, sp)
+
+    def genome_gaps(self, n, extraband=7, long_frac=0.1, long_hi=600, **kw):
+        sp = self.params(extraband=extraband, len_lo=22, len_hi=60, p_sub=0.02, p_del=0.005, p_ins=0.005,
+                         long_frac=long_frac, long_hi=long_hi, **kw)
+        per = 2 * (sp.long_hi if long_frac > 0 else sp.len_hi) + 32
+        return self._gen("synth_genome_gaps", n, per, sp)
+
+    def cdna_gaps(self, n, extraband=7, **kw):
+        d = dict(extraband=extraband, len_lo=4, len_hi=40, intron_lo=10, intron_hi=60, p_sub=0.02, p_del=0.005, p_ins=0.005)
+        d.update(kw)
+        sp = self.params(**d)
+        return self._gen("synth_cdna_gaps", n, 2 * sp.len_hi + sp.intron_hi + 64, sp)
+
+    def make_setup(self, splice_prob=None, splice_known=None, novelsplicingp=1):
+        s = Setup()
+        s.genome_blocks = self.blocks.ctypes.data
+        s.genome_nwords = self.blocks.size
+        s.novelsplicingp = novelsplicingp
+        s.splice_prob = C.cast(splice_prob, C.c_void_p).value if splice_prob is not None else None
+        s.splice_known = C.cast(splice_known, C.c_void_p).value if splice_known is not None else None
+        s.user = None
+        self._keep.append((splice_prob, splice_known))
+        return s
+
+
+# --------------------------------------------------------------------------- solvers
+class _SolverLib:
+    """Common driver for the three libraries that speak dpc_problem_t / dpc_result_t."""
+
+    prefix = None
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+        self.path = path
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+
+def _solve_common(fn, problems, want_pairs=True, pair_cap=None):
+    n = len(problems)
+    results = np.zeros(n, dtype=RESULT_DT)
+    pair_off = np.zeros(n + 1, dtype=np.int64)
+    if want_pairs:
+        if pair_cap is None:
+            pair_cap = int((problems["length1"].astype(np.int64) + problems["length1R"] + problems["length2"]
+                            + problems["length2R"] + 8).clip(min=8).sum()) + 64
+        pairs = np.zeros(pair_cap, dtype=PAIR_DT)
+        rc = fn(_ptr(problems), n, _ptr(results), _ptr(pairs), pair_cap, _ptr(pair_off))
+    else:
+        pairs = np.zeros(0, dtype=PAIR_DT)
+        rc = fn(_ptr(problems), n, _ptr(results), None, 0, _ptr(pair_off))
+    if rc != 0:
+        raise RuntimeError("solve failed with code %d" % rc)
+    return results, pairs[: pair_off[n]] if want_pairs else pairs, pair_off
+
+
+class PortOracle(_SolverLib):
+    """oracle/liboracle_port.so -- TEST INFRASTRUCTURE (CPU restatement)."""
+
+    def __init__(self, path=None):
+        super().__init__(path or os.path.join(ROOT, "oracle", "liboracle_port.so"))
+        L = self.lib
+        L.port_init.argtypes = [C.c_int] * 6
+        L.port_setup.argtypes = [C.POINTER(Setup)]
+        L.port_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.port_pairdistance.argtypes = [C.c_int] * 3
+
+    def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
+        self.lib.port_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
+
+    def setup(self, setup):
+        self._setup = setup
+        self.lib.port_setup(C.byref(setup))
+
+    def solve(self, problems, want_pairs=True):
+        return _solve_common(self.lib.port_solve, problems, want_pairs)
+
+
+class RefOracle(_SolverLib):
+    """oracle/_ref/libdynprog_ref.so -- the compiled, unmodified reference (TEST INFRASTRUCTURE)."""
+
+    def __init__(self, path=None):
+        super().__init__(path or os.path.join(ROOT, "oracle", "_ref", "libdynprog_ref.so"))
+        L = self.lib
+        L.ref_init.argtypes = [C.c_int] * 6
+        L.ref_setup.argtypes = [C.POINTER(Setup)]
+        L.ref_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.ref_solve_mt.restype = C.c_double
+        L.ref_solve_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_pairdistance.argtypes = [C.c_int] * 2
+        L.ref_splice_prob.restype = C.c_double
+        self.splice_prob = C.cast(L.ref_splice_prob, PROB_FN)
+
+    def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
+        self.lib.ref_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
+
+    def setup(self, setup):
+        self._setup = setup
+        self.lib.ref_setup(C.byref(setup))
+
+    def solve(self, problems, want_pairs=True):
+        return _solve_common(self.lib.ref_solve, problems, want_pairs)
+
+    def solve_mt(self, problems, nthreads):
+        results = np.zeros(len(problems), dtype=RESULT_DT)
+        secs = self.lib.ref_solve_mt(_ptr(problems), len(problems), _ptr(results), nthreads)
+        return results, secs
+
+
+class CudaLib(_SolverLib):
+    """gmap-gsnap_b200/csrc/libdynprog_cuda.so -- THE PRODUCT."""
+
+    def __init__(self, path=None):
+        path = path or os.path.join(HERE, "csrc", "libdynprog_cuda.so")
+        if not os.path.exists(path):
+            raise RuntimeError("libdynprog_cuda.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        super().__init__(path)
+        L = self.lib
+        L.dpc_init.argtypes = [C.c_int] * 6
+        L.dpc_setup.argtypes = [C.POINTER(Setup)]
+        L.dpc_ctx_new.restype = C.c_void_p
+        L.dpc_ctx_new.argtypes = [C.c_int]
+        L.dpc_ctx_free.argtypes = [C.c_void_p]
+        L.dpc_add_bulk.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.dpc_add.argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("dpc_flush", "dpc_wait", "dpc_reset", "dpc_relaunch"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.dpc_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.dpc_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.dpc_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.dpc_stream.restype = C.c_void_p
+        L.dpc_stream.argtypes = [C.c_void_p]
+        L.dpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
+        L.dpc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.dpc_pairdistance.argtypes = [C.c_int] * 3
+        L.dpc_strerror.restype = C.c_char_p
+        L.dpc_strerror.argtypes = [C.c_int]
+        L.dpc_maxlengths.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self.ctx = None
+
+    def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
+        rc = self.lib.dpc_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
+        if rc != 0:
+            raise RuntimeError("dpc_init: %s" % self.lib.dpc_strerror(rc).decode())
+
+    def setup(self, setup):
+        self._setup = setup
+        rc = self.lib.dpc_setup(C.byref(setup))
+        if rc != 0:
+            raise RuntimeError("dpc_setup: %s" % self.lib.dpc_strerror(rc).decode())
+
+    def open(self, device=0):
+        self.ctx = self.lib.dpc_ctx_new(device)
+        if not self.ctx:
+            raise RuntimeError("dpc_ctx_new(%d) failed: no usable CUDA device (no CPU fallback)" % device)
+        return self
+
+    def close(self):
+        if self.ctx:
+            self.lib.dpc_ctx_free(self.ctx)
+            self.ctx = None
+
+    def check(self, rc, what):
+        if rc < 0:
+            raise RuntimeError("%s: %s" % (what, self.lib.dpc_strerror(rc).decode()))
+        return rc
+
+    def solve(self, problems, want_pairs=True):
+        def fn(p, n, r, pr, cap, off):
+            return self.lib.dpc_solve(self.ctx, p, n, r, pr, cap, off)
+        return _solve_common(fn, problems, want_pairs)
+
+    def stats(self):
+        s = Stats()
+        self.check(self.lib.dpc_get_stats(self.ctx, C.byref(s)), "dpc_get_stats")
+        return s
+
+    def kernel_ms(self):
+        ms = (C.c_float * 3)()
+        self.check(self.lib.dpc_last_kernel_ms(self.ctx, C.byref(ms)), "dpc_last_kernel_ms")
+        return list(ms)
+
+
+# --------------------------------------------------------------------------- comparison
+RESULT_FIELDS = [n for n, _ in Result._fields_ if n != "reserved"]
+
+
+def compare(res_a, pairs_a, off_a, res_b, pairs_b, off_b, rtol=1e-6):
+    """Returns a list of human-readable mismatches (empty = identical)."""
+    bad = []
+    for f in RESULT_FIELDS:
+        a, b = res_a[f], res_b[f]
+        if f in ("left_prob", "right_prob"):
+            ok = np.isclose(a, b, rtol=rtol, atol=0.0) | (a == b)
+        else:
+            ok = a == b
+        for i in np.nonzero(~ok)[0][:5]:
+            bad.append("problem %d field %s: %r vs %r" % (i, f, a[i], b[i]))
+    if not np.array_equal(off_a, off_b):
+        i = int(np.nonzero(off_a != off_b)[0][0])
+        bad.append("pair offsets differ first at problem %d" % (i - 1))
+    elif len(pairs_a):
+        neq = pairs_a != pairs_b
+        if neq.any():
+            j = int(np.nonzero(neq)[0][0])
+            i = int(np.searchsorted(off_a, j, side="right") - 1)
+            bad.append("pair %d (problem %d, #%d): %r vs %r" % (j, i, j - off_a[i], pairs_a[j], pairs_b[j]))
+    return bad

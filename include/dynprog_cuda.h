@@ -1,0 +1,238 @@
+/* libdynprog_cuda -- C ABI of the B200-native banded gap-fill DP for GMAP/GSNAP.
+ *
+ * This header is the drop-in boundary.  It replaces, for the five gap-fill
+ * solvers only, the interface declared in the reference's src/dynprog.h:
+ *
+ *   reference (src/dynprog.h)                    this library
+ *   -------------------------------------------  ---------------------------------
+ *   Dynprog_init          dynprog.h:67-69        dpc_init
+ *   Dynprog_setup         dynprog.h:37-45        dpc_setup
+ *   Dynprog_term          dynprog.h:65-66        dpc_term
+ *   Dynprog_new/_free     dynprog.h:51-55        dpc_ctx_new / dpc_ctx_free
+ *   Dynprog_single_gap    dynprog.h:71-82        dpc_add(kind=DPC_SINGLE_GAP) ...
+ *   Dynprog_cdna_gap      dynprog.h:84-97        dpc_add(kind=DPC_CDNA_GAP)
+ *   Dynprog_genome_gap    dynprog.h:99-117       dpc_add(kind=DPC_GENOME_GAP)
+ *   Dynprog_end5_gap      dynprog.h:119-132      dpc_add(kind=DPC_END5_GAP)
+ *   Dynprog_end3_gap      dynprog.h:148-161      dpc_add(kind=DPC_END3_GAP)
+ *   (List_T of Pair_T via Pairpool_push)         dpc_pairs (flat dpc_pair_t records,
+ *                                                in the order of the returned List_T)
+ *
+ * The reference solves one problem per call; this library collects problems
+ * (dpc_add / dpc_add_bulk), solves a whole batch on the GPU (dpc_flush +
+ * dpc_wait) and hands back scores plus device-computed traceback runs, from
+ * which dpc_pairs rebuilds the Pair records on the host.  The reference-named
+ * functions with their exact signatures live in
+ * gmap-gsnap_b200/host/dynprog_dropin.c (compiled inside a GMAP tree, see
+ * INTEGRATION.md) and are "add 1 + flush + wait + pairs".
+ *
+ * Plain C, plain pointers and sizes.  No CPU fallback: every solver entry
+ * point returns DPC_ERR_CUDA when no device/driver is usable.
+ */
+#ifndef DYNPROG_CUDA_H
+#define DYNPROG_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants mirrored from the reference ---------------------------- */
+#define DPC_UNKNOWNJUMP   (-1000000)   /* dynprog.h:30  UNKNOWNJUMP   */
+#define DPC_NEG_INFINITY  (-1000000)   /* dynprog.c:119 NEG_INFINITY  */
+#define DPC_UNSET         (-2000000001)/* "output parameter left untouched by the reference" */
+
+/* Endalign_T, dynprog.h:7 */
+enum { DPC_QUERYEND_GAP = 0, DPC_QUERYEND_INDELS = 1, DPC_QUERYEND_NOGAPS = 2, DPC_BEST_LOCAL = 3 };
+
+/* Mode_T, mode.h (only reaches the DP through pairdistance_init, dynprog.c:1215) */
+enum { DPC_MODE_STANDARD = 0, DPC_MODE_CMET_STRANDED = 1, DPC_MODE_CMET_NONSTRANDED = 2,
+       DPC_MODE_ATOI_STRANDED = 3, DPC_MODE_ATOI_NONSTRANDED = 4 };
+
+/* which solver a problem is for */
+enum { DPC_SINGLE_GAP = 0, DPC_GENOME_GAP = 1, DPC_CDNA_GAP = 2, DPC_END5_GAP = 3, DPC_END3_GAP = 4 };
+
+/* error codes (negative return values) */
+enum {
+  DPC_OK = 0,
+  DPC_ERR_CUDA = -1,          /* no device, driver error, kernel fault: fatal, like exit(9) in gmap.c:2287 */
+  DPC_ERR_ARG = -2,           /* malformed problem (negative length where the reference abort()s, ...) */
+  DPC_ERR_ALPHABET = -3,      /* query byte >= 128, or genome byte outside ACGTNX* */
+  DPC_ERR_UNSUPPORTED = -4,   /* known-introns-only bridge mode (dynprog.c:3552-3696): needs IIT pair lookups */
+  DPC_ERR_STATE = -5,         /* called before dpc_init/dpc_setup, ticket out of range, ... */
+  DPC_ERR_NOMEM = -6
+};
+
+/* ---- one gap-fill problem ---------------------------------------------
+ * Field meaning per kind (names on the right are the reference's parameters):
+ *
+ *              SINGLE        GENOME            CDNA              END5            END3
+ *  seq1        sequence1     sequence1         sequence1L        revsequence1    sequence1
+ *  seq1R       -             -                 revsequence1R     -               -
+ *  length1     length1       length1           length1L          length1         length1
+ *  length1R    -             -                 length1R          -               -
+ *  length2     length2       length2L          length2           length2         length2
+ *  length2R    -             length2R          -                 -               -
+ *  offset1     offset1       offset1           offset1L          revoffset1      offset1
+ *  offset1R    -             -                 revoffset1R       -               -
+ *  offset2     offset2       offset2L          offset2           revoffset2      offset2
+ *  offset2R    -             revoffset2R       -                 -               -
+ *  extraband   _single       _paired           _paired           _end            _end
+ *
+ * "rev" pointers follow the reference convention: they point at the LAST
+ * character and are indexed with non-positive offsets (dynprog.c:1674).
+ * The upper-case twin (sequenceuc1) is derived as toupper(seq1[i]).
+ * The genomic side is never passed as characters: like the reference with
+ * use_genomicseg_p == false (stage3.c:9864) it is fetched from the 2-bit
+ * genome registered with dpc_setup, through get_genomic_nt semantics
+ * (dynprog.c:403-441) evaluated on the device.
+ * Dead reference parameters (onesidegapp, close_indels_mode, maxhoriz/vertjump,
+ * sequence2*, genomicuc_ptr, use_genomicseg_p) have no field.
+ */
+typedef struct dpc_problem {
+  const char *seq1;
+  const char *seq1R;
+  int32_t kind;
+  int32_t endalign;
+  int32_t length1, length1R, length2, length2R;
+  int32_t offset1, offset1R, offset2, offset2R;
+  uint32_t chroffset, chrhigh, chrpos, genomiclength;
+  int32_t chrnum;
+  int32_t cdna_direction;
+  int32_t extraband;
+  int32_t maxpeelback;
+  int32_t score_threshold;
+  int32_t dynprogindex;       /* value of *dynprogindex at call time (stamped on the pairs) */
+  uint8_t watsonp, jump_late_p, widebandp, halfp;
+  uint8_t finalp, use_probabilities_p, splicingp, reserved;
+  double defect_rate;
+} dpc_problem_t;
+
+/* ---- one result ---------------------------------------------------------
+ * Every field starts as DPC_UNSET (doubles: -1.0) and is written exactly when
+ * the reference writes the corresponding output parameter, so "left untouched"
+ * (e.g. *introntype in probability mode, dynprog.c:4071) is observable.
+ * null_list != 0 means the reference returns (List_T) NULL.
+ * dynprogindex_out is *dynprogindex after the call (unchanged on the early
+ * returns listed in SURVEY.md 8a).
+ */
+typedef struct dpc_result {
+  int32_t null_list;
+  int32_t dynprogindex_out;
+  int32_t finalscore;
+  int32_t nmatches, nmismatches, nopens, nindels;
+  int32_t new_leftgenomepos, new_rightgenomepos;
+  int32_t exonhead, introntype;
+  int32_t incompletep;          /* cdna gap: 1 when the reference sets *incompletep = true */
+  int32_t npairs;               /* number of dpc_pair_t records dpc_pairs will produce */
+  int32_t reserved;
+  double left_prob, right_prob;
+} dpc_result_t;
+
+/* One rebuilt Pair (pairdef.h:10-47), only the fields Pairpool_push /
+ * Pairpool_push_gapholder set to something other than their constants
+ * (pairpool.c:169-215, 352-401).  gapp != 0 is a gapholder: querypos =
+ * genomepos = -1, chars ' ', queryjump = genomejump = DPC_UNKNOWNJUMP,
+ * dynprogindex 0. */
+typedef struct dpc_pair {
+  int32_t querypos;
+  int32_t genomepos;
+  int32_t dynprogindex;
+  char cdna, comp, genome;
+  uint8_t gapp;
+} dpc_pair_t;
+
+/* Host hooks that stay on the CPU side of the boundary.
+ * splice_prob: the reference's Maxent_hr_{donor,acceptor,antidonor,antiacceptor}_prob
+ *   (maxent_hr.c:27217-27340); which = 0 donor, 1 acceptor, 2 antidonor, 3 antiacceptor.
+ *   Needed for finalp (dynprog.c:3195-3287) and use_probabilities_p (3829-3903).
+ * splice_known: known-splice-site lookup (dynprog.c:3377-3542); returns nonzero when
+ *   the position is a known site.  which as above; sign as the reference passes it.
+ *   NULL means splicing_iit == NULL. */
+typedef double (*dpc_splice_prob_fn)(int which, uint32_t splice_pos, uint32_t chroffset, void *user);
+typedef int (*dpc_splice_known_fn)(int which, int chrnum, uint32_t splicesitepos, int sign, void *user);
+
+typedef struct dpc_setup {
+  const uint32_t *genome_blocks;   /* 3 x UINT4 per 32 nt: high, low, flags (genome.c:9325-9362) */
+  uint64_t genome_nwords;          /* number of UINT4 in genome_blocks */
+  int32_t novelsplicingp;          /* Dynprog_setup novelsplicingp_in */
+  int32_t reserved;
+  dpc_splice_prob_fn splice_prob;
+  dpc_splice_known_fn splice_known;
+  void *user;
+} dpc_setup_t;
+
+typedef struct dpc_ctx dpc_ctx_t;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+/* Dynprog_init (dynprog.c:1338): builds the four pairdistance tables and the
+ * consistent table for `mode`, and the length caps of compute_maxlengths
+ * (dynprog.c:831-852).  GMAP passes (nullgap=600, 10, maxpeelback=11, 10, 8). */
+int dpc_init(int maxlookback, int extraquerygap, int maxpeelback,
+             int extramaterial_end, int extramaterial_paired, int mode);
+/* Dynprog_setup (dynprog.c:349): registers the genome and the splicing hooks;
+ * the genome blocks are mirrored into HBM on every device that has a context. */
+int dpc_setup(const dpc_setup_t *setup);
+void dpc_term(void);
+/* Dynprog_pairdistance (dynprog.c:1048) for any of the 4 mismatch types (0 HIGHQ .. 3 ENDQ). */
+int dpc_pairdistance(int mismatchtype, int c1, int c2);
+/* maxlength1 / maxlength2 of struct Dynprog_T (dynprog.c:822-829). */
+void dpc_maxlengths(int *maxlength1, int *maxlength2);
+const char *dpc_strerror(int code);
+/* Number of usable CUDA devices (0 when there is no driver/GPU). */
+int dpc_device_count(void);
+
+/* ---- per-thread batch context (one Dynprog_T triple + stream) ---------- */
+dpc_ctx_t *dpc_ctx_new(int device);
+void dpc_ctx_free(dpc_ctx_t *ctx);
+
+/* Enqueue.  Sequences are copied at enqueue time.  Returns the ticket (>= 0,
+ * consecutive) of the first problem added, or a negative error code. */
+int dpc_add(dpc_ctx_t *ctx, const dpc_problem_t *problem);
+int dpc_add_bulk(dpc_ctx_t *ctx, const dpc_problem_t *problems, int n);
+/* Asynchronous: H2D, fill/bridge/traceback kernels, D2H on the context's stream. */
+int dpc_flush(dpc_ctx_t *ctx);
+/* Blocks until the batch is back; afterwards dpc_result / dpc_pairs are valid. */
+int dpc_wait(dpc_ctx_t *ctx);
+int dpc_result(dpc_ctx_t *ctx, int ticket, dpc_result_t *out);
+/* Rebuilds the Pair records of one problem in the order of the List_T the
+ * reference returns (head first).  Returns the count, or a negative code;
+ * cap too small -> DPC_ERR_ARG. */
+int dpc_pairs(dpc_ctx_t *ctx, int ticket, dpc_pair_t *out, int cap);
+/* Forget the batch (tickets restart at 0). */
+int dpc_reset(dpc_ctx_t *ctx);
+
+/* Whole batch in one call: add_bulk + flush + wait + results (+ pairs when
+ * pairs != NULL; pair_off[i] = index of problem i's first record, pair_off has
+ * n+1 entries).  Returns 0 or a negative code; DPC_ERR_NOMEM if pair_cap is too small. */
+int dpc_solve(dpc_ctx_t *ctx, const dpc_problem_t *problems, int n,
+              dpc_result_t *results, dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off);
+
+/* ---- measurement hooks (bench.py) -------------------------------------- */
+/* After dpc_flush+dpc_wait the batch stays resident in HBM; dpc_relaunch runs
+ * the device work again (kernels only, no copies) on the context's stream and
+ * returns the number of kernel launches it made.  stream_out receives the
+ * cudaStream_t so the caller can bracket it with events. */
+int dpc_relaunch(dpc_ctx_t *ctx);
+void *dpc_stream(dpc_ctx_t *ctx);
+/* Average device time in ms of the last dpc_flush/dpc_relaunch per kernel
+ * stage (CUDA events recorded on the context's stream):
+ * 0 fill(+bridge), 1 traceback, 2 total.  Returns DPC_OK or an error. */
+int dpc_last_kernel_ms(dpc_ctx_t *ctx, float ms[3]);
+/* Work counters of the current batch: in-band DP cells (SURVEY.md 8d
+ * definition), matrices filled, algorithmic HBM bytes of the fill kernel,
+ * bytes copied H2D / D2H by the last flush. */
+typedef struct dpc_stats {
+  int64_t nproblems, nmatrices, cells;
+  int64_t fill_bytes;           /* direction words written + inputs read by the fill kernel */
+  int64_t traceback_bytes;      /* direction words read + ops written by the traceback kernel */
+  int64_t h2d_bytes, d2h_bytes;
+  int32_t launches;             /* kernel launches of the last flush/relaunch */
+  int32_t reserved;
+} dpc_stats_t;
+int dpc_get_stats(dpc_ctx_t *ctx, dpc_stats_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNPROG_CUDA_H */
