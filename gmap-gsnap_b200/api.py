@@ -283,6 +283,30 @@ class RefOracle(_SolverLib):
         return results, secs
 
 
+class EmulLib(_SolverLib):
+    """tests/emul/libdpc_emul.so -- TEST SCAFFOLDING: the device routines compiled single-lane for the CPU."""
+
+    def __init__(self, path=None):
+        super().__init__(path or os.path.join(ROOT, "tests", "emul", "libdpc_emul.so"))
+        L = self.lib
+        L.emul_init.argtypes = [C.c_int] * 6
+        L.emul_setup.argtypes = [C.POINTER(Setup)]
+        L.emul_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.emul_pairdistance.argtypes = [C.c_int] * 3
+
+    def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
+        rc = self.lib.emul_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
+        if rc != 0:
+            raise RuntimeError("emul_init failed: %d" % rc)
+
+    def setup(self, setup):
+        self._setup = setup
+        self.lib.emul_setup(C.byref(setup))
+
+    def solve(self, problems, want_pairs=True):
+        return _solve_common(self.lib.emul_solve, problems, want_pairs)
+
+
 class CudaLib(_SolverLib):
     """gmap-gsnap_b200/csrc/libdynprog_cuda.so -- THE PRODUCT."""
 

@@ -1,0 +1,666 @@
+/* dpc_core.h -- the gap-fill algorithms of libdynprog_cuda, as warp-level routines.
+ *
+ * One warp solves one problem: it stages the query and genomic characters in its
+ * arena (shared memory, or HBM scratch for oversize problems), fills one or two
+ * banded 3-state Gotoh matrices, searches the end point / intron bridge, and
+ * walks the traceback, leaving run-length ops for the host to rebuild Pair
+ * records from.  Semantics follow the reference's src/dynprog.c (GMAP/GSNAP
+ * 2012-07-03); each routine cites the lines it answers to.
+ *
+ * The routines are written against a `Lanes` handle (lane id, lane count):
+ *   - under nvcc they run with 32 lanes and __syncwarp / __shfl_sync;
+ *   - tests/emul compiles the same header with g++ and a single lane, so the
+ *     index arithmetic, tie-breaks and boundary rules can be unit-tested on a
+ *     machine without a GPU.  That build is test scaffolding only; the product
+ *     library (dynprog_cuda.cu) has no CPU path.
+ */
+#ifndef DPC_CORE_H
+#define DPC_CORE_H
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define DPC_HD __device__ __forceinline__
+#define DPC_HDM __device__ __forceinline__
+#define DPC_SYNC() __syncwarp()
+#else
+#define DPC_HD static inline
+#define DPC_HDM inline
+#define DPC_SYNC() ((void)0)
+#endif
+
+#define DPC_NEG (-1000000)                 /* NEG_INFINITY, dynprog.c:119 */
+#define DPC_BRIDGE_FLOOR (-100000)         /* initial bestscore of the bridges, dynprog.c:3072, 3310 */
+#define DPC_MICROINTRON 9                  /* MICROINTRON_LENGTH, dynprog.c:139 */
+
+/* direction nibble of one cell: bits 0-1 nogap direction, bit 2 gap1 came from gap1 (HORIZ),
+ * bit 3 gap2 came from gap2 (VERT).  (struct Direction3_T, dynprog.c:717, needs 3 bytes.) */
+enum { DPC_DIAG = 0, DPC_HORIZ = 1, DPC_VERT = 2 };
+
+/* traceback ops: (length << 2) | type, in traceback order */
+enum { DPC_OP_M = 0,        /* n aligned columns (match / mismatch decided from the characters) */
+       DPC_OP_GSKIP = 1,    /* genome-only run kept as dashes (add_genomeskip, dynprog.c:2416) */
+       DPC_OP_QSKIP = 2,    /* query-only run (add_queryskip, dynprog.c:2372) */
+       DPC_OP_GAPHOLDER = 3 /* genome-only run of >= 9 with intron dinucleotides: one gapholder (2507) */ };
+
+/* genome codes: A C G T N and '*' (outside the genomic segment, dynprog.c:415-419) */
+enum { DPC_GN = 4, DPC_GSTAR = 5 };
+
+/* problem flags */
+enum {
+  DPC_F_WATSON = 1, DPC_F_LATE = 2, DPC_F_WIDEBAND = 4, DPC_F_HALFP = 8, DPC_F_FINALP = 16,
+  DPC_F_PROBMODE = 32, DPC_F_ALLSTAR = 64, DPC_F_KNOWN = 128, DPC_F_NOVEL = 256
+};
+
+/* device-side problem descriptor (host packs it from dpc_problem_t) */
+struct DevProb {
+  uint32_t q0, q1;          /* byte-pool offsets of the first / second query span (forward order) */
+  uint32_t gbase, glen;     /* chroffset + chrpos, genomiclength */
+  uint32_t aux;             /* byte-pool offset (8-aligned) of known flags / probabilities, genome gaps only */
+  int32_t L1, L1R, L2, L2R; /* lengths after the reference's clipping */
+  int32_t off2, off2R;      /* segment-relative genomic start of each matrix */
+  int32_t gap;              /* rightoffset - leftoffset of the bridge constraint */
+  int32_t score_threshold;
+  int32_t extraband;
+  uint32_t scratch_lo, scratch_hi; /* HBM scratch offset (bytes) for problems that do not fit shared memory */
+  int8_t open, extend, reward, cdna_direction;
+  uint8_t kind, endalign, type, pad;
+  uint32_t flags;
+};
+
+#define DPC_INLINE_OPS 38
+/* device-side result record, 128 bytes */
+struct DevRes {
+  int32_t finalscore;
+  int32_t nmatches, nmismatches, nopens, nindels;
+  int32_t bestrL, bestcL, bestrR, bestcR;
+  int32_t introntype;
+  uint32_t status;          /* DPC_ST_* */
+  uint16_t nopsL, nopsR;
+  uint32_t ovf;             /* first op in the overflow arena when nopsL + nopsR > DPC_INLINE_OPS */
+  uint16_t ops[DPC_INLINE_OPS];
+};
+enum { DPC_ST_DONE = 1, DPC_ST_HAVE = 2, DPC_ST_OK = 4, DPC_ST_STAR = 8, DPC_ST_OVF_LOST = 16 };
+
+/* score and consistency tables reduced to the 6 genome codes.
+ * score[type][q][g] = pairdistance_array[type][q][g] (dynprog.c:1127-1226);
+ * cons[q] bit g = consistent_array[q][g]; consT[q] bit g = consistent_array[g][q]. */
+struct DevTables {
+  int8_t score[4][128][8];
+  uint8_t cons[128];
+  uint8_t consT[128];
+};
+
+struct Lanes { int lane, n; };
+
+/* ---- genome access: get_genomic_nt, dynprog.c:403-441; uncompress_one_char, genome.c:9325 ---- */
+DPC_HD int dpc_genome_code(const uint32_t *blocks, uint32_t pos) {
+  const uint32_t *b = blocks + (uint64_t)(pos >> 5) * 3;
+  int bit = (int)(pos & 31);
+  if ((b[2] >> bit) & 1U) return DPC_GN;
+  return (int)((bit < 16 ? b[1] >> (2 * bit) : b[0] >> (2 * bit - 32)) & 3U);
+}
+DPC_HD int dpc_genomic_code(const DevProb &p, const uint32_t *blocks, int genomicpos) {
+  if (genomicpos < 0 || (uint32_t)genomicpos >= p.glen || (p.flags & DPC_F_ALLSTAR)) return DPC_GSTAR;
+  if (p.flags & DPC_F_WATSON) return dpc_genome_code(blocks, p.gbase + (uint32_t)genomicpos);
+  int c = dpc_genome_code(blocks, p.gbase + (p.glen - 1) - (uint32_t)genomicpos);
+  return c < 4 ? (c ^ 3) : c;                      /* complCode, complement.h:31 */
+}
+DPC_HD int dpc_code_char(int code) { return "ACGTN*"[code]; }
+DPC_HD int dpc_query_uc(int c) {                   /* UPPERCASE_U2T, complement.h:36 */
+  if (c >= 'a' && c <= 'z') c -= 32;
+  return c == 'U' ? 'T' : c;
+}
+
+/* ---- one banded matrix ----------------------------------------------------------------- */
+struct Mat {
+  int L1, L2;               /* rows, columns */
+  int lband, rband, W;      /* W = lband + rband + 1 diagonals */
+  int wstride;              /* 32-bit words of direction nibbles per row */
+  int open, extend, late;
+  int query_rows;           /* 1: rows = query, columns = genome (compute_scores_lookup_fwd/_rev, 1424-1736);
+                               0: rows = genome, columns = query (_fwd_12/_rev_12, 1741-2044) */
+  uint8_t *rowch, *colch;   /* characters in matrix order: raw query bytes / genome codes */
+  uint32_t *dir;            /* rows 1..L1, nibble (r-1)*wstride*8 + (c-r+lband) */
+  int32_t *nband;           /* nogap score of rows 1..L1, (r-1)*W + (c-r+lband); NULL when no bridge follows */
+};
+
+DPC_HD void dpc_bands(int L1, int L2, int extraband, int widebandp, int *lband, int *rband) {
+  /* dynprog.c:1442-1454 */
+  if (!widebandp) { *lband = *rband = extraband; }
+  else if (L2 >= L1) { *rband = L2 - L1 + extraband; *lband = extraband; }
+  else { *lband = L1 - L2 + extraband; *rband = extraband; }
+}
+DPC_HD int dpc_wstride(int W) { return (W + 7) >> 3; }
+DPC_HD bool dpc_inband(const Mat &m, int r, int c) {
+  int k = c - r;
+  return r >= 1 && c >= 1 && r <= m.L1 && c <= m.L2 && k >= -m.lband && k <= m.rband;
+}
+DPC_HD int dpc_nib(const Mat &m, int r, int c) {
+  int idx = (r - 1) * (m.wstride << 3) + (c - r + m.lband);
+  return (int)((m.dir[idx >> 3] >> ((idx & 7) << 2)) & 15U);
+}
+/* directions as the reference's matrices hold them, including row 0 / column 0 (1460-1488)
+ * and the memset STOP everywhere else (724-751): returns -1 for STOP */
+DPC_HD int dpc_dirN(const Mat &m, int r, int c) { return dpc_inband(m, r, c) ? (dpc_nib(m, r, c) & 3) : -1; }
+DPC_HD bool dpc_g1_horiz(const Mat &m, int r, int c) {
+  if (r == 0) return c >= 2 && c <= m.rband && c <= m.L2;
+  return dpc_inband(m, r, c) && ((dpc_nib(m, r, c) >> 2) & 1);
+}
+DPC_HD bool dpc_g2_vert(const Mat &m, int r, int c) {
+  if (c == 0) return r >= 2 && r <= m.lband && r <= m.L1;
+  return dpc_inband(m, r, c) && ((dpc_nib(m, r, c) >> 3) & 1);
+}
+DPC_HD int dpc_nscore(const Mat &m, int r, int c) {
+  /* nogap score as the bridges read it; row 0 inside the band is NEG (1464-1475) */
+  if (dpc_inband(m, r, c)) return m.nband[(r - 1) * m.W + (c - r + m.lband)];
+  return DPC_NEG;
+}
+
+/* argmax with an explicit scan-order key: the reference's loops keep the FIRST best (`>`)
+ * or, with jump_late_p, the LAST best (`>=`) in their own scan order (2251-2285). */
+struct Best { int score; int key; };
+DPC_HD bool dpc_better(int s, int k, const Best &b, int late) {
+  return s > b.score || (s == b.score && (late ? k > b.key : k < b.key));
+}
+DPC_HD void dpc_warp_best(Best &b, int late, const Lanes &ln) {
+#ifdef __CUDACC__
+  for (int o = 16; o > 0; o >>= 1) {
+    int s = __shfl_xor_sync(0xffffffffu, b.score, o), k = __shfl_xor_sync(0xffffffffu, b.key, o);
+    if (dpc_better(s, k, b, late)) { b.score = s; b.key = k; }
+  }
+#else
+  (void)b; (void)late; (void)ln;
+#endif
+}
+DPC_HD int dpc_warp_sum(int v, const Lanes &ln) {
+#ifdef __CUDACC__
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#else
+  (void)ln;
+#endif
+  return v;
+}
+DPC_HD int dpc_bcast(int v, const Lanes &ln) {
+#ifdef __CUDACC__
+  return __shfl_sync(0xffffffffu, v, 0);
+#else
+  (void)ln; return v;
+#endif
+}
+
+/* end-point search folded into the fill.
+ * mode 1: find_best_endpoint (2235-2290): rows 1..L1, |c - r| <= extraband (the UNwidened band), start 0 at (0,0)
+ * mode 2: find_best_endpoint_to_queryend_indels (2293-2355): last row, widened band, start NEG at (L1,0) */
+struct EndSearch { int mode, eb; Best best; };   /* mode 3: the corner (L1,L2), Dynprog_single_gap 4541 */
+
+DPC_HD void dpc_cell(int Nl, int G1l, int Nu, int G2u, int Nd, int G1d, int G2d, int P,
+                     int open, int extend, int late, int *N, int *G1, int *G2, int *nib) {
+  /* dynprog.c:1519-1561 */
+  int best, s, d1 = 0, d2 = 0, dn = DPC_DIAG;
+  best = Nl + open; s = G1l;
+  if (s > best || (s == best && late)) { best = s; d1 = 1; }
+  *G1 = best + extend;
+  best = Nu + open; s = G2u;
+  if (s > best || (s == best && late)) { best = s; d2 = 1; }
+  *G2 = best + extend;
+  best = Nd;
+  if (G1d > best || (G1d == best && late)) { best = G1d; dn = DPC_HORIZ; }
+  if (G2d > best || (G2d == best && late)) { best = G2d; dn = DPC_VERT; }
+  *N = best + P;
+  *nib = dn | (d1 << 2) | (d2 << 3);
+}
+
+/* Reference fill, any band width: anti-diagonal sweep with the last two anti-diagonals kept in
+ * `st` (3 rotating buffers of N, G1, G2 indexed by row; 9*(L1+1) ints).  compute_scores_lookup_*,
+ * dynprog.c:1424-2044: all four variants leave the same matrix (see oracle/dynprog_port.c:fill). */
+DPC_HD void dpc_fill_generic(const Mat &m, int32_t *st, const int8_t *score /* [128][8] of the mismatch type */,
+                             EndSearch &es, const Lanes &ln) {
+  const int R = m.L1 + 1, L1 = m.L1, L2 = m.L2;
+  for (int d = 2; d <= L1 + L2; d++) {
+    int32_t *cur = st + (d % 3) * 3 * R, *p1 = st + ((d + 2) % 3) * 3 * R, *p2 = st + ((d + 1) % 3) * 3 * R;
+    int rlo = (d - m.rband + 1) >> 1, rhi = (d + m.lband) >> 1;
+    if (rlo < 1) rlo = 1;
+    if (rlo < d - L2) rlo = d - L2;
+    if (rhi > L1) rhi = L1;
+    if (rhi > d - 1) rhi = d - 1;
+    for (int r = rlo + ln.lane; r <= rhi; r += ln.n) {
+      int c = d - r, k = c - r;
+      int Nl, G1l, Nu, G2u, Nd, G1d, G2d;
+      /* left neighbour (r, c-1) */
+      if (c - 1 == 0) { Nl = DPC_NEG; G1l = DPC_NEG; }
+      else if (k - 1 < -m.lband) { Nl = DPC_NEG; G1l = DPC_NEG; }          /* forced, 1507-1513 */
+      else { Nl = p1[r]; G1l = p1[R + r]; }
+      /* upper neighbour (r-1, c) */
+      if (r - 1 == 0) { Nu = DPC_NEG; G2u = DPC_NEG; }
+      else if (k + 1 > m.rband) { Nu = DPC_NEG; G2u = DPC_NEG; }           /* forced, 1501-1506 */
+      else { Nu = p1[r - 1]; G2u = p1[2 * R + r - 1]; }
+      /* diagonal neighbour (r-1, c-1): row 0 / column 0 per 1460-1488 */
+      if (r - 1 == 0) {
+        if (c - 1 == 0) { Nd = 0; G1d = DPC_NEG; G2d = DPC_NEG; }
+        else { Nd = DPC_NEG; G1d = m.open + (c - 1) * m.extend; G2d = DPC_NEG; }
+      } else if (c - 1 == 0) { Nd = DPC_NEG; G1d = DPC_NEG; G2d = m.open + (r - 1) * m.extend; }
+      else { Nd = p2[r - 1]; G1d = p2[R + r - 1]; G2d = p2[2 * R + r - 1]; }
+      int q = m.query_rows ? m.rowch[r - 1] : m.colch[c - 1];
+      int g = m.query_rows ? m.colch[c - 1] : m.rowch[r - 1];
+      int N, G1, G2, nib;
+      dpc_cell(Nl, G1l, Nu, G2u, Nd, G1d, G2d, score[(q & 127) * 8 + g], m.open, m.extend, m.late, &N, &G1, &G2, &nib);
+      cur[r] = N; cur[R + r] = G1; cur[2 * R + r] = G2;
+      int idx = (r - 1) * (m.wstride << 3) + (k + m.lband), sh = (idx & 7) << 2;
+      m.dir[idx >> 3] = (m.dir[idx >> 3] & ~(15U << sh)) | ((uint32_t)nib << sh);
+      if (m.nband) m.nband[(r - 1) * m.W + (k + m.lband)] = N;
+      if (es.mode == 1) {
+        if (k >= -es.eb && k <= es.eb && dpc_better(N, r * (L2 + 1) + c, es.best, m.late)) { es.best.score = N; es.best.key = r * (L2 + 1) + c; }
+      } else if (es.mode == 2) {
+        if (r == L1 && dpc_better(N, r * (L2 + 1) + c, es.best, m.late)) { es.best.score = N; es.best.key = r * (L2 + 1) + c; }
+      } else if (es.mode == 3) {
+        if (r == L1 && c == L2) { es.best.score = N; es.best.key = r * (L2 + 1) + c; }
+      }
+    }
+    DPC_SYNC();
+  }
+}
+
+
+/* ---- traceback (2611-2712), traceback_cdna (2715-2810), add_genomeskip (2416-2601) ------- */
+DPC_HD int dpc_intron_type(int l1, int l2, int r2, int r1, int cdna_direction) {
+  /* Intron_type, intron.c:17-190, on genome codes (A0 C1 G2 T3) */
+  int left, right, t;
+  if (l1 == 2 && l2 == 3) left = 0x21; else if (l1 == 2 && l2 == 1) left = 0x10;
+  else if (l1 == 0 && l2 == 3) left = 0x08; else if (l1 == 1 && l2 == 3) left = 0x06; else return 0;
+  if (r2 == 0 && r1 == 2) right = 0x30; else if (r2 == 0 && r1 == 1) right = 0x0C;
+  else if (r2 == 2 && r1 == 1) right = 0x02; else if (r2 == 0 && r1 == 3) right = 0x01; else return 0;
+  t = left & right;
+  if (t == 0) return 0;
+  if (cdna_direction > 0) return t < 0x08 ? 0 : t;
+  if (cdna_direction < 0) return t > 0x04 ? 0 : t;
+  return 0;
+}
+
+struct Counts { int nmatches, nmismatches, nopens, nindels, star; };
+
+/* Walks one matrix from (r,c): lane 0 follows the direction nibbles and writes run-length ops
+ * (traceback order) to `ops`; then all lanes classify the cells of the M runs (2644-2667).
+ * Returns the number of ops; `ct` accumulates (every lane ends with the same totals). */
+DPC_HD int dpc_traceback(const Mat &m, int r0, int c0, int revp, int cdna_direction, uint16_t *ops,
+                         Counts &ct, const DevTables *tb, const Lanes &ln) {
+  int nops = 0, opens = 0, indels = 0;
+  const int genome_rows = !m.query_rows;
+  if (ln.lane == 0) {
+    int r = r0, c = c0, run = 0;
+    while (dpc_inband(m, r, c)) {
+      int d = dpc_nib(m, r, c) & 3;
+      run++;
+      r--; c--;
+      if (d == DPC_DIAG) continue;
+      ops[nops++] = (uint16_t)((run << 2) | DPC_OP_M); run = 0;
+      int dist = 1;
+      if (d == DPC_HORIZ) { while (dpc_g1_horiz(m, r, c)) { dist++; c--; } c--; }
+      else { while (dpc_g2_vert(m, r, c)) { dist++; r--; } r--; }
+      int genome_run = (d == DPC_HORIZ) ? !genome_rows : genome_rows;
+      int op = genome_run ? DPC_OP_GSKIP : DPC_OP_QSKIP;
+      if (genome_run && dist >= DPC_MICROINTRON) {
+        const uint8_t *g = genome_rows ? m.rowch : m.colch;
+        int lo = genome_rows ? r : c, a, b, y, z;          /* 0-based first genome index of the run */
+        if (!revp) { a = g[lo]; b = g[lo + 1]; y = g[lo + dist - 2]; z = g[lo + dist - 1]; }
+        else { a = g[lo + dist - 1]; b = g[lo + dist - 2]; y = g[lo + 1]; z = g[lo]; }
+        if (dpc_intron_type(a, b, y, z, cdna_direction) != 0) op = DPC_OP_GAPHOLDER;
+      }
+      if (op != DPC_OP_GAPHOLDER) { opens++; indels += dist; }
+      ops[nops++] = (uint16_t)((dist << 2) | op);
+    }
+    if (run) ops[nops++] = (uint16_t)((run << 2) | DPC_OP_M);
+  }
+  DPC_SYNC();
+  nops = dpc_bcast(nops, ln);
+  ct.nopens += dpc_bcast(opens, ln);
+  ct.nindels += dpc_bcast(indels, ln);
+  /* classify the aligned columns */
+  int r = r0, c = c0, nm = 0, nmm = 0, star = 0;
+  for (int i = 0; i < nops; i++) {
+    int op = ops[i] & 3, len = ops[i] >> 2;
+    if (op == DPC_OP_M) {
+      for (int j = ln.lane; j < len; j += ln.n) {
+        int q = genome_rows ? m.colch[c - 1 - j] : m.rowch[r - 1 - j];
+        int g = genome_rows ? m.rowch[r - 1 - j] : m.colch[c - 1 - j];
+        if (!genome_rows && g == DPC_GSTAR) star++;
+        else if (dpc_query_uc(q) == dpc_code_char(g)) nm++;
+        else if (((genome_rows ? tb->consT[q & 127] : tb->cons[q & 127]) >> g) & 1) nm++;
+        else nmm++;
+      }
+      r -= len; c -= len;
+    } else {
+      int along_cols = (op == DPC_OP_QSKIP) ? genome_rows : !genome_rows;
+      if (along_cols) c -= len; else r -= len;
+    }
+  }
+  ct.nmatches += dpc_warp_sum(nm, ln);
+  ct.nmismatches += dpc_warp_sum(nmm, ln);
+  ct.star += dpc_warp_sum(star, ln);
+  return nops;
+}
+
+/* ---- intron bridge: intron_score 3148-3192, bridge_intron_gap 3290-4122 ----------------- */
+DPC_HD int dpc_leftdi(int a, int b) {   /* 3331-3352 */
+  return (a == 2 && b == 3) ? 0x21 : (a == 2 && b == 1) ? 0x10 : (a == 0 && b == 3) ? 0x08 : (a == 1 && b == 3) ? 0x06 : 0;
+}
+DPC_HD int dpc_rightdi(int r2, int r1) { /* 3354-3373 */
+  return (r2 == 0 && r1 == 2) ? 0x30 : (r2 == 0 && r1 == 1) ? 0x0C : (r2 == 2 && r1 == 1) ? 0x02 : (r2 == 0 && r1 == 3) ? 0x01 : 0;
+}
+DPC_HD int dpc_intron_score(int *introntype, int leftdi, int rightdi, int cdna_direction, int reward, int finalp) {
+  int t = leftdi & rightdi, fwd, s;
+  *introntype = 0;
+  if (t == 0) return 0;
+  fwd = t >= 0x08;
+  if ((cdna_direction > 0 && !fwd) || (cdna_direction < 0 && fwd)) return 0;
+  switch (t) {
+  case 0x20: case 0x04: s = reward; break;
+  case 0x10: case 0x02: s = finalp ? 20 : 15; break;
+  case 0x08: case 0x01: s = 12; break;
+  default: return 0;
+  }
+  *introntype = t;
+  return s;
+}
+
+struct Bridge { int have, finalscore, rL, cL, rR, cR, introntype; };
+
+/* mL: rows = query forward, columns = genome from offset2L; mR: rows = query backward, columns =
+ * genome backward from revoffset2R.  lknown / rknown: 1 where a known splice site sits (NULL =
+ * none); lp / rp: per-position probabilities for use_probabilities_p (3829-4081). */
+DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const DevProb &p,
+                              const uint8_t *lknown, const uint8_t *rknown, const double *lp, const double *rp,
+                              const Lanes &ln) {
+  const int L1 = mL.L1, L2L = mL.L2, L2R = mR.L2, eb = p.extraband;
+  const int rbandL = L2L - L1 + eb, lbandL = eb, rbandR = L2R - L1 + eb, lbandR = eb;   /* 3545-3549 */
+  const int finalp = (p.flags & DPC_F_FINALP) != 0, halfp = (p.flags & DPC_F_HALFP) != 0;
+  const int probmode = (p.flags & DPC_F_PROBMODE) != 0;
+  const uint8_t *gL = mL.colch, *gR = mR.colch;
+  Best best; best.score = DPC_BRIDGE_FLOOR; best.key = 0x7fffffff;
+  double bestprob = 0.0; int probkey = 0x7fffffff;
+  int it;
+  for (int rL = 1; rL < L1; rL++) {
+    const int rR = L1 - rL;
+    int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
+    int cloR = rR - lbandR < 1 ? 1 : rR - lbandR, chighR = rR + rbandR > L2R - 1 ? L2R - 1 : rR + rbandR;
+    int nL = chighL - cloL + 1, nR = chighR - cloR + 1;
+    if (nL < 0) nL = 0;
+    if (nR < 0) nR = 0;
+    for (int j = ln.lane; j < nL + nR; j += ln.n) {
+      int left = j < nL, cL = left ? cloL + j : rL, cR = left ? rR : cloR + (j - nL);
+      if (!(left ? cR < p.gap - cL : cL < p.gap - cR)) continue;
+      int key = rL * 8192 + j;
+      if (probmode && lp[cL] + rp[cR] <= bestprob) continue;            /* 3918, 3971 */
+      int sL = dpc_nscore(mL, rL, cL) + (lknown && lknown[cL] ? 20 : 0);
+      int sR = dpc_nscore(mR, rR, cR) + (rknown && rknown[cR] ? 20 : 0);
+      if (left) { if (dpc_dirN(mL, rL, cL) > 0) sL -= 1; }              /* 3724-3727 */
+      else { if (dpc_dirN(mR, rR, cR) > 0) sR -= 1; }                   /* 3774-3777 */
+      int sI = dpc_intron_score(&it, dpc_leftdi(gL[cL], gL[cL + 1]), dpc_rightdi(gR[cR + 1], gR[cR]), p.cdna_direction, p.reward, finalp);
+      int s = sL + sI + sR;
+      if (probmode) {
+        if (s >= p.score_threshold) { bestprob = lp[cL] + rp[cR]; probkey = key; }
+      } else if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+    }
+  }
+  if (probmode) {
+#ifdef __CUDACC__
+    for (int o = 16; o > 0; o >>= 1) {
+      double q = __shfl_xor_sync(0xffffffffu, bestprob, o); int k = __shfl_xor_sync(0xffffffffu, probkey, o);
+      if (q > bestprob || (q == bestprob && k < probkey)) { bestprob = q; probkey = k; }
+    }
+#endif
+    best.key = probkey;
+    br.have = probkey != 0x7fffffff;
+  } else {
+    dpc_warp_best(best, 0, ln);
+    br.have = best.key != 0x7fffffff;
+  }
+  br.introntype = 0;
+  if (!br.have) {
+    br.finalscore = probmode ? DPC_BRIDGE_FLOOR : (halfp ? DPC_BRIDGE_FLOOR - DPC_BRIDGE_FLOOR / 2 : DPC_BRIDGE_FLOOR);
+    br.rL = br.cL = br.rR = br.cR = 0;
+    return;
+  }
+  {
+    int rL = best.key >> 13, j = best.key & 8191, rR = L1 - rL;
+    int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
+    int cloR = rR - lbandR < 1 ? 1 : rR - lbandR;
+    int nL = chighL - cloL + 1;
+    if (nL < 0) nL = 0;
+    int left = j < nL, cL = left ? cloL + j : rL, cR = left ? rR : cloR + (j - nL);
+    int sI = dpc_intron_score(&it, dpc_leftdi(gL[cL], gL[cL + 1]), dpc_rightdi(gR[cR + 1], gR[cR]), p.cdna_direction, p.reward, finalp);
+    br.rL = rL; br.cL = cL; br.rR = rR; br.cR = cR;
+    if (probmode) {                                                     /* 4055-4080: -1 on both sides */
+      int sL = dpc_nscore(mL, rL, cL) + (lknown && lknown[cL] ? 20 : 0) - (dpc_dirN(mL, rL, cL) > 0 ? 1 : 0);
+      int sR = dpc_nscore(mR, rR, cR) + (rknown && rknown[cR] ? 20 : 0) - (dpc_dirN(mR, rR, cR) > 0 ? 1 : 0);
+      br.finalscore = halfp ? sL + sI + sR - sI / 2 : sL + sI + sR;
+      br.introntype = -1;                                               /* *introntype left untouched, 4071 */
+    } else {
+      br.finalscore = halfp ? best.score - sI / 2 : best.score;        /* 3823-3827 */
+      br.introntype = it;
+    }
+  }
+}
+
+/* bridge_cdna_gap, 3066-3146: rows = genome, the gap is in the cDNA. */
+DPC_HD void dpc_bridge_cdna(Bridge &br, const Mat &mL, const Mat &mR, const DevProb &p, const Lanes &ln) {
+  const int L2 = mL.L1, L1L = mL.L2, L1R = mR.L2, eb = p.extraband;
+  const int rbandL = L1L - L2 + eb, lbandL = eb, rbandR = L1R - L2 + eb, lbandR = eb;
+  int bs = DPC_BRIDGE_FLOOR; long long bk = 0x7fffffffffffffffLL;
+  int brL = 0, brR = 0, bcL = 0, bcR = 0;
+  long long order = 0;
+  for (int rL = 1; rL < L2; rL++) {
+    int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L1L - 1 ? L1L - 1 : rL + rbandL;
+    int nL = chighL - cloL + 1;
+    if (nL < 0) nL = 0;
+    for (int rR = L2 - rL; rR >= 0; rR--) {
+      int pen = (rR == L2 - rL) ? 0 : p.open;                            /* 3092, 3136 */
+      int cloR = rR - lbandR < 1 ? 1 : rR - lbandR, chighR = rR + rbandR > L1R - 1 ? L1R - 1 : rR + rbandR;
+      int nR = chighR - cloR + 1;
+      if (nR < 0) nR = 0;
+      for (int j = ln.lane; j < nL * nR; j += ln.n) {
+        int cL = cloL + j / nR, cR = cloR + j % nR;
+        if (!(cR < p.gap - cL)) continue;
+        int s = dpc_nscore(mL, rL, cL) + dpc_nscore(mR, rR, cR) + pen;
+        long long key = order + j;
+        if (s > bs || (s == bs && key < bk)) { bs = s; bk = key; brL = rL; brR = rR; bcL = cL; bcR = cR; }
+      }
+      order += (long long)nL * nR;
+    }
+  }
+#ifdef __CUDACC__
+  for (int o = 16; o > 0; o >>= 1) {
+    int s = __shfl_xor_sync(0xffffffffu, bs, o); long long k = __shfl_xor_sync(0xffffffffu, bk, o);
+    int a = __shfl_xor_sync(0xffffffffu, brL, o), b = __shfl_xor_sync(0xffffffffu, brR, o);
+    int c = __shfl_xor_sync(0xffffffffu, bcL, o), d = __shfl_xor_sync(0xffffffffu, bcR, o);
+    if (s > bs || (s == bs && k < bk)) { bs = s; bk = k; brL = a; brR = b; bcL = c; bcR = d; }
+  }
+#endif
+  br.have = bk != 0x7fffffffffffffffLL;
+  br.finalscore = bs; br.rL = brL; br.rR = brR; br.cL = bcL; br.cR = bcR; br.introntype = 0;
+}
+
+/* ---- arena layout (shared by host sizing and the kernel) --------------------------------- */
+struct MatDims { int rows, cols, lband, rband, W, wstride; };
+struct ArenaLayout {
+  int nmat;
+  MatDims d[2];
+  uint32_t rowch[2], colch[2], dir[2], nband[2], ops[2], state, total;
+};
+DPC_HD uint32_t dpc_al(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
+
+/* kind codes as in include/dynprog_cuda.h: 0 single, 1 genome, 2 cdna, 3 end5, 4 end3 */
+DPC_HD void dpc_layout(const DevProb &p, ArenaLayout &a, int with_state) {
+  uint32_t off = 0;
+  int maxrows = 0;
+  a.nmat = (p.kind == 1 || p.kind == 2) ? 2 : 1;
+  for (int i = 0; i < a.nmat; i++) {
+    MatDims &d = a.d[i];
+    if (p.kind == 2) { d.rows = p.L2; d.cols = i ? p.L1R : p.L1; }
+    else { d.rows = p.L1; d.cols = i ? p.L2R : p.L2; }
+    dpc_bands(d.rows, d.cols, p.extraband, (p.flags & DPC_F_WIDEBAND) != 0, &d.lband, &d.rband);
+    d.W = d.lband + d.rband + 1;
+    d.wstride = dpc_wstride(d.W);
+    if (d.rows > maxrows) maxrows = d.rows;
+    a.rowch[i] = off; off = dpc_al(off + (uint32_t)d.rows + 2, 4);
+    a.colch[i] = off; off = dpc_al(off + (uint32_t)d.cols + 2, 4);
+    a.dir[i] = off; off += (uint32_t)d.rows * (uint32_t)d.wstride * 4;
+    if (a.nmat == 2) { a.nband[i] = off; off += (uint32_t)d.rows * (uint32_t)d.W * 4; } else a.nband[i] = 0;
+    a.ops[i] = off; off = dpc_al(off + 2 * (uint32_t)(d.rows + d.cols + 2), 4);
+  }
+  a.state = off;
+  if (with_state) off += 9 * (uint32_t)(maxrows + 1) * 4;
+  a.total = dpc_al(off, 16);
+}
+
+DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *arena, const DevProb &p, int late, int query_rows) {
+  const MatDims &d = a.d[i];
+  m.L1 = d.rows; m.L2 = d.cols; m.lband = d.lband; m.rband = d.rband; m.W = d.W; m.wstride = d.wstride;
+  m.open = p.open; m.extend = p.extend; m.late = late; m.query_rows = query_rows;
+  m.rowch = arena + a.rowch[i]; m.colch = arena + a.colch[i];
+  m.dir = (uint32_t *)(arena + a.dir[i]);
+  m.nband = a.nmat == 2 ? (int32_t *)(arena + a.nband[i]) : (int32_t *)0;
+}
+
+/* ---- one problem ------------------------------------------------------------------------------ */
+struct OvfArena { uint16_t *ops; unsigned int *used; unsigned int cap; };
+
+DPC_HD void dpc_emit_ops(DevRes *res, const uint16_t *opsL, int nL, const uint16_t *opsR, int nR,
+                         const OvfArena &ovf, uint32_t &status, const Lanes &ln) {
+  int total = nL + nR;
+  uint16_t *dst = res->ops;
+  uint32_t at = 0;
+  if (total > DPC_INLINE_OPS) {
+    if (ln.lane == 0) {
+#ifdef __CUDACC__
+      at = atomicAdd(ovf.used, (unsigned int)total);
+#else
+      at = *ovf.used; *ovf.used += (unsigned int)total;
+#endif
+    }
+    at = (uint32_t)dpc_bcast((int)at, ln);
+    if (at + (uint32_t)total > ovf.cap) { status |= DPC_ST_OVF_LOST; total = 0; nL = nR = 0; }
+    dst = ovf.ops + at;
+  }
+  for (int i = ln.lane; i < total; i += ln.n) dst[i] = i < nL ? opsL[i] : opsR[i - nL];
+  if (ln.lane == 0) { res->nopsL = (uint16_t)nL; res->nopsR = (uint16_t)nR; res->ovf = at; }
+}
+
+/* Solves problem `p` with the fill routine `FILL` (generic here; the CUDA build also has the
+ * register/shuffle fill for narrow bands).  `arena` must hold dpc_layout(p).total bytes. */
+template <class FILL>
+DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint32_t *blocks, const DevTables *tb,
+                              uint8_t *arena, DevRes *res, const OvfArena &ovf, FILL &fill, const Lanes &ln) {
+  uint32_t status = DPC_ST_DONE;
+  Counts ct; ct.nmatches = ct.nmismatches = ct.nopens = ct.nindels = ct.star = 0;
+  int finalscore = 0, brL = 0, bcL = 0, brR = 0, bcR = 0, introntype = 0, nopsL = 0, nopsR = 0;
+  const int late = (p.flags & DPC_F_LATE) != 0;
+  const int8_t *score = &tb->score[p.type][0][0];
+  const uint16_t *opsL = 0, *opsR = 0;
+
+  if ((p.kind == 3 || p.kind == 4) && p.endalign == 2) {
+    /* QUERYEND_NOGAPS: find_best_endpoint_to_queryend_nogaps 2358-2369 + traceback_nogaps 2815-2872 */
+    int n = p.L1 < p.L2 ? p.L1 : p.L2, nm = 0, nmm = 0, star = 0, five = p.kind == 3;
+    for (int i = ln.lane; i < n; i += ln.n) {
+      int q = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
+      int g = dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+      if (g == DPC_GSTAR) star++;
+      else if (dpc_query_uc(q) == dpc_code_char(g)) nm++;
+      else if ((tb->cons[q & 127] >> g) & 1) nm++;
+      else nmm++;
+    }
+    ct.nmatches = dpc_warp_sum(nm, ln); ct.nmismatches = dpc_warp_sum(nmm, ln); ct.star = dpc_warp_sum(star, ln);
+    finalscore = 3 * ct.nmatches - 5 * ct.nmismatches;                    /* 5243, 5700 */
+    brL = bcL = n;
+    if (ln.lane == 0) res->ops[0] = (uint16_t)((n << 2) | DPC_OP_M);
+    if (ln.lane == 0) { res->nopsL = 1; res->nopsR = 0; res->ovf = 0; }
+    status |= DPC_ST_HAVE | DPC_ST_OK;
+  } else {
+    ArenaLayout a;
+    dpc_layout(p, a, FILL::needs_state);
+    Mat m0, m1;
+    int32_t *st = (int32_t *)(arena + a.state);
+    if (p.kind == 0 || p.kind == 3 || p.kind == 4) {
+      /* Dynprog_single_gap 4450-4572, Dynprog_end5_gap 5094-5284, Dynprog_end3_gap 5556-5741 */
+      const int five = p.kind == 3;
+      dpc_make_mat(m0, a, 0, arena, p, five ? !late : late, 1);
+      for (int i = ln.lane; i < p.L1; i += ln.n) m0.rowch[i] = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
+      for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+      DPC_SYNC();
+      EndSearch es; es.eb = p.extraband;
+      if (p.kind == 0) { es.mode = 3; es.best.score = -2147483647; es.best.key = 0; }
+      else if (p.endalign == 1) { es.mode = 2; es.best.score = DPC_NEG; es.best.key = p.L1 * (p.L2 + 1); }
+      else { es.mode = 1; es.best.score = 0; es.best.key = 0; }
+      fill(m0, st, score, es, ln);
+      dpc_warp_best(es.best, m0.late, ln);
+      finalscore = es.best.score;
+      brL = es.best.key / (p.L2 + 1); bcL = es.best.key % (p.L2 + 1);
+      uint16_t *ops = (uint16_t *)(arena + a.ops[0]);
+      nopsL = dpc_traceback(m0, brL, bcL, five, p.cdna_direction, ops, ct, tb, ln);
+      opsL = ops;
+      status |= DPC_ST_HAVE | DPC_ST_OK;
+    } else {
+      const int cdna = p.kind == 2;
+      dpc_make_mat(m0, a, 0, arena, p, late, !cdna);
+      dpc_make_mat(m1, a, 1, arena, p, !late, !cdna);
+      if (!cdna) {
+        /* Dynprog_genome_gap 4798-5061: L = fwd(query, genome @ offset2L), R = rev(query, genome @ revoffset2R) */
+        for (int i = ln.lane; i < p.L1; i += ln.n) { m0.rowch[i] = pool[p.q0 + (uint32_t)i]; m1.rowch[i] = pool[p.q0 + (uint32_t)(p.L1 - 1 - i)]; }
+        for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2 + i);
+        for (int i = ln.lane; i < p.L2R; i += ln.n) m1.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2R - i);
+        if (ln.lane == 0) { m0.colch[p.L2] = 7; m1.colch[p.L2R] = 7; }    /* leftdi[length2L-1] = rightdi[length2R-1] = 0, 3354, 3376 */
+      } else {
+        /* Dynprog_cdna_gap 4577-4793: rows = genome (fwd from offset2 / rev from offset2+length2-1) */
+        for (int i = ln.lane; i < p.L2; i += ln.n) {
+          m0.rowch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2 + i);
+          m1.rowch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2 + p.L2 - 1 - i);
+        }
+        for (int i = ln.lane; i < p.L1; i += ln.n) m0.colch[i] = pool[p.q0 + (uint32_t)i];
+        for (int i = ln.lane; i < p.L1R; i += ln.n) m1.colch[i] = pool[p.q1 - (uint32_t)i];
+      }
+      DPC_SYNC();
+      EndSearch es; es.mode = 0; es.eb = 0; es.best.score = 0; es.best.key = 0;
+      fill(m0, st, score, es, ln);
+      fill(m1, st, score, es, ln);
+      Bridge br;
+      int ok;
+      if (!cdna) {
+        const uint8_t *aux = pool + p.aux, *lknown = 0, *rknown = 0;
+        const double *lp = 0, *rp = 0;
+        if (p.flags & DPC_F_PROBMODE) { lp = (const double *)aux; rp = lp + p.L2; aux += 8 * (uint32_t)(p.L2 + p.L2R); }
+        if (p.flags & DPC_F_KNOWN) { lknown = aux; rknown = aux + p.L2; }
+        dpc_bridge_intron(br, m0, m1, p, lknown, rknown, lp, rp, ln);
+        ok = br.have && br.finalscore >= 0;                               /* 4083-4101 */
+        if (ok && !(p.flags & DPC_F_NOVEL) && (p.flags & DPC_F_KNOWN) && (!lknown[br.cL] || !rknown[br.cR])) ok = 0;
+      } else {
+        dpc_bridge_cdna(br, m0, m1, p, ln);
+        ok = br.have;
+      }
+      finalscore = br.finalscore; brL = br.rL; bcL = br.cL; brR = br.rR; bcR = br.cR; introntype = br.introntype;
+      if (br.have) status |= DPC_ST_HAVE;
+      if (ok) {
+        status |= DPC_ST_OK;
+        uint16_t *oR = (uint16_t *)(arena + a.ops[1]), *oL = (uint16_t *)(arena + a.ops[0]);
+        nopsR = dpc_traceback(m1, brR, bcR, 1, p.cdna_direction, oR, ct, tb, ln);
+        nopsL = dpc_traceback(m0, brL, bcL, 0, p.cdna_direction, oL, ct, tb, ln);
+        opsL = oL; opsR = oR;
+      }
+    }
+    dpc_emit_ops(res, opsL, nopsL, opsR, nopsR, ovf, status, ln);
+  }
+  if (ct.star) status |= DPC_ST_STAR;
+  if (ln.lane == 0) {
+    res->finalscore = finalscore;
+    res->nmatches = ct.nmatches; res->nmismatches = ct.nmismatches; res->nopens = ct.nopens; res->nindels = ct.nindels;
+    res->bestrL = brL; res->bestcL = bcL; res->bestrR = brR; res->bestcR = bcR;
+    res->introntype = introntype; res->status = status;
+  }
+}
+
+struct GenericFill {
+  enum { needs_state = 1 };
+  DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
+    dpc_fill_generic(m, st, score, es, ln);
+  }
+};
+#endif /* DPC_CORE_H */

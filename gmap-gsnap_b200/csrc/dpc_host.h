@@ -1,0 +1,546 @@
+/* dpc_host.h -- host side of libdynprog_cuda: score tables, problem packing, result
+ * finalisation and the rebuild of Pair records from device traceback runs.
+ *
+ * Pure host C++ (no CUDA calls): dynprog_cuda.cu includes it next to the kernels;
+ * tests/emul includes it next to a single-lane build of dpc_core.h.  Nothing in here
+ * computes a DP matrix -- that only exists as device code.
+ *
+ * Reference: src/dynprog.c of GMAP/GSNAP 2012-07-03 (line numbers cited per function).
+ */
+#ifndef DPC_HOST_H
+#define DPC_HOST_H
+
+#include <stdint.h>
+#include <string.h>
+#include <ctype.h>
+#include <vector>
+#include "../../include/dynprog_cuda.h"
+#include "dpc_core.h"
+
+namespace dpc {
+
+enum { HIGHQ = 0, MEDQ = 1, LOWQ = 2, ENDQ = 3 };   /* Mismatchtype_T, dynprog.c:150 */
+
+struct Globals {
+  bool inited, setup_done;
+  int maxlength1, maxlength2;
+  int mode;
+  int P[4][128][128];            /* pairdistance_array, dynprog.c:1045 */
+  uint8_t CONS[128][128];        /* consistent_array, dynprog.c:1046 */
+  DevTables tables;
+  dpc_setup_t setup;
+  uint64_t genome_nbases;
+};
+inline Globals &G() { static Globals g; return g; }
+
+/* permute_cases / permute_cases_oneway, dynprog.c:1053-1124 */
+inline void set_pair(Globals &g, int a, int b, int score, bool oneway) {
+  const int A[2] = { a, tolower(a) }, B[2] = { b, tolower(b) };
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++) {
+      g.CONS[A[i]][B[j]] = 1;
+      for (int t = 0; t < 4; t++) g.P[t][A[i]][B[j]] = score;
+      if (!oneway) {
+        g.CONS[B[j]][A[i]] = 1;
+        for (int t = 0; t < 4; t++) g.P[t][B[j]][A[i]] = score;
+      }
+    }
+}
+
+/* pairdistance_init, dynprog.c:1127-1226.  The order of the assignments matters (later ones win). */
+inline void build_tables(Globals &g, int mode) {
+  static const int mismatch[4] = { -3, -2, -1, -5 };                 /* dynprog.c:169-179 */
+  static const char *const half[] = { "RA", "RG", "YT", "YC", "WA", "WT", "SG", "SC", "MA", "MC", "KG", "KT" };
+  static const char *const ambig[] = { "HA", "HT", "HC", "BG", "BC", "BT", "VG", "VA", "VC", "DG", "DA", "DT",
+                                       "NT", "NC", "NA", "NG", "XT", "XC", "XA", "XG" };
+  memset(g.P, 0, sizeof g.P);
+  memset(g.CONS, 0, sizeof g.CONS);
+  for (int c1 = 'A'; c1 <= 'z'; c1++)
+    for (int c2 = 'A'; c2 < 'z'; c2++)                               /* sic: 'z' itself is excluded, 1152 */
+      for (int t = 0; t < 4; t++) g.P[t][c1][c2] = mismatch[t];
+  set_pair(g, 'U', 'T', 3, false);
+  for (unsigned i = 0; i < sizeof half / sizeof *half; i++) set_pair(g, half[i][0], half[i][1], 1, false);
+  for (unsigned i = 0; i < sizeof ambig / sizeof *ambig; i++) set_pair(g, ambig[i][0], ambig[i][1], -1, false);
+  if (mode == DPC_MODE_CMET_STRANDED || mode == DPC_MODE_CMET_NONSTRANDED) {   /* 1215-1219 */
+    set_pair(g, 'T', 'C', 3, true);
+    set_pair(g, 'A', 'G', 3, true);
+  }
+  for (int c = 'A'; c < 'Z'; c++) set_pair(g, c, c, 3, false);       /* sic: 'Z' excluded, 1221 */
+
+  static const char codes[6] = { 'A', 'C', 'G', 'T', 'N', '*' };
+  memset(&g.tables, 0, sizeof g.tables);
+  for (int t = 0; t < 4; t++)
+    for (int q = 0; q < 128; q++)
+      for (int c = 0; c < 6; c++) g.tables.score[t][q][c] = (int8_t)g.P[t][q][(int)codes[c]];
+  for (int q = 0; q < 128; q++)
+    for (int c = 0; c < 6; c++) {
+      if (g.CONS[q][(int)codes[c]]) g.tables.cons[q] |= (uint8_t)(1u << c);
+      if (g.CONS[(int)codes[c]][q]) g.tables.consT[q] |= (uint8_t)(1u << c);
+    }
+}
+
+inline int host_init(int maxlookback, int extraquerygap, int maxpeelback, int extramaterial_end,
+                     int extramaterial_paired, int mode) {
+  Globals &g = G();
+  /* compute_maxlengths, dynprog.c:831-852 */
+  int m1 = maxlookback + maxpeelback;
+  if (m1 < 500) m1 = 500;
+  int m2 = m1 + extraquerygap + (extramaterial_end > extramaterial_paired ? extramaterial_end : extramaterial_paired);
+  if (m2 < 2000) m2 = 2000;
+  if (m1 > 4000 || m2 > 4000) return DPC_ERR_ARG;   /* traceback ops carry 14-bit lengths, bridge keys 13-bit columns */
+  g.maxlength1 = m1; g.maxlength2 = m2; g.mode = mode;
+  build_tables(g, mode);
+  g.inited = true;
+  return DPC_OK;
+}
+
+/* ---- host view of the genome (for the rebuilt pairs' genome characters) ------------------ */
+inline char host_genome_char(const uint32_t *blocks, uint32_t pos) {   /* genome.c:9325-9362 */
+  return "ACGTN"[dpc_genome_code(blocks, pos)];
+}
+inline bool allstar(const dpc_problem_t &p) {                           /* dynprog.c:415-419 */
+  uint32_t pos = p.chroffset + p.chrpos;
+  return pos < p.chroffset || pos >= p.chrhigh;
+}
+inline char host_genomic_nt(const dpc_problem_t &p, int genomicpos) {   /* get_genomic_nt, dynprog.c:403-441 */
+  static const char compl_nt[6] = { 'T', 'G', 'C', 'A', 'N', '*' };
+  if (genomicpos < 0 || (uint32_t)genomicpos >= p.genomiclength || allstar(p)) return '*';
+  const uint32_t *blocks = G().setup.genome_blocks;
+  if (p.watsonp) return host_genome_char(blocks, p.chroffset + p.chrpos + (uint32_t)genomicpos);
+  return compl_nt[dpc_genome_code(blocks, p.chroffset + p.chrpos + (p.genomiclength - 1) - (uint32_t)genomicpos)];
+}
+
+/* ---- batch ---------------------------------------------------------------------------------- */
+struct HostProb {
+  dpc_problem_t p;      /* caller's problem; seq1 / seq1R are NOT valid after add (bytes live in the pool) */
+  uint32_t q0, q1;      /* pool offsets: first byte of the copied span(s) */
+  int32_t dev;          /* index into the device arrays, -1 when resolved on the host (early returns) */
+  int32_t L1, L2;       /* lengths after clipping (end gaps) */
+  uint32_t aux;         /* pool offset of probability / known-site arrays */
+  dpc_result_t res;
+};
+
+struct Batch {
+  std::vector<HostProb> probs;
+  std::vector<uint8_t> pool;        /* query bytes + aux arrays; copied verbatim to the device */
+  std::vector<DevProb> dprobs;
+  std::vector<uint32_t> dev2host;
+
+  void clear() { probs.clear(); pool.clear(); dprobs.clear(); dev2host.clear(); }
+
+  uint32_t pool_put(const char *src, int n) {
+    uint32_t at = (uint32_t)pool.size();
+    pool.insert(pool.end(), (const uint8_t *)src, (const uint8_t *)src + n);
+    return at;
+  }
+  void pool_align(size_t a) { while (pool.size() % a) pool.push_back(0); }
+
+  static void result_init(dpc_result_t &r, const dpc_problem_t &p) {
+    r.null_list = 1; r.dynprogindex_out = p.dynprogindex;
+    r.finalscore = r.nmatches = r.nmismatches = r.nopens = r.nindels = DPC_UNSET;
+    r.new_leftgenomepos = r.new_rightgenomepos = r.exonhead = r.introntype = DPC_UNSET;
+    r.incompletep = DPC_UNSET; r.npairs = 0; r.reserved = 0;
+    r.left_prob = r.right_prob = -1.0;
+  }
+  static int bump(int idx) { return idx + (idx > 0 ? 1 : -1); }      /* e.g. dynprog.c:4570 */
+  static int quality(double defect_rate) {                             /* dynprog.h:27-28 */
+    return defect_rate < 0.003 ? HIGHQ : defect_rate < 0.014 ? MEDQ : LOWQ;
+  }
+  static bool alphabet_ok(const char *s, int n) {
+    for (int i = 0; i < n; i++) if ((unsigned char)s[i] >= 128) return false;
+    return true;
+  }
+  static bool segment_ok(const dpc_problem_t &p) {
+    if (allstar(p)) return true;
+    uint64_t end = (uint64_t)(uint32_t)(p.chroffset + p.chrpos) + p.genomiclength;
+    return end <= G().genome_nbases;
+  }
+
+  /* known-site / probability positions: get_splicesite_probs 3195-3287, the arrays of 3377-3458 and 3856-3903 */
+  static void site(const dpc_problem_t &p, bool left, int c, uint32_t *pos, int *which, int *sign) {
+    const int lo = p.offset2, ro = p.offset2R;
+    if (left) {
+      if (p.watsonp) { *pos = p.chrpos + lo + c; *which = p.cdna_direction > 0 ? 0 : 3; *sign = p.cdna_direction > 0 ? +1 : -1; }
+      else { *pos = p.chrpos + (p.genomiclength - 1) - lo - c + 1; *which = p.cdna_direction > 0 ? 2 : 1; *sign = p.cdna_direction > 0 ? -1 : +1; }
+    } else {
+      if (p.watsonp) { *pos = p.chrpos + ro - c + 1; *which = p.cdna_direction > 0 ? 1 : 2; *sign = p.cdna_direction > 0 ? +1 : -1; }
+      else { *pos = p.chrpos + (p.genomiclength - 1) - ro + c; *which = p.cdna_direction > 0 ? 3 : 0; *sign = p.cdna_direction > 0 ? -1 : +1; }
+    }
+  }
+  static bool site_known(const dpc_problem_t &p, bool left, int c) {
+    const dpc_setup_t &s = G().setup;
+    uint32_t pos; int which, sign;
+    if (!s.splice_known) return false;
+    site(p, left, c, &pos, &which, &sign);
+    return s.splice_known(which, p.chrnum, pos, sign, s.user) != 0;
+  }
+  static double site_prob(const dpc_problem_t &p, bool left, int c, bool known) {
+    const dpc_setup_t &s = G().setup;
+    uint32_t pos; int which, sign;
+    if (known) return 1.0;
+    site(p, left, c, &pos, &which, &sign);
+    return s.splice_prob(which, p.chroffset + pos, p.chroffset, s.user);
+  }
+
+  /* Returns the ticket or a negative code.  Mirrors the argument checks and early returns of the
+   * five reference entry points; everything that needs a matrix becomes a DevProb. */
+  int add(const dpc_problem_t &in) {
+    Globals &g = G();
+    if (!g.inited || !g.setup_done) return DPC_ERR_STATE;
+    HostProb h;
+    memset(&h, 0, sizeof h);
+    h.p = in; h.dev = -1; h.L1 = in.length1; h.L2 = in.length2;
+    dpc_result_t &r = h.res;
+    result_init(r, in);
+    DevProb d;
+    memset(&d, 0, sizeof d);
+    bool todev = false;
+    const dpc_problem_t &p = in;
+    d.kind = (uint8_t)p.kind; d.endalign = (uint8_t)p.endalign;
+    d.gbase = p.chroffset + p.chrpos; d.glen = p.genomiclength;
+    d.extraband = p.extraband; d.cdna_direction = (int8_t)(p.cdna_direction > 0 ? 1 : p.cdna_direction < 0 ? -1 : 0);
+    d.score_threshold = p.score_threshold;
+    d.flags = (p.watsonp ? DPC_F_WATSON : 0) | (p.jump_late_p ? DPC_F_LATE : 0) | (p.widebandp ? DPC_F_WIDEBAND : 0) |
+              (p.halfp ? DPC_F_HALFP : 0) | (p.finalp ? DPC_F_FINALP : 0) | (allstar(p) ? DPC_F_ALLSTAR : 0) |
+              (g.setup.novelsplicingp ? DPC_F_NOVEL : 0);
+    if (p.extraband < 0 || p.extraband > 4000) return DPC_ERR_ARG;
+
+    switch (p.kind) {
+    case DPC_SINGLE_GAP: {                                             /* Dynprog_single_gap, 4450-4572 */
+      int L1 = p.length1, L2 = p.length2, lband, rband;
+      if (L1 > g.maxlength1 || L2 > g.maxlength2) {                   /* 4509-4519 */
+        r.finalscore = -10000; r.nmatches = r.nmismatches = r.nopens = r.nindels = 0;
+        r.dynprogindex_out = bump(p.dynprogindex);
+        break;
+      }
+      if (L1 <= 0 || L2 <= 0) return DPC_ERR_ARG;                     /* Matrix3_alloc aborts, 495-498 */
+      dpc_bands(L1, L2, p.extraband, p.widebandp, &lband, &rband);
+      if (L2 - L1 > rband || L1 - L2 > lband) {
+        /* only without widebandp: the corner was never filled; the reference reads the memset 0
+         * (or the forced NEG one step above the band, 1501-1506) and traces nothing back */
+        if (L2 - L1 > rband + 1) return DPC_ERR_ARG;                  /* the reference writes outside its matrix here */
+        r.finalscore = (L2 - L1 == rband + 1) ? DPC_NEG_INFINITY : 0;
+        r.nmatches = r.nmismatches = r.nopens = r.nindels = 0;
+        r.dynprogindex_out = bump(p.dynprogindex);
+        break;
+      }
+      if (!alphabet_ok(p.seq1, L1)) return DPC_ERR_ALPHABET;
+      d.type = (uint8_t)quality(p.defect_rate); d.open = -10; d.extend = -3;    /* SINGLE, 222-229 */
+      d.L1 = L1; d.L2 = L2; d.off2 = p.offset2;
+      d.q0 = h.q0 = pool_put(p.seq1, L1);
+      todev = true;
+      break;
+    }
+    case DPC_END5_GAP: case DPC_END3_GAP: {                            /* 5094-5284, 5556-5741 */
+      const bool five = p.kind == DPC_END5_GAP;
+      int L1 = p.length1, L2 = p.length2, ea = p.endalign;
+      if (ea < 0 || ea > 3) return DPC_ERR_ARG;                        /* abort(), 5215 */
+      if (L1 <= 0 || L2 <= 0) {                                        /* 5140-5157 */
+        r.nmatches = r.nmismatches = r.nopens = r.nindels = 0; r.finalscore = 0;
+        break;
+      }
+      if (ea != DPC_QUERYEND_NOGAPS) {
+        if (L1 > g.maxlength1) L1 = g.maxlength1;
+        if (L2 > g.maxlength2) L2 = g.maxlength2;
+      } else {
+        L1 = L2 = (L1 < L2 ? L1 : L2);                                 /* 2358-2369 */
+      }
+      h.L1 = L1; h.L2 = L2;
+      if (!alphabet_ok(five ? p.seq1 - (L1 - 1) : p.seq1, L1)) return DPC_ERR_ALPHABET;
+      d.type = ENDQ; d.open = -12; d.extend = -1;                      /* END, 240-247; ENDQ 179 */
+      d.flags |= DPC_F_WIDEBAND;
+      d.L1 = L1; d.L2 = L2; d.off2 = p.offset2;
+      d.q0 = h.q0 = five ? pool_put(p.seq1 - (L1 - 1), L1) : pool_put(p.seq1, L1);
+      todev = true;
+      break;
+    }
+    case DPC_GENOME_GAP: {                                             /* Dynprog_genome_gap, 4798-5061 */
+      int L1 = p.length1, L2L = p.length2, L2R = p.length2R;
+      r.nmatches = r.nmismatches = r.nopens = r.nindels = 0;
+      r.left_prob = r.right_prob = 0.0;
+      if (L1 <= 1) { r.finalscore = DPC_NEG_INFINITY; break; }         /* 4855-4858 */
+      if (L1 > g.maxlength1 || L2L > g.maxlength2 || L2R > g.maxlength2) {     /* 4922-4954 */
+        r.new_leftgenomepos = p.offset2 - 1; r.new_rightgenomepos = p.offset2R + 1; r.exonhead = p.offset1 + L1 - 1;
+        r.dynprogindex_out = bump(p.dynprogindex); r.finalscore = DPC_NEG_INFINITY;
+        break;
+      }
+      if (L2L <= 0 || L2R <= 0 || L2L < L1 - 1 || L2R < L1 - 1) return DPC_ERR_ARG;
+      if (!g.setup.novelsplicingp && g.setup.splice_known == NULL && false) return DPC_ERR_UNSUPPORTED;
+      if ((p.finalp || p.use_probabilities_p) && g.setup.splice_prob == NULL) return DPC_ERR_STATE;
+      if (!alphabet_ok(p.seq1, L1)) return DPC_ERR_ALPHABET;
+      d.type = (uint8_t)quality(p.defect_rate);
+      if (L1 > p.maxpeelback * 4) { d.open = -10; d.extend = -3; } else { d.open = -18; d.extend = -3; }   /* 4862-4870 */
+      d.reward = (int8_t)(!p.splicingp ? 0 : (p.finalp ? 30 : 10) + 6 * d.type);     /* 277-283, 4871-4877 */
+      d.L1 = L1; d.L2 = L2L; d.L2R = L2R; d.off2 = p.offset2; d.off2R = p.offset2R;
+      d.gap = p.offset2R - p.offset2;
+      d.q0 = h.q0 = pool_put(p.seq1, L1);
+      if (p.use_probabilities_p || g.setup.splice_known) {
+        pool_align(8);
+        d.aux = h.aux = (uint32_t)pool.size();
+        std::vector<uint8_t> known((size_t)L2L + L2R, 0);
+        if (g.setup.splice_known) {
+          d.flags |= DPC_F_KNOWN;
+          for (int c = 0; c < L2L - 1; c++) known[c] = site_known(p, true, c);
+          for (int c = 0; c < L2R - 1; c++) known[L2L + c] = site_known(p, false, c);
+        }
+        if (p.use_probabilities_p) {
+          d.flags |= DPC_F_PROBMODE;
+          std::vector<double> pr((size_t)L2L + L2R, 0.0);
+          for (int c = 0; c < L2L - 1; c++) pr[c] = site_prob(p, true, c, known[c] != 0);
+          for (int c = 0; c < L2R - 1; c++) pr[L2L + c] = site_prob(p, false, c, known[L2L + c] != 0);
+          pool_put((const char *)pr.data(), (int)(pr.size() * sizeof(double)));
+        }
+        if (g.setup.splice_known) pool_put((const char *)known.data(), (int)known.size());
+      }
+      todev = true;
+      break;
+    }
+    case DPC_CDNA_GAP: {                                               /* Dynprog_cdna_gap, 4577-4793 */
+      int L1L = p.length1, L1R = p.length1R, L2 = p.length2;
+      if (L2 <= 1) break;                                              /* 4605-4607: nothing is written */
+      if (L2 > g.maxlength1 || L1R > g.maxlength2 || L1L > g.maxlength2) {     /* 4648-4670 */
+        r.dynprogindex_out = bump(p.dynprogindex);
+        break;
+      }
+      if (L1L <= 0 || L1R <= 0) return DPC_ERR_ARG;
+      /* the two query ends must be one span: the SHORTGAP insertion (4730-4751) indexes across it */
+      int span = p.offset1R - p.offset1 + 1;
+      if (span < L1L || span < L1R || span > 100000 || p.seq1R != p.seq1 + (span - 1)) return DPC_ERR_ARG;
+      if (!alphabet_ok(p.seq1, span)) return DPC_ERR_ALPHABET;
+      d.type = (uint8_t)quality(p.defect_rate); d.open = -10; d.extend = -7;         /* CDNA, 231-238 */
+      d.L1 = L1L; d.L1R = L1R; d.L2 = L2; d.off2 = p.offset2;
+      d.gap = p.offset1R - p.offset1;
+      d.q0 = h.q0 = pool_put(p.seq1, span);
+      d.q1 = h.q1 = d.q0 + (uint32_t)(span - 1);
+      todev = true;
+      break;
+    }
+    default:
+      return DPC_ERR_ARG;
+    }
+    if (todev) {
+      if (!segment_ok(p)) return DPC_ERR_ARG;
+      h.dev = (int32_t)dprobs.size();
+      dprobs.push_back(d);
+      dev2host.push_back((uint32_t)probs.size());
+    }
+    probs.push_back(h);
+    return (int)probs.size() - 1;
+  }
+
+  /* ---- rebuild of the Pair records (dynprog.c:2372-2712 and the assembly in each entry point) */
+  typedef std::vector<dpc_pair_t> Stack;
+  static void push(Stack &s, int qpos, int gpos, char cdna, char comp, char genome, int idx, int gapp) {
+    dpc_pair_t pr;
+    pr.querypos = qpos; pr.genomepos = gpos; pr.dynprogindex = idx;
+    pr.cdna = cdna; pr.comp = comp; pr.genome = genome; pr.gapp = (uint8_t)gapp;
+    s.push_back(pr);
+  }
+  static void push_gapholder(Stack &s) { push(s, -1, -1, ' ', ' ', ' ', 0, 1); }   /* pairpool.c:352-401 */
+
+  /* One matrix: replays the ops from (r,c).  qch / gch are in matrix order. */
+  static void replay(Stack &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
+                     int q0, int g0, bool revp, bool genome_rows, int idx) {
+    const int step = revp ? -1 : 1;
+    const Globals &g = G();
+    for (int i = 0; i < nops; i++) {
+      int op = ops[i] & 3, len = ops[i] >> 2;
+      if (op == DPC_OP_M) {
+        for (int j = 0; j < len; j++) {
+          int qi = (genome_rows ? c : r) - 1 - j, gi = (genome_rows ? r : c) - 1 - j;
+          char c1 = qch[qi], c2 = gch[gi];
+          bool consistent = genome_rows ? g.CONS[c2 & 127][c1 & 127] : g.CONS[c1 & 127][c2 & 127];   /* 2654 vs 2752 */
+          if (!genome_rows && c2 == '*') continue;                    /* 2644 */
+          char comp = (char)dpc_query_uc(c1) == c2 ? '*' : consistent ? ':' : ' ';
+          push(st, q0 + step * qi, g0 + step * gi, c1, comp, c2, idx, 0);
+        }
+        r -= len; c -= len;
+        continue;
+      }
+      bool along_cols = (op == DPC_OP_QSKIP) ? genome_rows : !genome_rows;
+      if (along_cols) c -= len; else r -= len;
+      if (op == DPC_OP_GAPHOLDER) { push_gapholder(st); continue; }  /* 2507 */
+      if (op == DPC_OP_GSKIP) {                                       /* add_genomeskip dashes, 2444-2505 */
+        int lo = genome_rows ? r : c, qi2 = genome_rows ? c - 1 : r - 1;
+        int qpos = revp ? q0 - qi2 : q0 + qi2 + 1;
+        for (int j = 0; j < len; j++) {
+          int gi2 = lo + len - 1 - j;
+          push(st, qpos, g0 + step * gi2, ' ', '-', gch[gi2], idx, 0);
+        }
+      } else {                                                        /* add_queryskip, 2372-2413 */
+        int lo = genome_rows ? c : r, gi2 = genome_rows ? r - 1 : c - 1;
+        int gpos = revp ? g0 - gi2 : g0 + gi2 + 1;
+        for (int j = 0; j < len; j++) {
+          int qi2 = lo + len - 1 - j;
+          push(st, q0 + step * qi2, gpos, qch[qi2], '-', ' ', idx, 0);
+        }
+      }
+    }
+  }
+
+  static void emit(Stack &out, const Stack &v, size_t from, bool reversed) {
+    size_t n = v.size() - from;
+    for (size_t i = 0; i < n; i++) out.push_back(v[from + (reversed ? n - 1 - i : i)]);
+  }
+
+  /* Fills `out` with the pairs of problem i in the order of the List_T the reference returns. */
+  void rebuild(int i, const DevRes &dr, const uint16_t *ops, Stack &out) const {
+    const HostProb &h = probs[i];
+    const dpc_problem_t &p = h.p;
+    const char *q = (const char *)&pool[h.q0];
+    std::vector<char> qa, ga, qb, gb;
+    Stack sL, sR;
+    out.clear();
+    switch (p.kind) {
+    case DPC_SINGLE_GAP: {
+      ga.resize(h.L2);
+      for (int k = 0; k < h.L2; k++) ga[k] = host_genomic_nt(p, p.offset2 + k);
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga.data(), p.offset1, p.offset2, false, false, p.dynprogindex);
+      emit(out, sL, 0, false);                                         /* List_reverse of the pushed list, 4571 */
+      break;
+    }
+    case DPC_END5_GAP: case DPC_END3_GAP: {
+      const bool five = p.kind == DPC_END5_GAP;
+      qa.resize(h.L1); ga.resize(h.L2);
+      for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
+      for (int k = 0; k < h.L2; k++) ga[k] = host_genomic_nt(p, five ? p.offset2 - k : p.offset2 + k);
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa.data(), ga.data(), p.offset1, p.offset2, five, false, p.dynprogindex);
+      if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) break;   /* 5259 */
+      size_t first = 0;                                                /* 5265-5268 */
+      while (first < sL.size() && sL[first].comp == '-') first++;
+      emit(out, sL, first, five);                                      /* end5: List_reverse again 5283; end3: as is 5740 */
+      break;
+    }
+    case DPC_GENOME_GAP: {
+      if (!(dr.status & DPC_ST_OK)) break;
+      const int L1 = p.length1, L2L = p.length2, L2R = p.length2R, revoffset1 = p.offset1 + L1 - 1;
+      qb.resize(L1); ga.resize(L2L); gb.resize(L2R);
+      for (int k = 0; k < L1; k++) qb[k] = q[L1 - 1 - k];
+      for (int k = 0; k < L2L; k++) ga[k] = host_genomic_nt(p, p.offset2 + k);
+      for (int k = 0; k < L2R; k++) gb[k] = host_genomic_nt(p, p.offset2R - k);
+      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb.data(), gb.data(), revoffset1, p.offset2R, true, false, p.dynprogindex);
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga.data(), p.offset1, p.offset2, false, false, p.dynprogindex);
+      if (sR.size() + sL.size() > 0) {                                 /* List_length == 1 -> NULL, 5051 */
+        emit(out, sR, 0, true);
+        push_gapholder(out);
+        emit(out, sL, 0, false);
+      }
+      break;
+    }
+    case DPC_CDNA_GAP: {
+      if (!(dr.status & DPC_ST_OK)) break;
+      const int L1L = p.length1, L1R = p.length1R, L2 = p.length2, revoffset2 = p.offset2 + L2 - 1;
+      const int span = p.offset1R - p.offset1 + 1;
+      qb.resize(L1R); ga.resize(L2); gb.resize(L2);
+      for (int k = 0; k < L1R; k++) qb[k] = q[span - 1 - k];
+      for (int k = 0; k < L2; k++) { ga[k] = host_genomic_nt(p, p.offset2 + k); gb[k] = host_genomic_nt(p, revoffset2 - k); }
+      Stack mid;
+      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb.data(), gb.data(), p.offset1R, revoffset2, true, true, p.dynprogindex);
+      int queryjump = (p.offset1R - dr.bestcR) - (p.offset1 + dr.bestcL) + 1;     /* 4725-4726 */
+      int genomejump = (revoffset2 - dr.bestrR) - (p.offset2 + dr.bestrL) + 1;
+      if (queryjump == 9 && genomejump == 9) {                         /* INSERT_PAIRS, 4730-4751 */
+        for (int k = p.offset1R - dr.bestcR; k >= p.offset1 + dr.bestcL; k--)
+          push(mid, k, revoffset2 - dr.bestrR + 1, q[k - p.offset1], '~', ' ', p.dynprogindex, 0);
+        for (int k = revoffset2 - dr.bestrR; k >= p.offset2 + dr.bestrL; k--)
+          push(mid, p.offset1 + dr.bestcL, k, ' ', '~', ga[k - p.offset2], p.dynprogindex, 0);
+      } else {
+        push_gapholder(mid);
+      }
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga.data(), p.offset1, p.offset2, false, true, p.dynprogindex);
+      (void)L1L;
+      if (sR.size() + mid.size() + sL.size() != 1) {                   /* 4784-4787 */
+        emit(out, sR, 0, true);
+        emit(out, mid, 0, false);
+        emit(out, sL, 0, false);
+      }
+      break;
+    }
+    default: break;
+    }
+  }
+
+  /* Turns the device record of problem i into the reference's output parameters. */
+  void finalize(int i, const DevRes &dr, const uint16_t *ops) {
+    HostProb &h = probs[i];
+    const dpc_problem_t &p = h.p;
+    dpc_result_t &r = h.res;
+    int npairs = -1;     /* -1: count by rebuilding */
+    /* pairs pushed = aligned columns that are not '*' + dashes + gapholders */
+    int pushed = dr.nmatches + dr.nmismatches;
+    for (int k = 0; k < dr.nopsL + dr.nopsR; k++) {
+      int op = ops[k] & 3, len = ops[k] >> 2;
+      if (op == DPC_OP_GSKIP || op == DPC_OP_QSKIP) pushed += len; else if (op == DPC_OP_GAPHOLDER) pushed += 1;
+    }
+    const bool star = (dr.status & DPC_ST_STAR) != 0;
+    switch (p.kind) {
+    case DPC_SINGLE_GAP:
+      r.finalscore = dr.finalscore;
+      r.nmatches = dr.nmatches; r.nmismatches = dr.nmismatches; r.nopens = dr.nopens; r.nindels = dr.nindels;
+      r.dynprogindex_out = bump(p.dynprogindex);
+      npairs = pushed;
+      break;
+    case DPC_END5_GAP: case DPC_END3_GAP:
+      r.finalscore = dr.finalscore;
+      r.nmatches = dr.nmatches; r.nmismatches = dr.nmismatches; r.nopens = dr.nopens; r.nindels = dr.nindels;
+      r.dynprogindex_out = bump(p.dynprogindex);
+      if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) {
+        r.finalscore = 0; npairs = 0;                                  /* 5259-5262 */
+      } else if (!star) npairs = pushed;                               /* a leading '-' needs a skipped '*' column before it */
+      break;
+    case DPC_GENOME_GAP: {
+      r.finalscore = dr.finalscore;
+      r.introntype = ((dr.status & DPC_ST_HAVE) && !p.use_probabilities_p) ? dr.introntype : DPC_UNSET;
+      npairs = 0;
+      if (dr.status & DPC_ST_OK) {
+        const uint8_t *known = (G().setup.splice_known != NULL)
+            ? &pool[h.aux + (p.use_probabilities_p ? 8u * (uint32_t)(p.length2 + p.length2R) : 0u)] : NULL;
+        if (p.finalp) {                                                /* 4104-4108 */
+          r.left_prob = site_prob(p, true, dr.bestcL, known && known[dr.bestcL]);
+          r.right_prob = site_prob(p, false, dr.bestcR, known && known[p.length2 + dr.bestcR]);
+        }
+        r.new_leftgenomepos = p.offset2 + (dr.bestcL - 1);             /* 5000-5004 */
+        r.new_rightgenomepos = p.offset2R - (dr.bestcR - 1);
+        r.exonhead = (p.offset1 + p.length1 - 1) - (dr.bestrR - 1);
+        r.nmatches = dr.nmatches; r.nmismatches = dr.nmismatches; r.nopens = dr.nopens; r.nindels = dr.nindels;
+        r.dynprogindex_out = bump(p.dynprogindex);
+        npairs = pushed > 0 ? pushed + 1 : 0;
+      }
+      break;
+    }
+    case DPC_CDNA_GAP: {
+      r.finalscore = dr.finalscore;
+      npairs = 0;
+      if (dr.status & DPC_ST_OK) {
+        int revoffset2 = p.offset2 + p.length2 - 1;
+        int queryjump = (p.offset1R - dr.bestcR) - (p.offset1 + dr.bestcL) + 1;
+        int genomejump = (revoffset2 - dr.bestrR) - (p.offset2 + dr.bestrL) + 1;
+        int mid = 1;
+        if (queryjump == 9 && genomejump == 9) mid = 18; else r.incompletep = 1;
+        r.dynprogindex_out = bump(p.dynprogindex);
+        npairs = pushed + mid == 1 ? 0 : pushed + mid;
+      }
+      break;
+    }
+    default: break;
+    }
+    if (npairs < 0) { Stack out; rebuild(i, dr, ops, out); npairs = (int)out.size(); }
+    r.npairs = npairs;
+    r.null_list = npairs == 0;
+  }
+};
+
+inline const char *strerror_(int code) {
+  switch (code) {
+  case DPC_OK: return "ok";
+  case DPC_ERR_CUDA: return "CUDA device or driver error (there is no CPU fallback)";
+  case DPC_ERR_ARG: return "malformed problem";
+  case DPC_ERR_ALPHABET: return "query byte >= 128";
+  case DPC_ERR_UNSUPPORTED: return "unsupported bridge mode";
+  case DPC_ERR_STATE: return "library not initialised / bad ticket / missing hook";
+  case DPC_ERR_NOMEM: return "out of memory or output capacity too small";
+  default: return "unknown error";
+  }
+}
+
+}  // namespace dpc
+#endif /* DPC_HOST_H */

@@ -1,0 +1,69 @@
+/* tests/emul/dpc_emul.cpp -- TEST SCAFFOLDING, NOT PRODUCT CODE.
+ *
+ * Compiles the warp-level routines of gmap-gsnap_b200/csrc/dpc_core.h with g++ and a single
+ * lane, plus the real host side (dpc_host.h: packing, finalisation, pair rebuild), so that the
+ * CPU test-suite can check index arithmetic, tie-breaks and boundary rules against the oracle on
+ * a machine without a GPU.  libdynprog_cuda never links or loads this file; it has no CPU path.
+ */
+#include <stdlib.h>
+#include <vector>
+#include "../../gmap-gsnap_b200/csrc/dpc_host.h"
+
+extern "C" int emul_init(int maxlookback, int extraquerygap, int maxpeelback, int end, int paired, int mode) {
+  return dpc::host_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode);
+}
+extern "C" int emul_setup(const dpc_setup_t *s) {
+  dpc::Globals &g = dpc::G();
+  g.setup = *s;
+  g.genome_nbases = s->genome_nwords / 3 * 32;
+  g.setup_done = true;
+  return 0;
+}
+extern "C" int emul_pairdistance(int type, int c1, int c2) { return dpc::G().P[type & 3][c1 & 127][c2 & 127]; }
+
+extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *results,
+                          dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off) {
+  dpc::Batch b;
+  for (int i = 0; i < n; i++) {
+    int t = b.add(problems[i]);
+    if (t < 0) return t;
+  }
+  std::vector<DevRes> dres(b.dprobs.size());
+  std::vector<uint16_t> ovfbuf(1 << 22);
+  unsigned int used = 0;
+  OvfArena ovf; ovf.ops = ovfbuf.data(); ovf.used = &used; ovf.cap = (unsigned int)ovfbuf.size();
+  Lanes ln; ln.lane = 0; ln.n = 1;
+  GenericFill fill;
+  std::vector<uint8_t> arena;
+  b.pool_align(16);
+  for (size_t k = 0; k < b.dprobs.size(); k++) {
+    ArenaLayout a;
+    dpc_layout(b.dprobs[k], a, 1);
+    arena.assign(a.total + 64, 0xAB);
+    memset(&dres[k], 0, sizeof(DevRes));
+    dpc_solve_problem(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables,
+                      arena.data(), &dres[k], ovf, fill, ln);
+  }
+  int64_t out = 0;
+  dpc::Batch::Stack st;
+  for (int i = 0; i < n; i++) {
+    dpc::HostProb &h = b.probs[i];
+    if (pair_off) pair_off[i] = out;
+    if (h.dev >= 0) {
+      const DevRes &dr = dres[h.dev];
+      const uint16_t *ops = (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? ovfbuf.data() + dr.ovf : dr.ops;
+      if (dr.status & DPC_ST_OVF_LOST) return DPC_ERR_NOMEM;
+      b.finalize(i, dr, ops);
+      b.rebuild(i, dr, ops, st);
+      if ((int)st.size() != h.res.npairs) return -100;
+      if (pairs) {
+        if (out + (int64_t)st.size() > pair_cap) return DPC_ERR_NOMEM;
+        if (!st.empty()) memcpy(pairs + out, st.data(), st.size() * sizeof(dpc_pair_t));
+      }
+      out += (int64_t)st.size();
+    }
+    results[i] = h.res;
+  }
+  if (pair_off) pair_off[n] = out;
+  return 0;
+}
