@@ -3,10 +3,10 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 PKG = gmap-gsnap_b200
 NVFLAGS = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function -Xptxas -v
 
-all: cuda synth oracle
+all: cuda synth oracle emul
 
 cuda: $(PKG)/csrc/libdynprog_cuda.so
-$(PKG)/csrc/libdynprog_cuda.so: $(PKG)/csrc/*.cu $(PKG)/csrc/*.h include/dynprog_cuda.h
+$(PKG)/csrc/libdynprog_cuda.so: $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/dynprog_cuda.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/dynprog_cuda.cu -lcudart 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; exit 1)
 	@grep -E "registers|spill" $(PKG)/csrc/ptxas.log | sort | uniq -c | head -40
 
@@ -17,7 +17,12 @@ $(PKG)/host/libdpc_synth.so: $(PKG)/host/synth.c include/dynprog_cuda.h
 oracle:
 	$(MAKE) -C oracle
 
+# single-lane CPU build of the device routines: test scaffolding only (tests/emul/dpc_emul.cpp)
+emul: tests/emul/libdpc_emul.so
+tests/emul/libdpc_emul.so: tests/emul/dpc_emul.cpp $(PKG)/csrc/dpc_core.h $(PKG)/csrc/dpc_host.h include/dynprog_cuda.h
+	g++ -O2 -fPIC -Wall -Wextra -shared -o $@ tests/emul/dpc_emul.cpp
+
 clean:
-	rm -f $(PKG)/csrc/*.so $(PKG)/host/*.so $(PKG)/csrc/ptxas.log
+	rm -f $(PKG)/csrc/*.so $(PKG)/host/*.so $(PKG)/csrc/ptxas.log tests/emul/*.so
 	$(MAKE) -C oracle clean
-.PHONY: all cuda synth oracle clean
+.PHONY: all cuda synth oracle emul clean

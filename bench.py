@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py -- banded gap-fill DP throughput (GCUPS, gap-fills/s) of libdynprog_cuda on B200.
+
+Workload (BASELINE.json configs[1]): batched Dynprog_single_gap, 1 M synthetic gap fills of 10-100 bp,
+band (extraband_single) 30, widebandp, on ONE B200; random genome, queries = genomic windows with 5 %
+substitutions, 3 % deletions, 3 % insertions.  Under torchrun each rank owns one GPU and its own
+1 M problems (sharded by read, no collective on the data path): weak scaling.
+
+A step = one pass of the hot path over the batch.
+  value   GCUPS with the batch resident in HBM (kernels only, CUDA events on the library's stream).
+  e2e     GCUPS through the C ABI with HOST buffers: dpc_solve = pack + H2D + kernels + D2H + result
+          finalisation + Pair-record rebuild, wall clock.
+  --impl reference   the reference's own dynprog.c (oracle/_ref, compiled unmodified) on all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gmap_gsnap_b200 import api  # noqa: E402
+
+METRIC = "banded_dp_gcups_single_gap"
+UNIT = "GCUPS"
+N_PROBLEMS = 1_000_000
+GENOME_BASES = 64_000_000
+EXTRABAND = 30
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def band_cells(probs):
+    """In-band cells of every matrix, for single gaps: one matrix each."""
+    L1 = probs["length1"].astype(np.int64)
+    L2 = probs["length2"].astype(np.int64)
+    eb = probs["extraband"].astype(np.int64)
+    rband = np.where(L2 >= L1, L2 - L1 + eb, eb)
+    lband = np.where(L2 >= L1, eb, L1 - L2 + eb)
+    total = np.zeros(len(probs), dtype=np.int64)
+    for c in range(1, int(L2.max()) + 1):
+        lo = np.maximum(1, c - rband)
+        hi = np.minimum(L1, c + lband)
+        total += np.where(c <= L2, np.maximum(hi - lo + 1, 0), 0)
+    return total
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_workload(rank, n):
+    w = api.Workload(GENOME_BASES, seed=0x9E3779B9 + rank, nchr=4)
+    probs = w.single_gaps(n, extraband=EXTRABAND, seed=0x5EED0002 + 1000 * rank)
+    return w, probs
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, all host threads (gmap -t N shape, gmap.c:2254-2276)."""
+    if rank != 0:
+        return
+    ref = api.RefOracle()
+    ref.init()
+    cores = os.cpu_count() or 1
+    sample = min(N_PROBLEMS, max(20000, 40000 * cores))
+    w, probs = make_workload(0, sample)
+    ref.setup(w.make_setup())
+    cells = int(band_cells(probs).sum())
+    for _ in range(args.warmup):
+        ref.solve_mt(probs[: sample // 4], cores)
+    secs = 0.0
+    for _ in range(args.steps):
+        _, s = ref.solve_mt(probs, cores)
+        secs += s
+    gcups = cells * args.steps / secs / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "fills_per_s": sample * args.steps / secs,
+        "config": {"workload": "Dynprog_single_gap, synthetic 10-100 bp gap fills, band 30 (BASELINE configs[1])",
+                   "problems_per_step": sample, "extraband_single": EXTRABAND, "genome_bases": GENOME_BASES},
+        "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "%d of the 1M single-gap problems per step, unmodified dynprog.c -O3, one Dynprog_T + Pairpool per thread" % sample},
+        "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--problems", type=int, default=N_PROBLEMS)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allreduce(x, op):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
+    w, probs = make_workload(rank, args.problems)
+    lib = api.CudaLib()
+    lib.init()
+    lib.setup(w.make_setup())
+    lib.open(local_rank)
+    L = lib.lib
+    n = len(probs)
+
+    # one full solve: loads the batch into HBM and gives the results used for the sanity check
+    res, _, _ = lib.solve(probs, want_pairs=False)
+    stats = lib.stats()
+    cells = int(stats.cells)
+    assert cells == int(band_cells(probs).sum()), "cell count mismatch"
+    assert (res["null_list"] == 0).all()
+
+    def step():
+        lib.check(L.dpc_relaunch(lib.ctx), "dpc_relaunch")
+        lib.check(L.dpc_sync(lib.ctx), "dpc_sync")
+        return lib.kernel_ms()[2]
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms = [step() for _ in range(args.steps)]
+    barrier()
+    dev_ms = allreduce(float(sum(ms)), "MAX")
+    total_cells = allreduce(float(cells), "SUM")
+    total_fills = allreduce(float(n), "SUM")
+    launches = lib.stats().launches * args.steps
+
+    # end to end through the C ABI with host buffers (results + Pair records)
+    lib.solve(probs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        r2, pairs, off = lib.solve(probs)
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    e2e_s = allreduce(e2e_s, "MAX")
+    st = lib.stats()
+    assert (r2 == res).all()
+
+    hbm_peak, peak_src, sm_max = peaks()
+    step_ms = dev_ms / args.steps
+    gcups = total_cells / (step_ms * 1e-3) / 1e9
+    algo_bytes = float(st.fill_bytes)
+    line = {
+        "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "fills_per_s": total_fills / (step_ms * 1e-3),
+        "config": {"workload": "Dynprog_single_gap, 1M synthetic 10-100 bp gap fills, band 30, on 1 B200 per rank (BASELINE configs[1])",
+                   "problems_per_gpu": n, "extraband_single": EXTRABAND, "genome_bases": GENOME_BASES,
+                   "cells_per_gpu": cells, "l2": "inputs larger than L2 (descriptors + sequences + results = %.0f MB per step)" % (algo_bytes / 1e6)},
+        "e2e": {"value": total_cells / e2e_s / 1e9, "unit": UNIT, "fills_per_s": total_fills / e2e_s, "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
+                "includes": "dpc_solve: pack, H2D, kernels, D2H, result finalisation, Pair-record rebuild (%d records)" % len(pairs)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms[len(ms) // 2] * 1e-3) / 1e9 if rank == 0 else None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9 / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "fused fill+traceback keeps matrices and direction nibbles in shared memory; algorithmic HBM bytes are "
+                             "descriptors, sequences and result records only, so the kernel is integer-ALU/latency bound (see alu_roofline)"},
+        "alu_roofline": {"achieved_gcups_per_gpu": cells / (float(np.mean(ms)) * 1e-3) / 1e9,
+                         "peak_gcups": 148 * 64 * sm_max * 1e6 / 25 / 1e9,
+                         "note": "peak = 148 SMs x 64 int32 ALU lanes/clk x max SM clock / 25 ALU ops per cell (DESIGN.md)"},
+    }
+    line["roofline"]["achieved"] = algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9
+    line["alu_roofline"]["frac"] = line["alu_roofline"]["achieved_gcups_per_gpu"] / line["alu_roofline"]["peak_gcups"]
+
+    if rank == 0 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdynprog_ref.so")):
+        ref = api.RefOracle()
+        ref.init()
+        ref.setup(w.make_setup())
+        cores = os.cpu_count() or 1
+        sample = min(n, max(20000, 40000 * cores))
+        _, secs = ref.solve_mt(probs[:sample], cores)
+        scells = int(band_cells(probs[:sample]).sum())
+        line["cpu_baseline"] = {"value": scells / secs / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+                                "fills_per_s": sample / secs,
+                                "sample": "first %d of the 1M problems, unmodified reference dynprog.c (-O3), %d threads" % (sample, cores)}
+    lib.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -153,7 +153,7 @@ class Workload:
         sp.p_sub, sp.p_del, sp.p_ins = 0.05, 0.03, 0.03
         sp.long_frac, sp.long_hi = 0.0, 600
         for k, v in kw.items():
-            setattr(sp, k, v)
+            setattr(sp, k, v)      # includes seed=... for an independent stream
         return sp
 
     def _gen(self, fname, n, qbytes_per, sp):
@@ -167,17 +167,23 @@ class Workload:
         return probs
 
     def single_gaps(self, n, extraband=30, **kw):
-        sp = self.params(extraband=extraband, len_lo=10, len_hi=100, p_sub=0.05, p_del=0.03, p_ins=0.03, **kw)
+        d = dict(extraband=extraband, len_lo=10, len_hi=100, p_sub=0.05, p_del=0.03, p_ins=0.03)
+        d.update(kw)
+        sp = self.params(**d)
         return self._gen("synth_single_gaps", n, 2 * sp.len_hi + 16, sp)
 
     def end_gaps(self, n, extraband=3, **kw):
-        sp = self.params(extraband=extraband, len_lo=1, len_hi=40, p_sub=0.03, p_del=0.0025, p_ins=0.0025, **kw)
+        d = dict(extraband=extraband, len_lo=1, len_hi=40, p_sub=0.03, p_del=0.0025, p_ins=0.0025)
+        d.update(kw)
+        sp = self.params(**d)
         return self._gen("synth_end_gaps", n, 2 * (sp.len_hi + 11) + 16, sp)
 
     def genome_gaps(self, n, extraband=7, long_frac=0.1, long_hi=600, **kw):
-        sp = self.params(extraband=extraband, len_lo=22, len_hi=60, p_sub=0.02, p_del=0.005, p_ins=0.005,
-                         long_frac=long_frac, long_hi=long_hi, **kw)
-        per = 2 * (sp.long_hi if long_frac > 0 else sp.len_hi) + 32
+        d = dict(extraband=extraband, len_lo=22, len_hi=60, p_sub=0.02, p_del=0.005, p_ins=0.005,
+                 long_frac=long_frac, long_hi=long_hi)
+        d.update(kw)
+        sp = self.params(**d)
+        per = 2 * (sp.long_hi if sp.long_frac > 0 else sp.len_hi) + 32
         return self._gen("synth_genome_gaps", n, per, sp)
 
     def cdna_gaps(self, n, extraband=7, **kw):
@@ -406,3 +412,63 @@ def compare(res_a, pairs_a, off_a, res_b, pairs_b, off_b, rtol=1e-6):
             i = int(np.searchsorted(off_a, j, side="right") - 1)
             bad.append("pair %d (problem %d, #%d): %r vs %r" % (j, i, j - off_a[i], pairs_a[j], pairs_b[j]))
     return bad
+
+
+# --------------------------------------------------------------------------- (de)serialisation of problem sets
+def _span(p):
+    """(address of the first byte, length) of the query bytes problem p points at."""
+    kind = int(p["kind"])
+    if kind == END5_GAP:
+        n = max(int(p["length1"]), 0)
+        return int(p["seq1"]) - (n - 1), n
+    if kind == CDNA_GAP:
+        n = int(p["offset1R"]) - int(p["offset1"]) + 1
+        return int(p["seq1"]), max(n, 0)
+    return int(p["seq1"]), max(int(p["length1"]), 0)
+
+
+def detach(problems):
+    """Copies the query bytes out of process memory: returns (problems with pointers zeroed, qbuf, offsets)."""
+    out = problems.copy()
+    chunks, offs, at = [], np.zeros(len(problems), dtype=np.int64), 0
+    for i, p in enumerate(problems):
+        addr, n = _span(p)
+        offs[i] = at
+        if n > 0:
+            chunks.append(C.string_at(addr, n))
+            at += n
+    out["seq1"] = 0
+    out["seq1R"] = 0
+    qbuf = np.frombuffer(b"".join(chunks) + b"\0" * 8, dtype=np.uint8).copy()
+    return out, qbuf, offs
+
+
+def attach(problems, qbuf, offs):
+    """Inverse of detach: points the problems at qbuf (which the caller must keep alive)."""
+    out = problems.copy()
+    base = qbuf.ctypes.data
+    for i in range(len(out)):
+        kind = int(out["kind"][i])
+        if kind == END5_GAP:
+            out["seq1"][i] = base + offs[i] + max(int(out["length1"][i]), 0) - 1
+        elif kind == CDNA_GAP:
+            out["seq1"][i] = base + offs[i]
+            out["seq1R"][i] = base + offs[i] + int(out["offset1R"][i]) - int(out["offset1"][i])
+        else:
+            out["seq1"][i] = base + offs[i]
+    return out
+
+
+def arm_probability_mode(problems, solver):
+    """Genome gaps the generator marked use_probabilities_p == 2 become the reference's second call
+    (stage3.c:5833): use_probabilities_p = true with score_threshold = first-pass finalscore + QOPEN + 3*QINDEL
+    (scores.h:7-8) = finalscore - 11.  `solver` is any of the libraries above."""
+    out = problems.copy()
+    sel = np.nonzero(out["use_probabilities_p"] == 2)[0]
+    if len(sel) == 0:
+        return out
+    out["use_probabilities_p"][sel] = 0
+    res, _, _ = solver.solve(out[sel], want_pairs=False)
+    out["use_probabilities_p"][sel] = 1
+    out["score_threshold"][sel] = res["finalscore"] - 11
+    return out

@@ -22,10 +22,12 @@
 #ifdef __CUDACC__
 #define DPC_HD __device__ __forceinline__
 #define DPC_HDM __device__ __forceinline__
+#define DPC_HB __host__ __device__ __forceinline__   /* also called by the host packing code */
 #define DPC_SYNC() __syncwarp()
 #else
 #define DPC_HD static inline
 #define DPC_HDM inline
+#define DPC_HB static inline
 #define DPC_SYNC() ((void)0)
 #endif
 
@@ -94,7 +96,7 @@ struct DevTables {
 struct Lanes { int lane, n; };
 
 /* ---- genome access: get_genomic_nt, dynprog.c:403-441; uncompress_one_char, genome.c:9325 ---- */
-DPC_HD int dpc_genome_code(const uint32_t *blocks, uint32_t pos) {
+DPC_HB int dpc_genome_code(const uint32_t *blocks, uint32_t pos) {
   const uint32_t *b = blocks + (uint64_t)(pos >> 5) * 3;
   int bit = (int)(pos & 31);
   if ((b[2] >> bit) & 1U) return DPC_GN;
@@ -106,8 +108,8 @@ DPC_HD int dpc_genomic_code(const DevProb &p, const uint32_t *blocks, int genomi
   int c = dpc_genome_code(blocks, p.gbase + (p.glen - 1) - (uint32_t)genomicpos);
   return c < 4 ? (c ^ 3) : c;                      /* complCode, complement.h:31 */
 }
-DPC_HD int dpc_code_char(int code) { return "ACGTN*"[code]; }
-DPC_HD int dpc_query_uc(int c) {                   /* UPPERCASE_U2T, complement.h:36 */
+DPC_HB int dpc_code_char(int code) { return "ACGTN*"[code]; }
+DPC_HB int dpc_query_uc(int c) {                   /* UPPERCASE_U2T, complement.h:36 */
   if (c >= 'a' && c <= 'z') c -= 32;
   return c == 'U' ? 'T' : c;
 }
@@ -125,13 +127,13 @@ struct Mat {
   int32_t *nband;           /* nogap score of rows 1..L1, (r-1)*W + (c-r+lband); NULL when no bridge follows */
 };
 
-DPC_HD void dpc_bands(int L1, int L2, int extraband, int widebandp, int *lband, int *rband) {
+DPC_HB void dpc_bands(int L1, int L2, int extraband, int widebandp, int *lband, int *rband) {
   /* dynprog.c:1442-1454 */
   if (!widebandp) { *lband = *rband = extraband; }
   else if (L2 >= L1) { *rband = L2 - L1 + extraband; *lband = extraband; }
   else { *lband = L1 - L2 + extraband; *rband = extraband; }
 }
-DPC_HD int dpc_wstride(int W) { return (W + 7) >> 3; }
+DPC_HB int dpc_wstride(int W) { return (W + 7) >> 3; }
 DPC_HD bool dpc_inband(const Mat &m, int r, int c) {
   int k = c - r;
   return r >= 1 && c >= 1 && r <= m.L1 && c <= m.L2 && k >= -m.lband && k <= m.rband;
@@ -487,10 +489,10 @@ struct ArenaLayout {
   MatDims d[2];
   uint32_t rowch[2], colch[2], dir[2], nband[2], ops[2], state, total;
 };
-DPC_HD uint32_t dpc_al(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
+DPC_HB uint32_t dpc_al(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
 
 /* kind codes as in include/dynprog_cuda.h: 0 single, 1 genome, 2 cdna, 3 end5, 4 end3 */
-DPC_HD void dpc_layout(const DevProb &p, ArenaLayout &a, int with_state) {
+DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int with_state) {
   uint32_t off = 0;
   int maxrows = 0;
   a.nmat = (p.kind == 1 || p.kind == 2) ? 2 : 1;
@@ -509,6 +511,11 @@ DPC_HD void dpc_layout(const DevProb &p, ArenaLayout &a, int with_state) {
     a.ops[i] = off; off = dpc_al(off + 2 * (uint32_t)(d.rows + d.cols + 2), 4);
   }
   a.state = off;
+  /* anti-diagonal state of dpc_fill_generic: 1 = always, 2 = only for bands the register fill cannot take */
+  if (with_state == 2) {
+    with_state = 0;
+    for (int i = 0; i < a.nmat; i++) if (a.d[i].lband + a.d[i].rband >= 64) with_state = 1;
+  }
   if (with_state) off += 9 * (uint32_t)(maxrows + 1) * 4;
   a.total = dpc_al(off, 16);
 }

@@ -215,6 +215,12 @@ int dpc_solve(dpc_ctx_t *ctx, const dpc_problem_t *problems, int n,
  * cudaStream_t so the caller can bracket it with events. */
 int dpc_relaunch(dpc_ctx_t *ctx);
 void *dpc_stream(dpc_ctx_t *ctx);
+/* Waits for the work queued by dpc_relaunch and refreshes dpc_last_kernel_ms. */
+int dpc_sync(dpc_ctx_t *ctx);
+/* Test hook: nonzero routes every matrix through the memory-state anti-diagonal fill
+ * (the routine used for bands of 64+ diagonals) instead of the register/shuffle fill.
+ * Both are device code; the environment variable DPC_FORCE_GENERIC_FILL=1 does the same. */
+int dpc_set_fill(int force_generic);
 /* Average device time in ms of the last dpc_flush/dpc_relaunch per kernel
  * stage (CUDA events recorded on the context's stream):
  * 0 fill(+bridge), 1 traceback, 2 total.  Returns DPC_OK or an error. */

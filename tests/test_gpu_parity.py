@@ -1,0 +1,162 @@
+"""GPU suite: libdynprog_cuda, called through its C ABI, against the oracle on the same seeded inputs.
+Bit-exact for scores, end points, intron boundaries, counts and Pair records; 1e-6 relative for the
+splice-site probabilities (the tolerance BASELINE.json's north_star states)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gmap_gsnap_b200 import api
+from util import GOLDEN_SETS, Golden, mixed_problems
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return Golden()
+
+
+@pytest.fixture(scope="module", params=[0, 1], ids=["register_fill", "memory_fill"])
+def fill_mode(request, cuda):
+    cuda.lib.dpc_set_fill(request.param)
+    yield request.param
+    cuda.lib.dpc_set_fill(0)
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_golden_vectors(golden, name):
+    lib = api.CudaLib()
+    lib.init()
+    lib.setup(golden.setup())
+    lib.open(0)
+    try:
+        for force in (0, 1):
+            lib.lib.dpc_set_fill(force)
+            got = lib.solve(golden.problems(name))
+            assert not api.compare(*golden.expected(name), *got, rtol=RTOL)
+    finally:
+        lib.lib.dpc_set_fill(0)
+        lib.close()
+    assert not golden.missing
+
+
+def test_mixed_batch_matches_oracle(workload, port, cuda, fill_mode):
+    probs = api.arm_probability_mode(mixed_problems(workload, 4000, 101, long_frac=0.03, long_hi=611), port)
+    assert not api.compare(*port.solve(probs), *cuda.solve(probs), rtol=RTOL)
+
+
+def test_matches_compiled_reference(workload, ref, cuda):
+    probs = api.arm_probability_mode(mixed_problems(workload, 3000, 202), ref)
+    assert not api.compare(*ref.solve(probs), *cuda.solve(probs), rtol=RTOL)
+
+
+@pytest.mark.parametrize("extraband", [0, 3, 30])
+def test_single_gap_bands(workload, port, cuda, fill_mode, extraband):
+    probs = workload.single_gaps(6000, extraband=extraband, seed=300 + extraband, edge_frac_pm=20, lower_case=1, iupac_pm=5)
+    assert not api.compare(*port.solve(probs), *cuda.solve(probs))
+
+
+def test_end_gaps_all_endalign(workload, port, cuda, fill_mode):
+    probs = workload.end_gaps(12000, seed=401, edge_frac_pm=30, lower_case=1, iupac_pm=10)
+    for ea in range(4):
+        probs["endalign"][ea::7] = ea
+    assert not api.compare(*port.solve(probs), *cuda.solve(probs))
+
+
+def test_genome_gaps_modes(workload, port, cuda, fill_mode):
+    probs = workload.genome_gaps(5000, seed=501, finalp_mode=2, prob_mode_pm=200, long_frac=0.08, long_hi=611, iupac_pm=3)
+    probs = api.arm_probability_mode(probs, port)
+    want, got = port.solve(probs), cuda.solve(probs)
+    assert not api.compare(*want, *got, rtol=RTOL)
+    assert want[0]["null_list"].sum() > 0 and (want[0]["null_list"] == 0).sum() > 0
+
+
+def test_cdna_gaps(workload, port, cuda, fill_mode):
+    probs = workload.cdna_gaps(1500, seed=601)
+    assert not api.compare(*port.solve(probs), *cuda.solve(probs))
+
+
+def test_wide_bands_and_max_sizes(workload, port, cuda):
+    """Bands of 64+ diagonals (memory-state fill inside the default kernel), problems that need HBM scratch,
+    and the largest matrices Dynprog_T allows (611 x 2000)."""
+    probs = workload.single_gaps(60, extraband=30, seed=21)
+    probs["length2"][:20] = np.minimum(probs["length1"][:20] + np.arange(20) * 7 + 30, 2000)
+    probs["extraband"][20:30] = 64
+    big = workload.single_gaps(4, extraband=3, seed=22, len_lo=580, len_hi=600, p_del=0.002, p_ins=0.002)
+    big["length2"][0] = 2000
+    gg = workload.genome_gaps(6, seed=23, long_frac=1.0, long_hi=611, len_hi=560)
+    allp = np.concatenate([probs, big, gg])
+    assert not api.compare(*port.solve(allp), *cuda.solve(allp))
+
+
+def test_known_splice_sites(workload, prob_hook):
+    known = api.KNOWN_FN(lambda which, chrnum, pos, sign, user: int((pos * 7 + which) % 11 == 0))
+    for novel in (1, 0):
+        s = workload.make_setup(splice_prob=prob_hook, splice_known=known, novelsplicingp=novel)
+        o, lib = api.PortOracle(), api.CudaLib()
+        o.init(); lib.init()
+        o.setup(s); lib.setup(s)
+        lib.open(0)
+        try:
+            probs = workload.genome_gaps(400, seed=31 + novel, finalp_mode=2, long_frac=0.0)
+            assert not api.compare(*o.solve(probs), *lib.solve(probs), rtol=RTOL)
+        finally:
+            lib.close()
+    lib = api.CudaLib()     # restore the session-wide setup
+    lib.init()
+
+
+def test_empty_and_degenerate_batches(workload, port, cuda):
+    probs = workload.end_gaps(8, seed=7)
+    res, pairs, off = cuda.solve(probs[:0])
+    assert len(res) == 0 and len(pairs) == 0 and off.tolist() == [0]
+    probs["length1"][:] = 0                      # every problem resolves on the host side of the boundary (5140)
+    assert not api.compare(*port.solve(probs), *cuda.solve(probs))
+
+
+def test_ticket_api_equals_bulk_api(workload, cuda):
+    """dpc_add / dpc_flush / dpc_wait / dpc_result / dpc_pairs (what a modified stage3.c calls) == dpc_solve."""
+    probs = mixed_problems(workload, 200, 77)
+    want_res, want_pairs, want_off = cuda.solve(probs)
+    L = cuda.lib
+    assert L.dpc_reset(cuda.ctx) == 0
+    tickets = [L.dpc_add(cuda.ctx, probs[i:i + 1].ctypes.data_as(C.c_void_p)) for i in range(len(probs))]
+    assert tickets == list(range(len(probs)))
+    assert L.dpc_flush(cuda.ctx) == 0 and L.dpc_wait(cuda.ctx) == 0
+    r = np.zeros(1, dtype=api.RESULT_DT)
+    buf = np.zeros(8192, dtype=api.PAIR_DT)
+    for t in tickets:
+        assert L.dpc_result(cuda.ctx, t, r.ctypes.data_as(C.c_void_p)) == 0
+        assert r[0] == want_res[t]
+        n = L.dpc_pairs(cuda.ctx, t, buf.ctypes.data_as(C.c_void_p), len(buf))
+        assert n == want_off[t + 1] - want_off[t]
+        assert (buf[:n] == want_pairs[want_off[t]:want_off[t + 1]]).all()
+    assert L.dpc_reset(cuda.ctx) == 0
+
+
+def test_full_size_properties(workload, port, cuda):
+    """BASELINE config 2 at full size (1 M single gaps, band 30): too big for the oracle in seconds, so
+    check size-independent properties plus an exact comparison on a strided sample."""
+    n = 1_000_000
+    probs = workload.single_gaps(n, extraband=30, seed=4242)
+    res, _, off = cuda.solve(probs, want_pairs=False)
+    assert (res["null_list"] == 0).all()
+    assert (res["dynprogindex_out"] == probs["dynprogindex"] + np.sign(probs["dynprogindex"])).all()
+    # every aligned column is a match or a mismatch and every run is an indel, so the pairs add up to the path and
+    # the global path consumes both sequences exactly -- except where a 9+ genome run became a gapholder or a
+    # column fell off the segment ('*'); those few are compared with the oracle one by one
+    cols = res["nmatches"] + res["nmismatches"]
+    plain = (cols + res["nindels"] == res["npairs"]) & (2 * cols + res["nindels"] == probs["length1"] + probs["length2"])
+    assert plain.mean() > 0.99
+    odd = probs[~plain][:2000]
+    if len(odd):
+        assert not api.compare(*port.solve(odd), *cuda.solve(odd))
+    # score bound: 3 per match, at least -3 per mismatch (HIGHQ/MEDQ/LOWQ), gaps cost open + n*extend <= -13
+    assert (res["finalscore"] <= 3 * res["nmatches"]).all()
+    # idempotence: solving again gives the same answer
+    res2, _, _ = cuda.solve(probs, want_pairs=False)
+    assert (res == res2).all()
+    sample = probs[:: n // 5000]
+    assert not api.compare(*port.solve(sample), *cuda.solve(sample))

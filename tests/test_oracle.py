@@ -1,0 +1,121 @@
+"""CPU suite, part 1: the oracle is pinned (restatement == compiled reference == golden vectors) and the
+device routines, compiled single-lane for the CPU (tests/emul), agree with it."""
+import numpy as np
+import pytest
+
+from gmap_gsnap_b200 import api
+from util import GOLDEN_SETS, Golden, mixed_problems
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return Golden()
+
+
+@pytest.fixture(scope="module")
+def golden_port(golden):
+    o = api.PortOracle()
+    o.init()
+    o.setup(golden.setup())
+    return o
+
+
+@pytest.fixture(scope="module")
+def golden_emul(golden):
+    e = api.EmulLib()
+    e.init()
+    e.setup(golden.setup())
+    return e
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_restatement_matches_golden(golden, golden_port, name):
+    got = golden_port.solve(golden.problems(name))
+    assert not api.compare(*golden.expected(name), *got)
+    assert not golden.missing
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_device_routines_single_lane_match_golden(golden, golden_emul, name):
+    got = golden_emul.solve(golden.problems(name))
+    assert not api.compare(*golden.expected(name), *got)
+    assert not golden.missing
+
+
+def test_golden_has_negative_cases(golden):
+    res, _, _ = golden.expected("edge")
+    assert res["null_list"].sum() >= 20
+    assert (res["finalscore"] == -10000).sum() >= 2          # "too long" sentinel, dynprog.c:4512
+    assert (res["finalscore"] == -1000000).sum() >= 2        # NEG_INFINITY sentinel, dynprog.c:4857
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_restatement_matches_compiled_reference(workload, ref, port, seed):
+    probs = api.arm_probability_mode(mixed_problems(workload, 1200, seed, long_frac=0.03, long_hi=611), ref)
+    assert not api.compare(*ref.solve(probs), *port.solve(probs))
+
+
+def test_probability_mode_matches_reference(workload, ref, port, emul):
+    probs = workload.genome_gaps(800, seed=5, finalp_mode=2, prob_mode_pm=1000, long_frac=0.0)
+    probs = api.arm_probability_mode(probs, ref)
+    assert (probs["use_probabilities_p"] == 1).all()
+    want = ref.solve(probs)
+    assert not api.compare(*want, *port.solve(probs))
+    assert not api.compare(*want, *emul.solve(probs))
+
+
+def test_device_routines_single_lane_match_oracle(workload, port, emul):
+    probs = api.arm_probability_mode(mixed_problems(workload, 1500, 9, long_frac=0.03, long_hi=611), port)
+    assert not api.compare(*port.solve(probs), *emul.solve(probs))
+
+
+def test_wide_bands_and_max_sizes(workload, port, emul):
+    """Bands of 64+ diagonals and the largest matrices Dynprog_T allows (611 x 2000, dynprog.c:831-852)."""
+    probs = workload.single_gaps(40, extraband=30, seed=21)
+    probs["length2"][:20] = np.minimum(probs["length1"][:20] + np.arange(20) * 7 + 30, 2000)
+    probs["extraband"][20:30] = 64
+    big = workload.single_gaps(3, extraband=3, seed=22, len_lo=580, len_hi=600, p_del=0.002, p_ins=0.002)
+    big["length2"][0] = 2000
+    allp = np.concatenate([probs, big])
+    assert not api.compare(*port.solve(allp), *emul.solve(allp))
+
+
+def test_known_splice_sites(workload, prob_hook):
+    """splicing_iit != NULL: +20 at known sites, and with novelsplicingp == false only known-known introns pass."""
+    known = api.KNOWN_FN(lambda which, chrnum, pos, sign, user: int((pos * 7 + which) % 11 == 0))
+    for novel in (1, 0):
+        s = workload.make_setup(splice_prob=prob_hook, splice_known=known, novelsplicingp=novel)
+        o, e = api.PortOracle(), api.EmulLib()
+        o.init(); e.init()
+        o.setup(s); e.setup(s)
+        probs = workload.genome_gaps(300, seed=31 + novel, finalp_mode=2, long_frac=0.0)
+        want, got = o.solve(probs), e.solve(probs)
+        assert not api.compare(*want, *got)
+        if not novel:
+            assert want[0]["null_list"].sum() > 0
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_pairdistance_tables(mode):
+    """pairdistance_init (dynprog.c:1127-1226) for every Mode_T: product table == restatement table,
+    including the 'z' / 'Z' loop-bound quirks."""
+    o, lib = api.PortOracle(), api.CudaLib()
+    o.init(mode=mode)
+    lib.init(mode=mode)
+    for t in range(4):
+        a = np.array([[o.lib.port_pairdistance(t, i, j) for j in range(128)] for i in range(128)])
+        b = np.array([[lib.lib.dpc_pairdistance(t, i, j) for j in range(128)] for i in range(128)])
+        assert (a == b).all()
+    assert lib.lib.dpc_pairdistance(0, ord("N"), ord("N")) == 3
+    assert lib.lib.dpc_pairdistance(0, ord("A"), ord("z")) == 0
+    assert lib.lib.dpc_pairdistance(0, ord("Z"), ord("Z")) == -3
+    assert lib.lib.dpc_pairdistance(3, ord("A"), ord("C")) == -5
+
+
+def test_pairdistance_matches_compiled_reference(ref):
+    lib = api.CudaLib()
+    lib.init(mode=0)
+    ref.init(mode=0)
+    for i in range(128):
+        for j in range(128):
+            assert ref.lib.ref_pairdistance(i, j) == lib.lib.dpc_pairdistance(0, i, j)   # Dynprog_pairdistance = HIGHQ table
