@@ -129,6 +129,7 @@ class Workload:
         self.blocks = np.zeros(int(lib.synth_genome_nwords(self.nbases)), dtype=np.uint32)
         lib.synth_genome(_ptr(self.blocks), self.nbases, seed, n_frac)
         self._keep = []
+        self.version = 0        # bumped whenever a generator plants splice sites into the genome
 
     @classmethod
     def from_ascii(cls, seq):
@@ -140,6 +141,7 @@ class Workload:
         self.blocks = np.zeros(int(lib.synth_genome_nwords(self.nbases)), dtype=np.uint32)
         lib.synth_genome_from_ascii(_ptr(self.blocks), seq.encode(), self.nbases)
         self._keep = []
+        self.version = 0
         return self
 
     def params(self, **kw):
@@ -184,6 +186,7 @@ class Workload:
         d.update(kw)
         sp = self.params(**d)
         per = 2 * (sp.long_hi if sp.long_frac > 0 else sp.len_hi) + 32
+        self.version = getattr(self, "version", 0) + 1     # plants GT..AG etc. into the genome
         return self._gen("synth_genome_gaps", n, per, sp)
 
     def cdna_gaps(self, n, extraband=7, **kw):
@@ -201,6 +204,7 @@ class Workload:
         s.splice_known = C.cast(splice_known, C.c_void_p).value if splice_known is not None else None
         s.user = None
         self._keep.append((splice_prob, splice_known))
+        s._workload = self
         return s
 
 
@@ -344,16 +348,24 @@ class CudaLib(_SolverLib):
         L.dpc_maxlengths.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
         self.ctx = None
 
+    _epoch = 0      # the library's init/setup state is process-wide: remember who registered last
+
     def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
+        self._init_args = (mode, maxlookback, extraquerygap, maxpeelback, end, paired)
         rc = self.lib.dpc_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
         if rc != 0:
             raise RuntimeError("dpc_init: %s" % self.lib.dpc_strerror(rc).decode())
+        CudaLib._epoch += 1
 
     def setup(self, setup):
         self._setup = setup
         rc = self.lib.dpc_setup(C.byref(setup))
         if rc != 0:
             raise RuntimeError("dpc_setup: %s" % self.lib.dpc_strerror(rc).decode())
+        wl = getattr(setup, "_workload", None)
+        self._genome_version = getattr(wl, "version", 0) if wl is not None else 0
+        CudaLib._epoch += 1
+        self._my_epoch = CudaLib._epoch
 
     def open(self, device=0):
         self.ctx = self.lib.dpc_ctx_new(device)
@@ -371,7 +383,20 @@ class CudaLib(_SolverLib):
             raise RuntimeError("%s: %s" % (what, self.lib.dpc_strerror(rc).decode()))
         return rc
 
+    def refresh_genome(self):
+        """The library mirrors the genome into HBM at dpc_setup; the synthetic generator for genome gaps
+        edits the host genome afterwards (planted splice sites), so register it again when that happened."""
+        wl = getattr(self._setup, "_workload", None)
+        if self._my_epoch != CudaLib._epoch:          # another wrapper re-initialised the shared library
+            mode, a, b, c, d, e = self._init_args
+            self.init(mode, a, b, c, d, e)
+            self.setup(self._setup)
+        elif wl is not None and getattr(wl, "version", 0) != self._genome_version:
+            self.setup(self._setup)
+
     def solve(self, problems, want_pairs=True):
+        self.refresh_genome()
+
         def fn(p, n, r, pr, cap, off):
             return self.lib.dpc_solve(self.ctx, p, n, r, pr, cap, off)
         return _solve_common(fn, problems, want_pairs)

@@ -13,6 +13,8 @@
 #include <stdint.h>
 #include <string.h>
 #include <ctype.h>
+#include <stdlib.h>
+#include <new>
 #include <vector>
 #include "../../include/dynprog_cuda.h"
 #include "dpc_core.h"
@@ -110,27 +112,93 @@ inline char host_genomic_nt(const dpc_problem_t &p, int genomicpos) {   /* get_g
   return compl_nt[dpc_genome_code(blocks, p.chroffset + p.chrpos + (p.genomiclength - 1) - (uint32_t)genomicpos)];
 }
 
+/* gathers get_genomic_nt(start +/- k) for k = 0..len-1 */
+inline void gather_genome(const dpc_problem_t &p, const uint32_t *blocks, int start, int len, bool rev, char *out) {
+  static const char fwd_nt[6] = { 'A', 'C', 'G', 'T', 'N', '*' }, compl_nt[6] = { 'T', 'G', 'C', 'A', 'N', '*' };
+  const bool star = allstar(p);
+  const uint32_t glen = p.genomiclength, base = p.chroffset + p.chrpos;
+  for (int k = 0; k < len; k++) {
+    int pos = rev ? start - k : start + k;
+    if (star || pos < 0 || (uint32_t)pos >= glen) out[k] = '*';
+    else if (p.watsonp) out[k] = fwd_nt[dpc_genome_code(blocks, base + (uint32_t)pos)];
+    else out[k] = compl_nt[dpc_genome_code(blocks, base + (glen - 1) - (uint32_t)pos)];
+  }
+}
+
+/* ---- growable buffers whose storage the CUDA side can make page-locked ------------------------ */
+struct Alloc { void *(*alloc)(size_t); void (*release)(void *); };
+inline Alloc default_alloc() { Alloc a = { malloc, free }; return a; }
+
+template <class T> struct PBuf {
+  T *p; size_t n, cap; Alloc al;
+  PBuf() : p(NULL), n(0), cap(0), al(default_alloc()) {}
+  ~PBuf() { if (p) al.release(p); }
+  void set_alloc(Alloc a) { if (p) al.release(p); p = NULL; n = cap = 0; al = a; }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    size_t nc = cap * 2 > want ? cap * 2 : want;
+    if (nc < 1024) nc = 1024;
+    T *q = (T *)al.alloc(nc * sizeof(T));
+    if (!q) throw std::bad_alloc();
+    if (n) memcpy(q, p, n * sizeof(T));
+    if (p) al.release(p);
+    p = q; cap = nc;
+  }
+  void clear() { n = 0; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T *data() { return p; }
+  const T *data() const { return p; }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
+  void push_back(const T &v) { if (n == cap) reserve(n + 1); p[n++] = v; }
+  T *grow(size_t k) { reserve(n + k); T *r = p + n; n += k; return r; }
+ private:
+  PBuf(const PBuf &); PBuf &operator=(const PBuf &);
+};
+
 /* ---- batch ---------------------------------------------------------------------------------- */
 struct HostProb {
-  dpc_problem_t p;      /* caller's problem; seq1 / seq1R are NOT valid after add (bytes live in the pool) */
   uint32_t q0, q1;      /* pool offsets: first byte of the copied span(s) */
+  uint32_t aux;         /* pool offset of probability / known-site arrays */
   int32_t dev;          /* index into the device arrays, -1 when resolved on the host (early returns) */
   int32_t L1, L2;       /* lengths after clipping (end gaps) */
-  uint32_t aux;         /* pool offset of probability / known-site arrays */
-  dpc_result_t res;
+};
+
+/* pair records are written through a bare cursor: every caller sizes the destination first */
+struct Out {
+  dpc_pair_t *p; int n;
+  void push(int qpos, int gpos, char cdna, char comp, char genome, int idx, int gapp) {
+    dpc_pair_t &pr = p[n++];
+    pr.querypos = qpos; pr.genomepos = gpos; pr.dynprogindex = idx;
+    pr.cdna = cdna; pr.comp = comp; pr.genome = genome; pr.gapp = (uint8_t)gapp;
+  }
+  void push_gapholder() { push(-1, -1, ' ', ' ', ' ', 0, 1); }       /* pairpool.c:352-401 */
+};
+
+/* per-thread scratch of the rebuild */
+struct Scratch {
+  std::vector<char> qa, ga, qb, gb;
+  std::vector<dpc_pair_t> sL, sR, out;
 };
 
 struct Batch {
   std::vector<HostProb> probs;
-  std::vector<uint8_t> pool;        /* query bytes + aux arrays; copied verbatim to the device */
-  std::vector<DevProb> dprobs;
+  PBuf<uint8_t> pool;               /* query bytes + aux arrays; copied verbatim to the device */
+  PBuf<DevProb> dprobs;
   std::vector<uint32_t> dev2host;
+  /* the caller's arrays (bulk API) or copies (ticket API) */
+  const dpc_problem_t *ext; dpc_result_t *ext_res;
+  std::vector<dpc_problem_t> own; std::vector<dpc_result_t> own_res;
 
-  void clear() { probs.clear(); pool.clear(); dprobs.clear(); dev2host.clear(); }
+  Batch() : ext(NULL), ext_res(NULL) {}
+  void clear() { probs.clear(); pool.clear(); dprobs.clear(); dev2host.clear(); own.clear(); own_res.clear(); ext = NULL; ext_res = NULL; }
+  const dpc_problem_t &P(int i) const { return ext ? ext[i] : own[i]; }
+  dpc_result_t &R(int i) { return ext_res ? ext_res[i] : own_res[i]; }
 
   uint32_t pool_put(const char *src, int n) {
     uint32_t at = (uint32_t)pool.size();
-    pool.insert(pool.end(), (const uint8_t *)src, (const uint8_t *)src + n);
+    memcpy(pool.grow((size_t)n), src, (size_t)n);
     return at;
   }
   void pool_align(size_t a) { while (pool.size() % a) pool.push_back(0); }
@@ -147,8 +215,9 @@ struct Batch {
     return defect_rate < 0.003 ? HIGHQ : defect_rate < 0.014 ? MEDQ : LOWQ;
   }
   static bool alphabet_ok(const char *s, int n) {
-    for (int i = 0; i < n; i++) if ((unsigned char)s[i] >= 128) return false;
-    return true;
+    unsigned char acc = 0;
+    for (int i = 0; i < n; i++) acc |= (unsigned char)s[i];
+    return acc < 128;
   }
   static bool segment_ok(const dpc_problem_t &p) {
     if (allstar(p)) return true;
@@ -182,20 +251,38 @@ struct Batch {
     return s.splice_prob(which, p.chroffset + pos, p.chroffset, s.user);
   }
 
+  /* ticket API: copies the problem */
+  int add(const dpc_problem_t &in) {
+    if (ext) return DPC_ERR_STATE;
+    own.push_back(in);
+    own_res.push_back(dpc_result_t());
+    int rc = add_impl(own.back(), own_res.back());
+    if (rc < 0) { own.pop_back(); own_res.pop_back(); }
+    return rc;
+  }
+  /* bulk API: the caller's arrays stay valid until the results are out */
+  int add_ext(const dpc_problem_t *problems, dpc_result_t *results, int n) {
+    if (!probs.empty()) return DPC_ERR_STATE;
+    ext = problems; ext_res = results;
+    probs.reserve((size_t)n); dprobs.reserve((size_t)n); dev2host.reserve((size_t)n);
+    for (int i = 0; i < n; i++) {
+      int rc = add_impl(problems[i], results[i]);
+      if (rc < 0) return rc;
+    }
+    return 0;
+  }
+
   /* Returns the ticket or a negative code.  Mirrors the argument checks and early returns of the
    * five reference entry points; everything that needs a matrix becomes a DevProb. */
-  int add(const dpc_problem_t &in) {
+  int add_impl(const dpc_problem_t &p, dpc_result_t &r) {
     Globals &g = G();
     if (!g.inited || !g.setup_done) return DPC_ERR_STATE;
     HostProb h;
-    memset(&h, 0, sizeof h);
-    h.p = in; h.dev = -1; h.L1 = in.length1; h.L2 = in.length2;
-    dpc_result_t &r = h.res;
-    result_init(r, in);
+    h.q0 = h.q1 = h.aux = 0; h.dev = -1; h.L1 = p.length1; h.L2 = p.length2;
+    result_init(r, p);
     DevProb d;
     memset(&d, 0, sizeof d);
     bool todev = false;
-    const dpc_problem_t &p = in;
     d.kind = (uint8_t)p.kind; d.endalign = (uint8_t)p.endalign;
     d.gbase = p.chroffset + p.chrpos; d.glen = p.genomiclength;
     d.extraband = p.extraband; d.cdna_direction = (int8_t)(p.cdna_direction > 0 ? 1 : p.cdna_direction < 0 ? -1 : 0);
@@ -265,7 +352,6 @@ struct Batch {
         break;
       }
       if (L2L <= 0 || L2R <= 0 || L2L < L1 - 1 || L2R < L1 - 1) return DPC_ERR_ARG;
-      if (!g.setup.novelsplicingp && g.setup.splice_known == NULL && false) return DPC_ERR_UNSUPPORTED;
       if ((p.finalp || p.use_probabilities_p) && g.setup.splice_prob == NULL) return DPC_ERR_STATE;
       if (!alphabet_ok(p.seq1, L1)) return DPC_ERR_ALPHABET;
       d.type = (uint8_t)quality(p.defect_rate);
@@ -329,17 +415,9 @@ struct Batch {
   }
 
   /* ---- rebuild of the Pair records (dynprog.c:2372-2712 and the assembly in each entry point) */
-  typedef std::vector<dpc_pair_t> Stack;
-  static void push(Stack &s, int qpos, int gpos, char cdna, char comp, char genome, int idx, int gapp) {
-    dpc_pair_t pr;
-    pr.querypos = qpos; pr.genomepos = gpos; pr.dynprogindex = idx;
-    pr.cdna = cdna; pr.comp = comp; pr.genome = genome; pr.gapp = (uint8_t)gapp;
-    s.push_back(pr);
-  }
-  static void push_gapholder(Stack &s) { push(s, -1, -1, ' ', ' ', ' ', 0, 1); }   /* pairpool.c:352-401 */
 
   /* One matrix: replays the ops from (r,c).  qch / gch are in matrix order. */
-  static void replay(Stack &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
+  static void replay(Out &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
                      int q0, int g0, bool revp, bool genome_rows, int idx) {
     const int step = revp ? -1 : 1;
     const Globals &g = G();
@@ -349,81 +427,97 @@ struct Batch {
         for (int j = 0; j < len; j++) {
           int qi = (genome_rows ? c : r) - 1 - j, gi = (genome_rows ? r : c) - 1 - j;
           char c1 = qch[qi], c2 = gch[gi];
-          bool consistent = genome_rows ? g.CONS[c2 & 127][c1 & 127] : g.CONS[c1 & 127][c2 & 127];   /* 2654 vs 2752 */
           if (!genome_rows && c2 == '*') continue;                    /* 2644 */
-          char comp = (char)dpc_query_uc(c1) == c2 ? '*' : consistent ? ':' : ' ';
-          push(st, q0 + step * qi, g0 + step * gi, c1, comp, c2, idx, 0);
+          char comp = '*';
+          if ((char)dpc_query_uc(c1) != c2) {
+            bool consistent = genome_rows ? g.CONS[c2 & 127][c1 & 127] : g.CONS[c1 & 127][c2 & 127];   /* 2654 vs 2752 */
+            comp = consistent ? ':' : ' ';
+          }
+          st.push(q0 + step * qi, g0 + step * gi, c1, comp, c2, idx, 0);
         }
         r -= len; c -= len;
         continue;
       }
       bool along_cols = (op == DPC_OP_QSKIP) ? genome_rows : !genome_rows;
       if (along_cols) c -= len; else r -= len;
-      if (op == DPC_OP_GAPHOLDER) { push_gapholder(st); continue; }  /* 2507 */
+      if (op == DPC_OP_GAPHOLDER) { st.push_gapholder(); continue; }  /* 2507 */
       if (op == DPC_OP_GSKIP) {                                       /* add_genomeskip dashes, 2444-2505 */
         int lo = genome_rows ? r : c, qi2 = genome_rows ? c - 1 : r - 1;
         int qpos = revp ? q0 - qi2 : q0 + qi2 + 1;
         for (int j = 0; j < len; j++) {
           int gi2 = lo + len - 1 - j;
-          push(st, qpos, g0 + step * gi2, ' ', '-', gch[gi2], idx, 0);
+          st.push(qpos, g0 + step * gi2, ' ', '-', gch[gi2], idx, 0);
         }
       } else {                                                        /* add_queryskip, 2372-2413 */
         int lo = genome_rows ? c : r, gi2 = genome_rows ? r - 1 : c - 1;
         int gpos = revp ? g0 - gi2 : g0 + gi2 + 1;
         for (int j = 0; j < len; j++) {
           int qi2 = lo + len - 1 - j;
-          push(st, q0 + step * qi2, gpos, qch[qi2], '-', ' ', idx, 0);
+          st.push(q0 + step * qi2, gpos, qch[qi2], '-', ' ', idx, 0);
         }
       }
     }
   }
 
-  static void emit(Stack &out, const Stack &v, size_t from, bool reversed) {
-    size_t n = v.size() - from;
-    for (size_t i = 0; i < n; i++) out.push_back(v[from + (reversed ? n - 1 - i : i)]);
+  static void emit(Out &out, const dpc_pair_t *v, int n, bool reversed) {
+    if (!reversed) { if (n > 0) memcpy(out.p + out.n, v, (size_t)n * sizeof(dpc_pair_t)); out.n += n; }
+    else for (int i = 0; i < n; i++) out.p[out.n++] = v[n - 1 - i];
   }
+  static char *fit(std::vector<char> &v, int n) { if ((int)v.size() < n + 8) v.resize((size_t)n + 64); return v.data(); }
+  static dpc_pair_t *fit(std::vector<dpc_pair_t> &v, int n) { if ((int)v.size() < n + 8) v.resize((size_t)n + 64); return v.data(); }
 
-  /* Fills `out` with the pairs of problem i in the order of the List_T the reference returns. */
-  void rebuild(int i, const DevRes &dr, const uint16_t *ops, Stack &out) const {
+  /* Writes the pairs of problem i, in the order of the List_T the reference returns, to dst (which must
+   * hold max_pairs(i) records) and returns their number. */
+  int max_pairs(int i) const {
+    const dpc_problem_t &p = P(i);
     const HostProb &h = probs[i];
-    const dpc_problem_t &p = h.p;
+    switch (p.kind) {
+    case DPC_GENOME_GAP: return 2 * p.length1 + p.length2 + p.length2R + 8;
+    case DPC_CDNA_GAP: return p.length1 + p.length1R + 2 * p.length2 + 32;
+    default: return h.L1 + h.L2 + 8;
+    }
+  }
+  int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s) const {
+    const HostProb &h = probs[i];
+    const dpc_problem_t &p = P(i);
+    const uint32_t *blocks = G().setup.genome_blocks;
     const char *q = (const char *)&pool[h.q0];
-    std::vector<char> qa, ga, qb, gb;
-    Stack sL, sR;
-    out.clear();
+    Out out; out.p = dst; out.n = 0;
     switch (p.kind) {
     case DPC_SINGLE_GAP: {
-      ga.resize(h.L2);
-      for (int k = 0; k < h.L2; k++) ga[k] = host_genomic_nt(p, p.offset2 + k);
-      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga.data(), p.offset1, p.offset2, false, false, p.dynprogindex);
-      emit(out, sL, 0, false);                                         /* List_reverse of the pushed list, 4571 */
+      char *ga = fit(s.ga, h.L2);
+      gather_genome(p, blocks, p.offset2, h.L2, false, ga);
+      /* List_reverse of the pushed list (4571) = push order */
+      replay(out, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex);
       break;
     }
     case DPC_END5_GAP: case DPC_END3_GAP: {
       const bool five = p.kind == DPC_END5_GAP;
-      qa.resize(h.L1); ga.resize(h.L2);
+      char *qa = fit(s.qa, h.L1), *ga = fit(s.ga, h.L2);
       for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
-      for (int k = 0; k < h.L2; k++) ga[k] = host_genomic_nt(p, five ? p.offset2 - k : p.offset2 + k);
-      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa.data(), ga.data(), p.offset1, p.offset2, five, false, p.dynprogindex);
+      gather_genome(p, blocks, p.offset2, h.L2, five, ga);
+      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0;
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex);
       if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) break;   /* 5259 */
-      size_t first = 0;                                                /* 5265-5268 */
-      while (first < sL.size() && sL[first].comp == '-') first++;
-      emit(out, sL, first, five);                                      /* end5: List_reverse again 5283; end3: as is 5740 */
+      int first = 0;                                                   /* 5265-5268 */
+      while (first < sL.n && sL.p[first].comp == '-') first++;
+      emit(out, sL.p + first, sL.n - first, five);                     /* end5: List_reverse again 5283; end3: as is 5740 */
       break;
     }
     case DPC_GENOME_GAP: {
       if (!(dr.status & DPC_ST_OK)) break;
       const int L1 = p.length1, L2L = p.length2, L2R = p.length2R, revoffset1 = p.offset1 + L1 - 1;
-      qb.resize(L1); ga.resize(L2L); gb.resize(L2R);
+      char *qb = fit(s.qb, L1), *ga = fit(s.ga, L2L), *gb = fit(s.gb, L2R);
       for (int k = 0; k < L1; k++) qb[k] = q[L1 - 1 - k];
-      for (int k = 0; k < L2L; k++) ga[k] = host_genomic_nt(p, p.offset2 + k);
-      for (int k = 0; k < L2R; k++) gb[k] = host_genomic_nt(p, p.offset2R - k);
-      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb.data(), gb.data(), revoffset1, p.offset2R, true, false, p.dynprogindex);
-      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga.data(), p.offset1, p.offset2, false, false, p.dynprogindex);
-      if (sR.size() + sL.size() > 0) {                                 /* List_length == 1 -> NULL, 5051 */
-        emit(out, sR, 0, true);
-        push_gapholder(out);
-        emit(out, sL, 0, false);
+      gather_genome(p, blocks, p.offset2, L2L, false, ga);
+      gather_genome(p, blocks, p.offset2R, L2R, true, gb);
+      Out sR, sL; sR.p = fit(s.sR, L1 + L2R + 2); sR.n = 0; sL.p = fit(s.sL, L1 + L2L + 2); sL.n = 0;
+      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, revoffset1, p.offset2R, true, false, p.dynprogindex);
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex);
+      if (sR.n + sL.n > 0) {                                           /* List_length == 1 -> NULL, 5051 */
+        emit(out, sR.p, sR.n, true);
+        out.push_gapholder();
+        emit(out, sL.p, sL.n, false);
       }
       break;
     }
@@ -431,39 +525,42 @@ struct Batch {
       if (!(dr.status & DPC_ST_OK)) break;
       const int L1L = p.length1, L1R = p.length1R, L2 = p.length2, revoffset2 = p.offset2 + L2 - 1;
       const int span = p.offset1R - p.offset1 + 1;
-      qb.resize(L1R); ga.resize(L2); gb.resize(L2);
+      char *qb = fit(s.qb, L1R), *ga = fit(s.ga, L2), *gb = fit(s.gb, L2);
       for (int k = 0; k < L1R; k++) qb[k] = q[span - 1 - k];
-      for (int k = 0; k < L2; k++) { ga[k] = host_genomic_nt(p, p.offset2 + k); gb[k] = host_genomic_nt(p, revoffset2 - k); }
-      Stack mid;
-      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb.data(), gb.data(), p.offset1R, revoffset2, true, true, p.dynprogindex);
+      gather_genome(p, blocks, p.offset2, L2, false, ga);
+      gather_genome(p, blocks, revoffset2, L2, true, gb);
+      Out sR, sL; sR.p = fit(s.sR, L1R + L2 + 2); sR.n = 0; sL.p = fit(s.sL, L1L + L2 + 2); sL.n = 0;
+      dpc_pair_t midbuf[24];
+      Out mid; mid.p = midbuf; mid.n = 0;
+      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, p.offset1R, revoffset2, true, true, p.dynprogindex);
       int queryjump = (p.offset1R - dr.bestcR) - (p.offset1 + dr.bestcL) + 1;     /* 4725-4726 */
       int genomejump = (revoffset2 - dr.bestrR) - (p.offset2 + dr.bestrL) + 1;
       if (queryjump == 9 && genomejump == 9) {                         /* INSERT_PAIRS, 4730-4751 */
         for (int k = p.offset1R - dr.bestcR; k >= p.offset1 + dr.bestcL; k--)
-          push(mid, k, revoffset2 - dr.bestrR + 1, q[k - p.offset1], '~', ' ', p.dynprogindex, 0);
+          mid.push(k, revoffset2 - dr.bestrR + 1, q[k - p.offset1], '~', ' ', p.dynprogindex, 0);
         for (int k = revoffset2 - dr.bestrR; k >= p.offset2 + dr.bestrL; k--)
-          push(mid, p.offset1 + dr.bestcL, k, ' ', '~', ga[k - p.offset2], p.dynprogindex, 0);
+          mid.push(p.offset1 + dr.bestcL, k, ' ', '~', ga[k - p.offset2], p.dynprogindex, 0);
       } else {
-        push_gapholder(mid);
+        mid.push_gapholder();
       }
-      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga.data(), p.offset1, p.offset2, false, true, p.dynprogindex);
-      (void)L1L;
-      if (sR.size() + mid.size() + sL.size() != 1) {                   /* 4784-4787 */
-        emit(out, sR, 0, true);
-        emit(out, mid, 0, false);
-        emit(out, sL, 0, false);
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, true, p.dynprogindex);
+      if (sR.n + mid.n + sL.n != 1) {                                  /* 4784-4787 */
+        emit(out, sR.p, sR.n, true);
+        emit(out, mid.p, mid.n, false);
+        emit(out, sL.p, sL.n, false);
       }
       break;
     }
     default: break;
     }
+    return out.n;
   }
 
   /* Turns the device record of problem i into the reference's output parameters. */
-  void finalize(int i, const DevRes &dr, const uint16_t *ops) {
-    HostProb &h = probs[i];
-    const dpc_problem_t &p = h.p;
-    dpc_result_t &r = h.res;
+  void finalize(int i, const DevRes &dr, const uint16_t *ops, Scratch &s) {
+    const dpc_problem_t &p = P(i);
+    dpc_result_t &r = R(i);
+    const HostProb &h = probs[i];
     int npairs = -1;     /* -1: count by rebuilding */
     /* pairs pushed = aligned columns that are not '*' + dashes + gapholders */
     int pushed = dr.nmatches + dr.nmismatches;
@@ -523,7 +620,7 @@ struct Batch {
     }
     default: break;
     }
-    if (npairs < 0) { Stack out; rebuild(i, dr, ops, out); npairs = (int)out.size(); }
+    if (npairs < 0) npairs = rebuild(i, dr, ops, fit(s.out, max_pairs(i)), s);
     r.npairs = npairs;
     r.null_list = npairs == 0;
   }

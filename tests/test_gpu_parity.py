@@ -104,8 +104,6 @@ def test_known_splice_sites(workload, prob_hook):
             assert not api.compare(*o.solve(probs), *lib.solve(probs), rtol=RTOL)
         finally:
             lib.close()
-    lib = api.CudaLib()     # restore the session-wide setup
-    lib.init()
 
 
 def test_empty_and_degenerate_batches(workload, port, cuda):
@@ -121,6 +119,7 @@ def test_ticket_api_equals_bulk_api(workload, cuda):
     probs = mixed_problems(workload, 200, 77)
     want_res, want_pairs, want_off = cuda.solve(probs)
     L = cuda.lib
+    cuda.refresh_genome()
     assert L.dpc_reset(cuda.ctx) == 0
     tickets = [L.dpc_add(cuda.ctx, probs[i:i + 1].ctypes.data_as(C.c_void_p)) for i in range(len(probs))]
     assert tickets == list(range(len(probs)))
