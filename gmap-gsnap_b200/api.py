@@ -338,6 +338,9 @@ class CudaLib(_SolverLib):
         L.dpc_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.dpc_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.dpc_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.dpc_sync.argtypes = [C.c_void_p]
+        L.dpc_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.dpc_set_fill.argtypes = [C.c_int]
         L.dpc_stream.restype = C.c_void_p
         L.dpc_stream.argtypes = [C.c_void_p]
         L.dpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
@@ -400,6 +403,20 @@ class CudaLib(_SolverLib):
         def fn(p, n, r, pr, cap, off):
             return self.lib.dpc_solve(self.ctx, p, n, r, pr, cap, off)
         return _solve_common(fn, problems, want_pairs)
+
+    def load(self, problems):
+        """Ticket-API path on the context's own stream: add_bulk + flush + wait.  Leaves the batch resident in
+        HBM (dpc_relaunch re-runs its kernels) and returns the results."""
+        self.refresh_genome()
+        L = self.lib
+        self.check(L.dpc_reset(self.ctx), "dpc_reset")
+        self.check(L.dpc_add_bulk(self.ctx, _ptr(problems), len(problems)), "dpc_add_bulk")
+        self.check(L.dpc_flush(self.ctx), "dpc_flush")
+        self.check(L.dpc_wait(self.ctx), "dpc_wait")
+        res = np.zeros(len(problems), dtype=RESULT_DT)
+        for i in range(len(problems)) if len(problems) <= 4096 else ():
+            L.dpc_result(self.ctx, i, res[i:i + 1].ctypes.data_as(C.c_void_p))
+        return res
 
     def stats(self):
         s = Stats()

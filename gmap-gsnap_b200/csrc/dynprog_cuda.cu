@@ -11,7 +11,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "dpc_host.h"
@@ -113,7 +117,7 @@ static int ensure_device(int dev) {
   return DPC_OK;
 }
 
-/* ---- context -------------------------------------------------------------------------------- */
+/* ---- buffers -------------------------------------------------------------------------------- */
 template <class T> struct DBuf {
   T *p; size_t cap;
   DBuf() : p(NULL), cap(0) {}
@@ -128,20 +132,13 @@ template <class T> struct DBuf {
   }
   void release() { if (p) cudaFree(p); p = NULL; cap = 0; }
 };
-template <class T> struct HBuf {   /* pinned */
-  T *p; size_t cap;
-  HBuf() : p(NULL), cap(0) {}
-  int need(size_t n) {
-    if (n <= cap) return DPC_OK;
-    if (p) cudaFreeHost(p);
-    p = NULL; cap = 0;
-    size_t want = n + n / 4 + 1024;
-    if (cudaMallocHost(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return DPC_ERR_NOMEM; }
-    cap = want;
-    return DPC_OK;
-  }
-  void release() { if (p) cudaFreeHost(p); p = NULL; cap = 0; }
-};
+static void *pinned_alloc(size_t n) {
+  void *p = NULL;
+  if (cudaMallocHost(&p, n) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  return p;
+}
+static void pinned_release(void *p) { cudaFreeHost(p); }
+static Alloc pinned() { Alloc a = { pinned_alloc, pinned_release }; return a; }
 
 struct ClassLaunch {
   bool smem;
@@ -155,10 +152,12 @@ struct ClassLaunch {
 static const uint32_t k_class_bytes[NCLASS] = { 3 << 10, 6 << 10, 12 << 10, 24 << 10, 48 << 10, 96 << 10, 192 << 10, 0 };
 #define SCRATCH_BUDGET (6ull << 30)
 
-struct dpc_ctx {
+/* ---- engine: one stream, its device buffers and the batch in flight on it -------------------- */
+struct Engine {
   int device;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
+  bool live;
   Batch batch;
   DBuf<DevProb> d_probs;
   DBuf<uint8_t> d_pool, d_scratch;
@@ -166,49 +165,251 @@ struct dpc_ctx {
   DBuf<uint32_t> d_list;
   DBuf<uint16_t> d_ovf;
   DBuf<unsigned int> d_counters;
-  HBuf<DevRes> h_res;
-  HBuf<uint16_t> h_ovf;
-  HBuf<unsigned int> h_counters;
-  std::vector<uint32_t> list;
+  PBuf<DevRes> h_res;
+  PBuf<uint16_t> h_ovf;
+  PBuf<unsigned int> h_counters;
+  PBuf<uint32_t> list;
+  std::vector<uint8_t> cls;
   std::vector<ClassLaunch> launches;
+  Scratch scratch;
   size_t ovf_cap;
   bool flushed, waited;
   int nlaunch;
   float ms_total;
   int64_t h2d_bytes, d2h_bytes;
-  int err;
+
+  Engine() : device(0), stream(0), ev0(0), ev1(0), live(false), ovf_cap(0), flushed(false), waited(false), nlaunch(0),
+             ms_total(0), h2d_bytes(0), d2h_bytes(0) {}
+
+  int open(int dev) {
+    device = dev;
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    batch.pool.set_alloc(pinned()); batch.dprobs.set_alloc(pinned());
+    h_res.set_alloc(pinned()); h_ovf.set_alloc(pinned()); h_counters.set_alloc(pinned()); list.set_alloc(pinned());
+    live = true;
+    return DPC_OK;
+  }
+  void close() {
+    if (!live) return;
+    cudaSetDevice(device);
+    cudaStreamSynchronize(stream);
+    d_probs.release(); d_pool.release(); d_scratch.release(); d_res.release(); d_list.release();
+    d_ovf.release(); d_counters.release();
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaStreamDestroy(stream);
+    live = false;
+  }
+  ~Engine() { close(); }
+
+  int reset() {
+    if (flushed && !waited) { cudaSetDevice(device); cudaStreamSynchronize(stream); }
+    batch.clear();
+    flushed = waited = false;
+    return DPC_OK;
+  }
+
+  int launch_all() {
+    DeviceState &d = g_dev[device];
+    const size_t ncnt = launches.size() + 1;
+    CK(cudaMemsetAsync(d_counters.p, 0, ncnt * sizeof(unsigned int), stream));
+    CK(cudaEventRecord(ev0, stream));
+    nlaunch = 0;
+    for (size_t k = 0; k < launches.size(); k++) {
+      const ClassLaunch &L = launches[k];
+      KernelArgs a;
+      a.probs = d_probs.p; a.list = d_list.p + L.list_off; a.n = L.n;
+      a.pool = d_pool.p; a.blocks = d.d_blocks; a.tables = d.d_tables; a.res = d_res.p;
+      a.ovf.ops = d_ovf.p; a.ovf.used = d_counters.p; a.ovf.cap = (unsigned int)ovf_cap;
+      a.scratch = d_scratch.p; a.arena_bytes = L.arena_bytes; a.counter = d_counters.p + 1 + k;
+      a.force_generic = g_force_generic;
+      const int threads = L.wpb * 32;
+      const size_t smem = L.smem ? (size_t)L.wpb * L.arena_bytes : 0;
+      int per_sm = 1;
+      if (L.smem) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dpc_solve_kernel<true>, threads, smem)); }
+      else { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dpc_solve_kernel<false>, threads, 0)); }
+      if (per_sm < 1) per_sm = 1;
+      int grid = (L.n + L.wpb - 1) / L.wpb;
+      if (grid > d.sm_count * per_sm) grid = d.sm_count * per_sm;
+      if (L.smem) dpc_solve_kernel<true><<<grid, threads, smem, stream>>>(a);
+      else dpc_solve_kernel<false><<<grid, threads, 0, stream>>>(a);
+      CK(cudaGetLastError());
+      nlaunch++;
+    }
+    CK(cudaEventRecord(ev1, stream));
+    return DPC_OK;
+  }
+
+  /* H2D + kernels + D2H, all asynchronous on this engine's stream */
+  int flush() {
+    if (flushed) return DPC_ERR_STATE;
+    CK(cudaSetDevice(device));
+    DeviceState &d = g_dev[device];
+    Batch &b = batch;
+    const size_t n = b.dprobs.size();
+    flushed = true; waited = false;
+    launches.clear();
+    h2d_bytes = d2h_bytes = 0;
+    if (n == 0) return DPC_OK;
+
+    /* bin the problems by arena size; oversize ones get HBM scratch */
+    const int with_state = g_force_generic ? 1 : 2;   /* must match FILL::needs_state of the kernel */
+    const uint32_t smem_limit = (uint32_t)(d.max_smem - (int)sizeof(DevTables) - 2048);
+    cls.resize(n);
+    size_t count[NCLASS] = { 0 };
+    uint64_t scratch_total = 0, ovf_worst = 0;
+    for (size_t i = 0; i < n; i++) {
+      DevProb &p = b.dprobs[i];
+      int k = 0;
+      if (!((p.kind == DPC_END5_GAP || p.kind == DPC_END3_GAP) && p.endalign == DPC_QUERYEND_NOGAPS)) {
+        ArenaLayout a;
+        dpc_layout(p, a, with_state);
+        for (k = 0; k < NCLASS - 1; k++) if (a.total <= k_class_bytes[k] && k_class_bytes[k] <= smem_limit) break;
+        if (k == NCLASS - 1) {
+          if (scratch_total + a.total > SCRATCH_BUDGET) return DPC_ERR_NOMEM;
+          p.scratch_lo = (uint32_t)scratch_total; p.scratch_hi = (uint32_t)(scratch_total >> 32);
+          scratch_total += a.total;
+        }
+        uint64_t worst = 0;
+        for (int m = 0; m < a.nmat; m++) worst += (uint64_t)(a.d[m].rows + a.d[m].cols + 2);
+        if (worst > DPC_INLINE_OPS) ovf_worst += worst;
+      }
+      cls[i] = (uint8_t)k;
+      count[k]++;
+    }
+    list.clear();
+    list.grow(n);
+    size_t off[NCLASS], at = 0;
+    for (int k = 0; k < NCLASS; k++) { off[k] = at; at += count[k]; }
+    {
+      size_t cur[NCLASS];
+      for (int k = 0; k < NCLASS; k++) cur[k] = off[k];
+      for (size_t i = 0; i < n; i++) list[cur[cls[i]]++] = (uint32_t)i;
+    }
+    for (int k = 0; k < NCLASS; k++) {
+      if (!count[k]) continue;
+      ClassLaunch L;
+      L.smem = k < NCLASS - 1;
+      L.arena_bytes = k_class_bytes[k];
+      L.wpb = 8;
+      if (L.smem) { while (L.wpb > 1 && (uint64_t)L.wpb * L.arena_bytes > smem_limit) L.wpb >>= 1; }
+      else L.wpb = 4;
+      L.list_off = off[k]; L.n = (int)count[k];
+      launches.push_back(L);
+    }
+    /* ops overflow arena: problems whose worst case exceeds the inline slots (bounded) */
+    if (ovf_worst > (1ull << 30)) ovf_worst = 1ull << 30;
+    ovf_cap = (size_t)ovf_worst + 64;
+
+    b.pool_align(16);
+    int rc;
+    if ((rc = d_probs.need(n)) || (rc = d_pool.need(b.pool.size())) || (rc = d_res.need(n)) ||
+        (rc = d_list.need(n)) || (rc = d_ovf.need(ovf_cap)) || (rc = d_counters.need(NCLASS + 2)) ||
+        (rc = d_scratch.need((size_t)scratch_total + 16)))
+      return rc;
+    h_res.clear(); h_res.grow(n);
+    h_counters.clear(); h_counters.grow(NCLASS + 2);
+    CK(cudaMemcpyAsync(d_probs.p, b.dprobs.data(), n * sizeof(DevProb), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_pool.p, b.pool.data(), b.pool.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_list.p, list.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    h2d_bytes = (int64_t)(n * sizeof(DevProb) + b.pool.size() + n * sizeof(uint32_t));
+    if ((rc = launch_all()) != DPC_OK) return rc;
+    CK(cudaMemcpyAsync(h_res.data(), d_res.p, n * sizeof(DevRes), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_counters.data(), d_counters.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    d2h_bytes = (int64_t)(n * sizeof(DevRes) + sizeof(unsigned int));
+    return DPC_OK;
+  }
+
+  const uint16_t *ops_of(const DevRes &dr) const {
+    return (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? h_ovf.data() + dr.ovf : dr.ops;
+  }
+
+  /* blocks until the batch is back, then turns every device record into the reference's outputs */
+  int wait() {
+    if (!flushed) return DPC_ERR_STATE;
+    if (waited) return DPC_OK;
+    Batch &b = batch;
+    const size_t n = b.dprobs.size();
+    if (n > 0) {
+      CK(cudaSetDevice(device));
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaEventElapsedTime(&ms_total, ev0, ev1));
+      unsigned int used = h_counters[0];
+      if (used > 0) {
+        if (used > ovf_cap) return DPC_ERR_NOMEM;
+        h_ovf.clear(); h_ovf.grow(used);
+        CK(cudaMemcpyAsync(h_ovf.data(), d_ovf.p, used * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        d2h_bytes += (int64_t)used * 2;
+      }
+      for (size_t k = 0; k < n; k++) {
+        const DevRes &dr = h_res[k];
+        if (!(dr.status & DPC_ST_DONE) || (dr.status & DPC_ST_OVF_LOST)) return DPC_ERR_CUDA;
+        b.finalize((int)b.dev2host[k], dr, ops_of(dr), scratch);
+      }
+    }
+    waited = true;
+    return DPC_OK;
+  }
+
+  int pairs_into(int ticket, dpc_pair_t *dst) {
+    const HostProb &h = batch.probs[ticket];
+    if (h.dev < 0) return 0;
+    const DevRes &dr = h_res[h.dev];
+    return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch);
+  }
 };
 
-static int launch_all(dpc_ctx *c) {
-  DeviceState &d = g_dev[c->device];
-  const size_t ncnt = c->launches.size() + 1;
-  CK(cudaMemsetAsync(c->d_counters.p, 0, ncnt * sizeof(unsigned int), c->stream));
-  CK(cudaEventRecord(c->ev0, c->stream));
-  c->nlaunch = 0;
-  for (size_t k = 0; k < c->launches.size(); k++) {
-    const ClassLaunch &L = c->launches[k];
-    KernelArgs a;
-    a.probs = c->d_probs.p; a.list = c->d_list.p + L.list_off; a.n = L.n;
-    a.pool = c->d_pool.p; a.blocks = d.d_blocks; a.tables = d.d_tables; a.res = c->d_res.p;
-    a.ovf.ops = c->d_ovf.p; a.ovf.used = c->d_counters.p; a.ovf.cap = (unsigned int)c->ovf_cap;
-    a.scratch = c->d_scratch.p; a.arena_bytes = L.arena_bytes; a.counter = c->d_counters.p + 1 + k;
-    a.force_generic = g_force_generic;
-    const int threads = L.wpb * 32;
-    const size_t smem = L.smem ? (size_t)L.wpb * L.arena_bytes : 0;
-    int per_sm = 1;
-    if (L.smem) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dpc_solve_kernel<true>, threads, smem)); }
-    else { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dpc_solve_kernel<false>, threads, 0)); }
-    if (per_sm < 1) per_sm = 1;
-    int grid = (L.n + L.wpb - 1) / L.wpb;
-    if (grid > d.sm_count * per_sm) grid = d.sm_count * per_sm;
-    if (L.smem) dpc_solve_kernel<true><<<grid, threads, smem, c->stream>>>(a);
-    else dpc_solve_kernel<false><<<grid, threads, 0, c->stream>>>(a);
-    CK(cudaGetLastError());
-    c->nlaunch++;
+/* ---- host worker threads of the bulk call -------------------------------------------------------- */
+struct Workers {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv, cv_done;
+  std::function<void(int)> fn;
+  std::atomic<int> next;
+  int njobs, active;
+  uint64_t gen;
+  bool stop;
+  explicit Workers(int n) : next(0), njobs(0), active(0), gen(0), stop(false) {
+    for (int t = 0; t < n; t++) th.emplace_back([this] { loop(); });
   }
-  CK(cudaEventRecord(c->ev1, c->stream));
-  return DPC_OK;
-}
+  ~Workers() {
+    { std::lock_guard<std::mutex> l(mu); stop = true; }
+    cv.notify_all();
+    for (auto &t : th) t.join();
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return stop || gen != seen; });
+        if (stop) return;
+        seen = gen;
+      }
+      for (int j; (j = next.fetch_add(1)) < njobs;) fn(j);
+      {
+        std::lock_guard<std::mutex> l(mu);
+        if (--active == 0) cv_done.notify_one();
+      }
+    }
+  }
+  void run(int jobs, const std::function<void(int)> &f) {
+    std::unique_lock<std::mutex> l(mu);
+    fn = f; njobs = jobs; next = 0; active = (int)th.size(); gen++;
+    cv.notify_all();
+    cv_done.wait(l, [&] { return active == 0; });
+  }
+};
+
+struct dpc_ctx {
+  Engine main;                       /* ticket API, dpc_relaunch */
+  std::vector<Engine *> subs;        /* bulk API: one engine per chunk in flight */
+  Workers *workers;
+  int nthreads;
+  dpc_ctx() : workers(NULL), nthreads(1) {}
+};
 
 /* ---- C ABI ---------------------------------------------------------------------------------- */
 extern "C" {
@@ -261,244 +462,219 @@ dpc_ctx_t *dpc_ctx_new(int device) {
   if (device < 0 || device >= dpc_device_count()) return NULL;
   if (ensure_device(device) != DPC_OK) return NULL;
   dpc_ctx *c = new dpc_ctx();
-  c->device = device; c->flushed = c->waited = false; c->err = 0; c->nlaunch = 0; c->ms_total = 0;
-  c->ovf_cap = 0; c->h2d_bytes = c->d2h_bytes = 0;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) { delete c; return NULL; }
+  if (c->main.open(device) != DPC_OK) { delete c; return NULL; }
+  int t = (int)std::thread::hardware_concurrency();
+  const char *e = getenv("DPC_HOST_THREADS");
+  if (e && atoi(e) > 0) t = atoi(e);
+  if (t < 1) t = 1;
+  if (t > 64) t = 64;
+  c->nthreads = t;
   return c;
 }
 
 void dpc_ctx_free(dpc_ctx_t *c) {
   if (!c) return;
-  cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  c->d_probs.release(); c->d_pool.release(); c->d_scratch.release(); c->d_res.release(); c->d_list.release();
-  c->d_ovf.release(); c->d_counters.release(); c->h_res.release(); c->h_ovf.release(); c->h_counters.release();
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
+  delete c->workers;
+  for (size_t i = 0; i < c->subs.size(); i++) delete c->subs[i];
   delete c;
 }
 
+int dpc_set_threads(dpc_ctx_t *c, int nthreads) {
+  if (!c || nthreads < 1 || nthreads > 64) return DPC_ERR_ARG;
+  if (c->workers && nthreads != c->nthreads) { delete c->workers; c->workers = NULL; }
+  c->nthreads = nthreads;
+  return DPC_OK;
+}
+
+#define GUARD(expr) do { try { expr; } catch (const std::bad_alloc &) { return DPC_ERR_NOMEM; } } while (0)
+
 int dpc_add(dpc_ctx_t *c, const dpc_problem_t *problem) {
   if (!c || !problem) return DPC_ERR_ARG;
-  if (c->flushed) return DPC_ERR_STATE;
-  return c->batch.add(*problem);
+  if (c->main.flushed) return DPC_ERR_STATE;
+  int rc = 0;
+  GUARD(rc = c->main.batch.add(*problem));
+  return rc;
 }
 
 int dpc_add_bulk(dpc_ctx_t *c, const dpc_problem_t *problems, int n) {
   if (!c || (!problems && n > 0) || n < 0) return DPC_ERR_ARG;
-  if (c->flushed) return DPC_ERR_STATE;
-  int first = (int)c->batch.probs.size();
-  c->batch.probs.reserve(c->batch.probs.size() + (size_t)n);
-  c->batch.dprobs.reserve(c->batch.dprobs.size() + (size_t)n);
-  for (int i = 0; i < n; i++) {
-    int t = c->batch.add(problems[i]);
-    if (t < 0) return t;
-  }
+  if (c->main.flushed) return DPC_ERR_STATE;
+  Batch &b = c->main.batch;
+  int first = (int)b.probs.size();
+  try {
+    b.probs.reserve(b.probs.size() + (size_t)n);
+    b.dprobs.reserve(b.dprobs.size() + (size_t)n);
+    for (int i = 0; i < n; i++) {
+      int t = b.add(problems[i]);
+      if (t < 0) return t;
+    }
+  } catch (const std::bad_alloc &) { return DPC_ERR_NOMEM; }
   return first;
 }
 
 int dpc_reset(dpc_ctx_t *c) {
   if (!c) return DPC_ERR_ARG;
-  cudaSetDevice(c->device);
-  if (c->flushed && !c->waited) cudaStreamSynchronize(c->stream);
-  c->batch.clear();
-  c->flushed = c->waited = false;
-  return DPC_OK;
+  return c->main.reset();
 }
 
 int dpc_flush(dpc_ctx_t *c) {
   if (!c) return DPC_ERR_ARG;
-  if (c->flushed) return DPC_ERR_STATE;
-  int rc = ensure_device(c->device);
+  int rc = ensure_device(c->main.device);
   if (rc != DPC_OK) return rc;
-  DeviceState &d = g_dev[c->device];
-  Batch &b = c->batch;
-  const size_t n = b.dprobs.size();
-  c->flushed = true; c->waited = false;
-  c->launches.clear();
-  c->h2d_bytes = c->d2h_bytes = 0;
-  if (n == 0) return DPC_OK;
-
-  /* bin the problems by arena size; oversize ones get HBM scratch */
-  const int with_state = g_force_generic ? 1 : 2;   /* must match FILL::needs_state of the kernel */
-  const uint32_t smem_limit = (uint32_t)(d.max_smem - (int)sizeof(DevTables) - 2048);
-  std::vector<uint8_t> cls(n);
-  size_t count[NCLASS] = { 0 };
-  uint64_t scratch_total = 0, ovf_worst = 0;
-  for (size_t i = 0; i < n; i++) {
-    DevProb &p = b.dprobs[i];
-    int k = NCLASS - 1;
-    if (!((p.kind == DPC_END5_GAP || p.kind == DPC_END3_GAP) && p.endalign == DPC_QUERYEND_NOGAPS)) {
-      ArenaLayout a;
-      dpc_layout(p, a, with_state);
-      for (k = 0; k < NCLASS - 1; k++) if (a.total <= k_class_bytes[k] && k_class_bytes[k] <= smem_limit) break;
-      if (k == NCLASS - 1) {
-        if (scratch_total + a.total > SCRATCH_BUDGET) return DPC_ERR_NOMEM;
-        p.scratch_lo = (uint32_t)scratch_total; p.scratch_hi = (uint32_t)(scratch_total >> 32);
-        scratch_total += a.total;
-      }
-      uint64_t worst = 0;
-      for (int m = 0; m < a.nmat; m++) worst += (uint64_t)(a.d[m].rows + a.d[m].cols + 2);
-      if (worst > DPC_INLINE_OPS) ovf_worst += worst;
-    } else k = 0;
-    cls[i] = (uint8_t)k;
-    count[k]++;
-  }
-  c->list.resize(n);
-  size_t off[NCLASS], at = 0;
-  for (int k = 0; k < NCLASS; k++) { off[k] = at; at += count[k]; }
-  {
-    size_t cur[NCLASS];
-    for (int k = 0; k < NCLASS; k++) cur[k] = off[k];
-    for (size_t i = 0; i < n; i++) c->list[cur[cls[i]]++] = (uint32_t)i;
-  }
-  for (int k = 0; k < NCLASS; k++) {
-    if (!count[k]) continue;
-    ClassLaunch L;
-    L.smem = k < NCLASS - 1;
-    L.arena_bytes = k_class_bytes[k];
-    L.wpb = 8;
-    if (L.smem) { while (L.wpb > 1 && (uint64_t)L.wpb * L.arena_bytes > smem_limit) L.wpb >>= 1; }
-    else L.wpb = 4;
-    L.list_off = off[k]; L.n = (int)count[k];
-    c->launches.push_back(L);
-  }
-  /* ops overflow arena: problems whose worst case exceeds the inline slots (bounded) */
-  if (ovf_worst > (1ull << 30)) ovf_worst = 1ull << 30;
-  c->ovf_cap = (size_t)ovf_worst + 64;
-
-  b.pool_align(16);
-  if ((rc = c->d_probs.need(n)) || (rc = c->d_pool.need(b.pool.size())) || (rc = c->d_res.need(n)) ||
-      (rc = c->d_list.need(n)) || (rc = c->d_ovf.need(c->ovf_cap)) || (rc = c->d_counters.need(NCLASS + 2)) ||
-      (rc = c->d_scratch.need((size_t)scratch_total + 16)) || (rc = c->h_res.need(n)) || (rc = c->h_counters.need(NCLASS + 2)))
-    return rc;
-  CK(cudaMemcpyAsync(c->d_probs.p, b.dprobs.data(), n * sizeof(DevProb), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_pool.p, b.pool.data(), b.pool.size(), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_list.p, c->list.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  c->h2d_bytes = (int64_t)(n * sizeof(DevProb) + b.pool.size() + n * sizeof(uint32_t));
-  if ((rc = launch_all(c)) != DPC_OK) return rc;
-  CK(cudaMemcpyAsync(c->h_res.p, c->d_res.p, n * sizeof(DevRes), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-  c->d2h_bytes = (int64_t)(n * sizeof(DevRes) + sizeof(unsigned int));
-  return DPC_OK;
+  GUARD(rc = c->main.flush());
+  return rc;
 }
 
 int dpc_wait(dpc_ctx_t *c) {
   if (!c) return DPC_ERR_ARG;
-  if (!c->flushed) return DPC_ERR_STATE;
-  if (c->waited) return DPC_OK;
-  Batch &b = c->batch;
-  const size_t n = b.dprobs.size();
-  if (n > 0) {
-    CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaEventElapsedTime(&c->ms_total, c->ev0, c->ev1));
-    unsigned int used = c->h_counters.p[0];
-    if (used > 0) {
-      if (used > c->ovf_cap) return DPC_ERR_NOMEM;
-      int rc = c->h_ovf.need(used);
-      if (rc) return rc;
-      CK(cudaMemcpy(c->h_ovf.p, c->d_ovf.p, used * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-      c->d2h_bytes += (int64_t)used * 2;
-    }
-    for (size_t k = 0; k < n; k++) {
-      const DevRes &dr = c->h_res.p[k];
-      if (!(dr.status & DPC_ST_DONE) || (dr.status & DPC_ST_OVF_LOST)) return DPC_ERR_CUDA;
-      const uint16_t *ops = (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? c->h_ovf.p + dr.ovf : dr.ops;
-      b.finalize((int)b.dev2host[k], dr, ops);
-    }
-  }
-  c->waited = true;
-  return DPC_OK;
+  int rc = 0;
+  GUARD(rc = c->main.wait());
+  return rc;
 }
 
 int dpc_result(dpc_ctx_t *c, int ticket, dpc_result_t *out) {
   if (!c || !out) return DPC_ERR_ARG;
-  if (!c->waited || ticket < 0 || ticket >= (int)c->batch.probs.size()) return DPC_ERR_STATE;
-  *out = c->batch.probs[ticket].res;
+  if (!c->main.waited || ticket < 0 || ticket >= (int)c->main.batch.probs.size()) return DPC_ERR_STATE;
+  *out = c->main.batch.R(ticket);
   return DPC_OK;
-}
-
-static int pairs_of(dpc_ctx *c, int ticket, Batch::Stack &st) {
-  const HostProb &h = c->batch.probs[ticket];
-  st.clear();
-  if (h.dev < 0) return 0;
-  const DevRes &dr = c->h_res.p[h.dev];
-  const uint16_t *ops = (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? c->h_ovf.p + dr.ovf : dr.ops;
-  c->batch.rebuild(ticket, dr, ops, st);
-  return (int)st.size();
 }
 
 int dpc_pairs(dpc_ctx_t *c, int ticket, dpc_pair_t *out, int cap) {
   if (!c) return DPC_ERR_ARG;
-  if (!c->waited || ticket < 0 || ticket >= (int)c->batch.probs.size()) return DPC_ERR_STATE;
-  Batch::Stack st;
-  int n = pairs_of(c, ticket, st);
+  Engine &e = c->main;
+  if (!e.waited || ticket < 0 || ticket >= (int)e.batch.probs.size()) return DPC_ERR_STATE;
+  int n = e.batch.R(ticket).npairs;
   if (n > cap || (n > 0 && !out)) return DPC_ERR_ARG;
-  if (n) memcpy(out, st.data(), (size_t)n * sizeof(dpc_pair_t));
-  return n;
+  if (n == 0) return 0;
+  int k = 0;
+  try {
+    dpc_pair_t *tmp = Batch::fit(e.scratch.out, e.batch.max_pairs(ticket));
+    k = e.pairs_into(ticket, tmp);
+    memcpy(out, tmp, (size_t)k * sizeof(dpc_pair_t));
+  } catch (const std::bad_alloc &) { return DPC_ERR_NOMEM; }
+  return k;
 }
 
+/* Bulk call: the problems are cut into chunks; host threads pack a chunk, queue its copies and kernels on
+ * the chunk's own stream, and finalise it when it is back, so packing, PCIe traffic, kernels and Pair
+ * rebuild of different chunks overlap.  Results and pairs come out in input order. */
 int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *results,
               dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off) {
-  int rc;
   if (!c || n < 0 || (n > 0 && (!problems || !results))) return DPC_ERR_ARG;
-  if ((rc = dpc_reset(c)) < 0) return rc;
-  if ((rc = dpc_add_bulk(c, problems, n)) < 0) return rc;
-  if ((rc = dpc_flush(c)) < 0) return rc;
-  if ((rc = dpc_wait(c)) < 0) return rc;
-  int64_t used = 0;
-  Batch::Stack st;
-  for (int i = 0; i < n; i++) {
-    results[i] = c->batch.probs[i].res;
-    if (pair_off) pair_off[i] = used;
-    if (pairs) {
-      int k = pairs_of(c, i, st);
-      if (used + k > pair_cap) return DPC_ERR_NOMEM;
-      if (k) memcpy(pairs + used, st.data(), (size_t)k * sizeof(dpc_pair_t));
-      used += k;
-    } else used += results[i].npairs;
+  int rc = ensure_device(c->main.device);
+  if (rc != DPC_OK) return rc;
+  const int device = c->main.device;
+  const int T = c->nthreads;
+  if (!c->workers) c->workers = new Workers(T);
+  int chunk = n / (4 * T) + 1;
+  if (chunk < 2048) chunk = 2048;
+  if (chunk > 32768) chunk = 32768;
+  const int nchunks = (n + chunk - 1) / chunk;
+  const int wave = 4 * T;                                     /* engines (chunks in flight) per wave */
+  while ((int)c->subs.size() < std::min(nchunks, wave)) {
+    Engine *e = new Engine();
+    if (e->open(device) != DPC_OK) { delete e; return DPC_ERR_CUDA; }
+    c->subs.push_back(e);
   }
-  if (pair_off) pair_off[n] = used;
+  std::atomic<int> err(0);
+  int64_t pair_base = 0;
+  for (int c0 = 0; c0 < nchunks; c0 += wave) {
+    const int nc = std::min(wave, nchunks - c0);
+    /* phase A: pack, solve on the device, finalise */
+    c->workers->run(nc, [&](int j) {
+      if (err.load()) return;
+      Engine &e = *c->subs[j];
+      const int lo = (c0 + j) * chunk, cnt = std::min(chunk, n - lo);
+      int r = 0;
+      try {
+        cudaSetDevice(device);
+        e.reset();
+        r = e.batch.add_ext(problems + lo, results + lo, cnt);
+        if (r >= 0) r = e.flush();
+        if (r >= 0) r = e.wait();
+      } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
+      if (r < 0) { int z = 0; err.compare_exchange_strong(z, r); }
+    });
+    if (err.load()) return err.load();
+    const int lo = c0 * chunk, hi = std::min(n, (c0 + nc) * chunk);
+    const int64_t wave_base = pair_base;
+    if (pair_off) for (int i = lo; i < hi; i++) { pair_off[i] = pair_base; pair_base += results[i].npairs; }
+    else for (int i = lo; i < hi; i++) pair_base += results[i].npairs;
+    if (pairs) {
+      if (pair_base > pair_cap) return DPC_ERR_NOMEM;
+      /* phase B: rebuild the Pair records of each chunk straight into the caller's array */
+      std::vector<int64_t> chunk_base((size_t)nc + 1);
+      chunk_base[0] = wave_base;
+      for (int j = 0; j < nc; j++) {
+        const int l = (c0 + j) * chunk, h = std::min(n, l + chunk);
+        int64_t s = 0;
+        for (int i = l; i < h; i++) s += results[i].npairs;
+        chunk_base[(size_t)j + 1] = chunk_base[(size_t)j] + s;
+      }
+      c->workers->run(nc, [&](int j) {
+        if (err.load()) return;
+        Engine &e = *c->subs[j];
+        const int l = (c0 + j) * chunk, cnt = std::min(chunk, n - l);
+        int64_t at = chunk_base[(size_t)j];
+        try {
+          for (int i = 0; i < cnt; i++) {
+            const int np = results[l + i].npairs;
+            if (np == 0) continue;
+            int k;
+            if (at + e.batch.max_pairs(i) <= pair_cap) k = e.pairs_into(i, pairs + at);     /* room for the worst case */
+            else {
+              dpc_pair_t *tmp = Batch::fit(e.scratch.out, e.batch.max_pairs(i));
+              k = e.pairs_into(i, tmp);
+              memcpy(pairs + at, tmp, (size_t)k * sizeof(dpc_pair_t));
+            }
+            if (k != np) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_STATE); return; }
+            at += k;
+          }
+        } catch (const std::bad_alloc &) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_NOMEM); }
+      });
+      if (err.load()) return err.load();
+    }
+  }
+  if (pair_off) pair_off[n] = pair_base;
   return DPC_OK;
 }
 
 int dpc_relaunch(dpc_ctx_t *c) {
   if (!c) return DPC_ERR_ARG;
-  if (!c->flushed || !c->waited) return DPC_ERR_STATE;
-  if (c->batch.dprobs.empty()) return 0;
-  CK(cudaSetDevice(c->device));
-  int rc = launch_all(c);
+  Engine &e = c->main;
+  if (!e.flushed || !e.waited) return DPC_ERR_STATE;
+  if (e.batch.dprobs.empty()) return 0;
+  CK(cudaSetDevice(e.device));
+  int rc = e.launch_all();
   if (rc != DPC_OK) return rc;
-  return c->nlaunch;
+  return e.nlaunch;
 }
 
-void *dpc_stream(dpc_ctx_t *c) { return c ? (void *)c->stream : NULL; }
+void *dpc_stream(dpc_ctx_t *c) { return c ? (void *)c->main.stream : NULL; }
 
 int dpc_sync(dpc_ctx_t *c) {
   if (!c) return DPC_ERR_ARG;
-  CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaEventElapsedTime(&c->ms_total, c->ev0, c->ev1));
+  Engine &e = c->main;
+  CK(cudaSetDevice(e.device));
+  CK(cudaStreamSynchronize(e.stream));
+  if (e.flushed && !e.batch.dprobs.empty()) CK(cudaEventElapsedTime(&e.ms_total, e.ev0, e.ev1));
   return DPC_OK;
 }
 
 int dpc_last_kernel_ms(dpc_ctx_t *c, float ms[3]) {
   if (!c || !ms) return DPC_ERR_ARG;
-  if (!c->flushed) return DPC_ERR_STATE;
-  ms[0] = c->ms_total; ms[1] = 0.0f; ms[2] = c->ms_total;   /* fill, bridge and traceback are one fused kernel */
+  if (!c->main.flushed) return DPC_ERR_STATE;
+  ms[0] = c->main.ms_total; ms[1] = 0.0f; ms[2] = c->main.ms_total;   /* fill, bridge and traceback are one fused kernel */
   return DPC_OK;
 }
 
-int dpc_get_stats(dpc_ctx_t *c, dpc_stats_t *out) {
-  if (!c || !out) return DPC_ERR_ARG;
-  memset(out, 0, sizeof *out);
-  const Batch &b = c->batch;
-  out->nproblems = (int64_t)b.probs.size();
+static void add_stats(const Engine &e, dpc_stats_t *out) {
+  const Batch &b = e.batch;
+  out->nproblems += (int64_t)b.probs.size();
   for (size_t i = 0; i < b.dprobs.size(); i++) {
     const DevProb &p = b.dprobs[i];
     if ((p.kind == DPC_END5_GAP || p.kind == DPC_END3_GAP) && p.endalign == DPC_QUERYEND_NOGAPS) {
-      out->fill_bytes += (int64_t)sizeof(DevProb) + p.L1 + (p.L2 + 3) / 4 + (int64_t)sizeof(DevRes);
+      out->fill_bytes += (int64_t)sizeof(DevProb) + 4 + p.L1 + (p.L2 + 3) / 4 + (int64_t)sizeof(DevRes);
       continue;
     }
     ArenaLayout a;
@@ -515,9 +691,16 @@ int dpc_get_stats(dpc_ctx_t *c, dpc_stats_t *out) {
     }
     out->fill_bytes += (int64_t)sizeof(DevProb) + 4 + (int64_t)sizeof(DevRes);   /* descriptor + list entry in, result out */
   }
-  out->traceback_bytes = 0;
-  out->h2d_bytes = c->h2d_bytes; out->d2h_bytes = c->d2h_bytes;
-  out->launches = c->nlaunch;
+  out->h2d_bytes += e.h2d_bytes; out->d2h_bytes += e.d2h_bytes;
+  out->launches += e.nlaunch;
+}
+
+/* Stats of the batch held by the ticket-API engine, or (after dpc_solve) of the chunks of its last wave. */
+int dpc_get_stats(dpc_ctx_t *c, dpc_stats_t *out) {
+  if (!c || !out) return DPC_ERR_ARG;
+  memset(out, 0, sizeof *out);
+  if (!c->main.batch.probs.empty()) add_stats(c->main, out);
+  else for (size_t i = 0; i < c->subs.size(); i++) add_stats(*c->subs[i], out);
   return DPC_OK;
 }
 

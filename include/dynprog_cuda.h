@@ -202,9 +202,15 @@ int dpc_pairs(dpc_ctx_t *ctx, int ticket, dpc_pair_t *out, int cap);
 /* Forget the batch (tickets restart at 0). */
 int dpc_reset(dpc_ctx_t *ctx);
 
+/* Host threads the bulk call (dpc_solve) may use for packing, finalising and rebuilding pairs;
+ * default: all cores, or the environment variable DPC_HOST_THREADS. */
+int dpc_set_threads(dpc_ctx_t *ctx, int nthreads);
+
 /* Whole batch in one call: add_bulk + flush + wait + results (+ pairs when
  * pairs != NULL; pair_off[i] = index of problem i's first record, pair_off has
  * n+1 entries).  Returns 0 or a negative code; DPC_ERR_NOMEM if pair_cap is too small. */
+/* The batch is cut into chunks that host threads pack, solve on their own streams and finalise
+ * concurrently; outputs are in input order.  The problems' sequences must stay valid during the call. */
 int dpc_solve(dpc_ctx_t *ctx, const dpc_problem_t *problems, int n,
               dpc_result_t *results, dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off);
 

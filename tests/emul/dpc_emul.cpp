@@ -45,7 +45,8 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
                       arena.data(), &dres[k], ovf, fill, ln);
   }
   int64_t out = 0;
-  dpc::Batch::Stack st;
+  dpc::Scratch sc;
+  std::vector<dpc_pair_t> st;
   for (int i = 0; i < n; i++) {
     dpc::HostProb &h = b.probs[i];
     if (pair_off) pair_off[i] = out;
@@ -53,16 +54,17 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
       const DevRes &dr = dres[h.dev];
       const uint16_t *ops = (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? ovfbuf.data() + dr.ovf : dr.ops;
       if (dr.status & DPC_ST_OVF_LOST) return DPC_ERR_NOMEM;
-      b.finalize(i, dr, ops);
-      b.rebuild(i, dr, ops, st);
-      if ((int)st.size() != h.res.npairs) return -100;
+      b.finalize(i, dr, ops, sc);
+      st.resize((size_t)b.max_pairs(i));
+      int k = b.rebuild(i, dr, ops, st.data(), sc);
+      if (k != b.R(i).npairs) return -100;
       if (pairs) {
-        if (out + (int64_t)st.size() > pair_cap) return DPC_ERR_NOMEM;
-        if (!st.empty()) memcpy(pairs + out, st.data(), st.size() * sizeof(dpc_pair_t));
+        if (out + k > pair_cap) return DPC_ERR_NOMEM;
+        if (k) memcpy(pairs + out, st.data(), (size_t)k * sizeof(dpc_pair_t));
       }
-      out += (int64_t)st.size();
+      out += k;
     }
-    results[i] = h.res;
+    results[i] = b.R(i);
   }
   if (pair_off) pair_off[n] = out;
   return 0;
