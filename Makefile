@@ -6,7 +6,7 @@ NVFLAGS = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcom
 all: cuda synth oracle emul
 
 cuda: $(PKG)/csrc/libdynprog_cuda.so
-$(PKG)/csrc/libdynprog_cuda.so: $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/dynprog_cuda.h
+$(PKG)/csrc/libdynprog_cuda.so: $(PKG)/csrc/*.cu $(PKG)/csrc/*.h include/dynprog_cuda.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/dynprog_cuda.cu -lcudart 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; exit 1)
 	@grep -E "registers|spill" $(PKG)/csrc/ptxas.log | sort | uniq -c | head -40
 

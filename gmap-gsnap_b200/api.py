@@ -303,6 +303,11 @@ class EmulLib(_SolverLib):
         L.emul_setup.argtypes = [C.POINTER(Setup)]
         L.emul_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_pairdistance.argtypes = [C.c_int] * 3
+        L.emul_set_fill.argtypes = [C.c_int]
+
+    def set_fill(self, force_generic):
+        """0: row-sweep fill + lane-parallel walk on 32 simulated lanes; 1: memory-state fill + serial walk."""
+        self.lib.emul_set_fill(int(force_generic))
 
     def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
         rc = self.lib.emul_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)

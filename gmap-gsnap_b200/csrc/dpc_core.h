@@ -123,7 +123,12 @@ struct Mat {
   int query_rows;           /* 1: rows = query, columns = genome (compute_scores_lookup_fwd/_rev, 1424-1736);
                                0: rows = genome, columns = query (_fwd_12/_rev_12, 1741-2044) */
   uint8_t *rowch, *colch;   /* characters in matrix order: raw query bytes / genome codes */
-  uint32_t *dir;            /* rows 1..L1, nibble (r-1)*wstride*8 + (c-r+lband) */
+  int planes, cpl;          /* planes != 0: directions are bit planes, cpl = ceil(W/32) 32-diagonal chunks per row */
+  uint32_t *prof;           /* planes, query rows: per row the 6 signed 4-bit scores of its query character */
+  uint32_t *dir;            /* nibbles: rows 1..L1, nibble (r-1)*wstride*8 + (c-r+lband);
+                               planes:  word ((r-1)*cpl + k/32)*4 + p, bit k%32, k = c-r+lband, with plane
+                               p = 0 nogap came from gap1 (HORIZ), 1 nogap came from gap2 (VERT),
+                                   2 gap1 of cell k+1 came from gap1 (HORIZ), 3 gap2 came from gap2 (VERT) */
   int32_t *nband;           /* nogap score of rows 1..L1, (r-1)*W + (c-r+lband); NULL when no bridge follows */
 };
 
@@ -142,16 +147,31 @@ DPC_HD int dpc_nib(const Mat &m, int r, int c) {
   int idx = (r - 1) * (m.wstride << 3) + (c - r + m.lband);
   return (int)((m.dir[idx >> 3] >> ((idx & 7) << 2)) & 15U);
 }
+DPC_HD int dpc_plane_bit(const Mat &m, int r, int k, int p) {
+  return (int)((m.dir[((r - 1) * m.cpl + (k >> 5)) * 4 + p] >> (k & 31)) & 1U);
+}
 /* directions as the reference's matrices hold them, including row 0 / column 0 (1460-1488)
  * and the memset STOP everywhere else (724-751): returns -1 for STOP */
-DPC_HD int dpc_dirN(const Mat &m, int r, int c) { return dpc_inband(m, r, c) ? (dpc_nib(m, r, c) & 3) : -1; }
+DPC_HD int dpc_dirN(const Mat &m, int r, int c) {
+  if (!dpc_inband(m, r, c)) return -1;
+  if (!m.planes) return dpc_nib(m, r, c) & 3;
+  int k = c - r + m.lband;
+  if (dpc_plane_bit(m, r, k, 1)) return DPC_VERT;
+  return dpc_plane_bit(m, r, k, 0) ? DPC_HORIZ : DPC_DIAG;
+}
 DPC_HD bool dpc_g1_horiz(const Mat &m, int r, int c) {
   if (r == 0) return c >= 2 && c <= m.rband && c <= m.L2;
-  return dpc_inband(m, r, c) && ((dpc_nib(m, r, c) >> 2) & 1);
+  if (!dpc_inband(m, r, c)) return false;
+  if (!m.planes) return (dpc_nib(m, r, c) >> 2) & 1;
+  int k = c - r + m.lband;
+  if (c == 1 || k == 0) return true;     /* left neighbour is column 0 or the forced cell: NEG beats NEG + open */
+  return dpc_plane_bit(m, r, k - 1, 2);
 }
 DPC_HD bool dpc_g2_vert(const Mat &m, int r, int c) {
   if (c == 0) return r >= 2 && r <= m.lband && r <= m.L1;
-  return dpc_inband(m, r, c) && ((dpc_nib(m, r, c) >> 3) & 1);
+  if (!dpc_inband(m, r, c)) return false;
+  if (!m.planes) return (dpc_nib(m, r, c) >> 3) & 1;
+  return dpc_plane_bit(m, r, c - r + m.lband, 3);
 }
 DPC_HD int dpc_nscore(const Mat &m, int r, int c) {
   /* nogap score as the bridges read it; row 0 inside the band is NEG (1464-1475) */
@@ -281,17 +301,28 @@ DPC_HD int dpc_intron_type(int l1, int l2, int r2, int r1, int cdna_direction) {
 
 struct Counts { int nmatches, nmismatches, nopens, nindels, star; };
 
-/* Walks one matrix from (r,c): lane 0 follows the direction nibbles and writes run-length ops
- * (traceback order) to `ops`; then all lanes classify the cells of the M runs (2644-2667).
- * Returns the number of ops; `ct` accumulates (every lane ends with the same totals). */
-DPC_HD int dpc_traceback(const Mat &m, int r0, int c0, int revp, int cdna_direction, uint16_t *ops,
-                         Counts &ct, const DevTables *tb, const Lanes &ln) {
-  int nops = 0, opens = 0, indels = 0;
+/* One gap run found by the walk at the cell (r,c) it hangs off: which op it becomes (2416-2601). */
+DPC_HD int dpc_run_op(const Mat &m, int d, int dist, int r, int c, int revp, int cdna_direction) {
   const int genome_rows = !m.query_rows;
+  int genome_run = (d == DPC_HORIZ) ? !genome_rows : genome_rows;
+  int op = genome_run ? DPC_OP_GSKIP : DPC_OP_QSKIP;
+  if (genome_run && dist >= DPC_MICROINTRON) {
+    const uint8_t *g = genome_rows ? m.rowch : m.colch;
+    int lo = genome_rows ? r : c, a, b, y, z;          /* 0-based first genome index of the run */
+    if (!revp) { a = g[lo]; b = g[lo + 1]; y = g[lo + dist - 2]; z = g[lo + dist - 1]; }
+    else { a = g[lo + dist - 1]; b = g[lo + dist - 2]; y = g[lo + 1]; z = g[lo]; }
+    if (dpc_intron_type(a, b, y, z, cdna_direction) != 0) op = DPC_OP_GAPHOLDER;
+  }
+  return op;
+}
+
+/* Serial walk (lane 0) from (r0,c0): writes run-length ops in traceback order, returns their number. */
+DPC_HD int dpc_walk_serial(const Mat &m, int r0, int c0, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) {
+  int nops = 0;
   if (ln.lane == 0) {
     int r = r0, c = c0, run = 0;
     while (dpc_inband(m, r, c)) {
-      int d = dpc_nib(m, r, c) & 3;
+      int d = dpc_dirN(m, r, c);
       run++;
       r--; c--;
       if (d == DPC_DIAG) continue;
@@ -299,26 +330,19 @@ DPC_HD int dpc_traceback(const Mat &m, int r0, int c0, int revp, int cdna_direct
       int dist = 1;
       if (d == DPC_HORIZ) { while (dpc_g1_horiz(m, r, c)) { dist++; c--; } c--; }
       else { while (dpc_g2_vert(m, r, c)) { dist++; r--; } r--; }
-      int genome_run = (d == DPC_HORIZ) ? !genome_rows : genome_rows;
-      int op = genome_run ? DPC_OP_GSKIP : DPC_OP_QSKIP;
-      if (genome_run && dist >= DPC_MICROINTRON) {
-        const uint8_t *g = genome_rows ? m.rowch : m.colch;
-        int lo = genome_rows ? r : c, a, b, y, z;          /* 0-based first genome index of the run */
-        if (!revp) { a = g[lo]; b = g[lo + 1]; y = g[lo + dist - 2]; z = g[lo + dist - 1]; }
-        else { a = g[lo + dist - 1]; b = g[lo + dist - 2]; y = g[lo + 1]; z = g[lo]; }
-        if (dpc_intron_type(a, b, y, z, cdna_direction) != 0) op = DPC_OP_GAPHOLDER;
-      }
-      if (op != DPC_OP_GAPHOLDER) { opens++; indels += dist; }
-      ops[nops++] = (uint16_t)((dist << 2) | op);
+      ops[nops++] = (uint16_t)((dist << 2) | dpc_run_op(m, d, dist, r, c, revp, cdna_direction));
     }
     if (run) ops[nops++] = (uint16_t)((run << 2) | DPC_OP_M);
   }
   DPC_SYNC();
-  nops = dpc_bcast(nops, ln);
-  ct.nopens += dpc_bcast(opens, ln);
-  ct.nindels += dpc_bcast(indels, ln);
-  /* classify the aligned columns */
-  int r = r0, c = c0, nm = 0, nmm = 0, star = 0;
+  return dpc_bcast(nops, ln);
+}
+
+/* All lanes classify the cells of the M runs (2644-2667) and add up the indel counts. */
+DPC_HD void dpc_count_ops(const Mat &m, int r0, int c0, const uint16_t *ops, int nops, Counts &ct,
+                          const DevTables *tb, const Lanes &ln) {
+  const int genome_rows = !m.query_rows;
+  int r = r0, c = c0, nm = 0, nmm = 0, star = 0, opens = 0, indels = 0;
   for (int i = 0; i < nops; i++) {
     int op = ops[i] & 3, len = ops[i] >> 2;
     if (op == DPC_OP_M) {
@@ -334,12 +358,13 @@ DPC_HD int dpc_traceback(const Mat &m, int r0, int c0, int revp, int cdna_direct
     } else {
       int along_cols = (op == DPC_OP_QSKIP) ? genome_rows : !genome_rows;
       if (along_cols) c -= len; else r -= len;
+      if (op != DPC_OP_GAPHOLDER) { opens++; indels += len; }
     }
   }
+  ct.nopens += opens; ct.nindels += indels;
   ct.nmatches += dpc_warp_sum(nm, ln);
   ct.nmismatches += dpc_warp_sum(nmm, ln);
   ct.star += dpc_warp_sum(star, ln);
-  return nops;
 }
 
 /* ---- intron bridge: intron_score 3148-3192, bridge_intron_gap 3290-4122 ----------------- */
@@ -482,19 +507,30 @@ DPC_HD void dpc_bridge_cdna(Bridge &br, const Mat &mL, const Mat &mR, const DevP
   br.finalscore = bs; br.rL = brL; br.rR = brR; br.cL = bcL; br.cR = bcR; br.introntype = 0;
 }
 
+/* the 6 scores of one query character against A C G T N *, 4 signed bits each (values -5..3) */
+DPC_HD uint32_t dpc_pack_prof(const int8_t *score, int q) {
+  const int8_t *s = score + (q & 127) * 8;
+  uint32_t w = 0;
+  for (int g = 0; g < 6; g++) w |= ((uint32_t)s[g] & 15u) << (4 * g);
+  return w;
+}
+
 /* ---- arena layout (shared by host sizing and the kernel) --------------------------------- */
-struct MatDims { int rows, cols, lband, rband, W, wstride; };
+struct MatDims { int rows, cols, lband, rband, W, wstride, planes, cpl; };
 struct ArenaLayout {
   int nmat;
   MatDims d[2];
-  uint32_t rowch[2], colch[2], dir[2], nband[2], ops[2], state, total;
+  uint32_t rowch[2], colch[2], prof[2], dir[2], nband[2], ops[2], state, total;
 };
+#define DPC_MAX_CPL 3                       /* row-sweep fill: bands of up to 96 diagonals */
 DPC_HB uint32_t dpc_al(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
 
-/* kind codes as in include/dynprog_cuda.h: 0 single, 1 genome, 2 cdna, 3 end5, 4 end3 */
-DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int with_state) {
+/* kind codes as in include/dynprog_cuda.h: 0 single, 1 genome, 2 cdna, 3 end5, 4 end3.
+ * fillmode 0: sizes only (stats); 1: every matrix through the memory-state fill (nibble directions +
+ * anti-diagonal state); 2: row-sweep fill (bit planes) wherever the band has at most 96 diagonals. */
+DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
   uint32_t off = 0;
-  int maxrows = 0;
+  int maxrows = 0, need_state = fillmode == 1;
   a.nmat = (p.kind == 1 || p.kind == 2) ? 2 : 1;
   for (int i = 0; i < a.nmat; i++) {
     MatDims &d = a.d[i];
@@ -503,20 +539,21 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int with_state) {
     dpc_bands(d.rows, d.cols, p.extraband, (p.flags & DPC_F_WIDEBAND) != 0, &d.lband, &d.rband);
     d.W = d.lband + d.rband + 1;
     d.wstride = dpc_wstride(d.W);
+    d.cpl = (d.W + 31) >> 5;
+    d.planes = fillmode == 2 && d.cpl <= DPC_MAX_CPL;
+    if (fillmode == 2 && !d.planes) need_state = 1;
     if (d.rows > maxrows) maxrows = d.rows;
     a.rowch[i] = off; off = dpc_al(off + (uint32_t)d.rows + 2, 4);
     a.colch[i] = off; off = dpc_al(off + (uint32_t)d.cols + 2, 4);
-    a.dir[i] = off; off += (uint32_t)d.rows * (uint32_t)d.wstride * 4;
+    a.prof[i] = off;
+    if (d.planes && p.kind != 2) off += (uint32_t)d.rows * 4;
+    if (d.planes) { off = dpc_al(off, 16); a.dir[i] = off; off += (uint32_t)d.rows * (uint32_t)d.cpl * 16; }
+    else { a.dir[i] = off; off += (uint32_t)d.rows * (uint32_t)d.wstride * 4; }
     if (a.nmat == 2) { a.nband[i] = off; off += (uint32_t)d.rows * (uint32_t)d.W * 4; } else a.nband[i] = 0;
     a.ops[i] = off; off = dpc_al(off + 2 * (uint32_t)(d.rows + d.cols + 2), 4);
   }
   a.state = off;
-  /* anti-diagonal state of dpc_fill_generic: 1 = always, 2 = only for bands the register fill cannot take */
-  if (with_state == 2) {
-    with_state = 0;
-    for (int i = 0; i < a.nmat; i++) if (a.d[i].lband + a.d[i].rband >= 64) with_state = 1;
-  }
-  if (with_state) off += 9 * (uint32_t)(maxrows + 1) * 4;
+  if (need_state) off += 9 * (uint32_t)(maxrows + 1) * 4;
   a.total = dpc_al(off, 16);
 }
 
@@ -525,6 +562,8 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *arena, co
   m.L1 = d.rows; m.L2 = d.cols; m.lband = d.lband; m.rband = d.rband; m.W = d.W; m.wstride = d.wstride;
   m.open = p.open; m.extend = p.extend; m.late = late; m.query_rows = query_rows;
   m.rowch = arena + a.rowch[i]; m.colch = arena + a.colch[i];
+  m.planes = d.planes; m.cpl = d.cpl;
+  m.prof = (uint32_t *)(arena + a.prof[i]);
   m.dir = (uint32_t *)(arena + a.dir[i]);
   m.nband = a.nmat == 2 ? (int32_t *)(arena + a.nband[i]) : (int32_t *)0;
 }
@@ -558,6 +597,7 @@ DPC_HD void dpc_emit_ops(DevRes *res, const uint16_t *opsL, int nL, const uint16
 template <class FILL>
 DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint32_t *blocks, const DevTables *tb,
                               uint8_t *arena, DevRes *res, const OvfArena &ovf, FILL &fill, const Lanes &ln) {
+  /* FILL provides: fillmode (layout), operator() = the matrix fill, walk() = the traceback walk */
   uint32_t status = DPC_ST_DONE;
   Counts ct; ct.nmatches = ct.nmismatches = ct.nopens = ct.nindels = ct.star = 0;
   int finalscore = 0, brL = 0, bcL = 0, brR = 0, bcR = 0, introntype = 0, nopsL = 0, nopsR = 0;
@@ -584,14 +624,18 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
     status |= DPC_ST_HAVE | DPC_ST_OK;
   } else {
     ArenaLayout a;
-    dpc_layout(p, a, FILL::needs_state);
+    dpc_layout(p, a, FILL::fillmode);
     Mat m0, m1;
     int32_t *st = (int32_t *)(arena + a.state);
     if (p.kind == 0 || p.kind == 3 || p.kind == 4) {
       /* Dynprog_single_gap 4450-4572, Dynprog_end5_gap 5094-5284, Dynprog_end3_gap 5556-5741 */
       const int five = p.kind == 3;
       dpc_make_mat(m0, a, 0, arena, p, five ? !late : late, 1);
-      for (int i = ln.lane; i < p.L1; i += ln.n) m0.rowch[i] = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
+      for (int i = ln.lane; i < p.L1; i += ln.n) {
+        int q = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
+        m0.rowch[i] = (uint8_t)q;
+        if (m0.planes) m0.prof[i] = dpc_pack_prof(score, q);
+      }
       for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
       DPC_SYNC();
       EndSearch es; es.eb = p.extraband;
@@ -603,7 +647,8 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       finalscore = es.best.score;
       brL = es.best.key / (p.L2 + 1); bcL = es.best.key % (p.L2 + 1);
       uint16_t *ops = (uint16_t *)(arena + a.ops[0]);
-      nopsL = dpc_traceback(m0, brL, bcL, five, p.cdna_direction, ops, ct, tb, ln);
+      nopsL = fill.walk(m0, brL, bcL, five, p.cdna_direction, ops, ln);
+      dpc_count_ops(m0, brL, bcL, ops, nopsL, ct, tb, ln);
       opsL = ops;
       status |= DPC_ST_HAVE | DPC_ST_OK;
     } else {
@@ -612,7 +657,12 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       dpc_make_mat(m1, a, 1, arena, p, !late, !cdna);
       if (!cdna) {
         /* Dynprog_genome_gap 4798-5061: L = fwd(query, genome @ offset2L), R = rev(query, genome @ revoffset2R) */
-        for (int i = ln.lane; i < p.L1; i += ln.n) { m0.rowch[i] = pool[p.q0 + (uint32_t)i]; m1.rowch[i] = pool[p.q0 + (uint32_t)(p.L1 - 1 - i)]; }
+        for (int i = ln.lane; i < p.L1; i += ln.n) {
+          int qf = pool[p.q0 + (uint32_t)i], qr = pool[p.q0 + (uint32_t)(p.L1 - 1 - i)];
+          m0.rowch[i] = (uint8_t)qf; m1.rowch[i] = (uint8_t)qr;
+          if (m0.planes) m0.prof[i] = dpc_pack_prof(score, qf);
+          if (m1.planes) m1.prof[i] = dpc_pack_prof(score, qr);
+        }
         for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2 + i);
         for (int i = ln.lane; i < p.L2R; i += ln.n) m1.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2R - i);
         if (ln.lane == 0) { m0.colch[p.L2] = 7; m1.colch[p.L2R] = 7; }    /* leftdi[length2L-1] = rightdi[length2R-1] = 0, 3354, 3376 */
@@ -648,8 +698,10 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       if (ok) {
         status |= DPC_ST_OK;
         uint16_t *oR = (uint16_t *)(arena + a.ops[1]), *oL = (uint16_t *)(arena + a.ops[0]);
-        nopsR = dpc_traceback(m1, brR, bcR, 1, p.cdna_direction, oR, ct, tb, ln);
-        nopsL = dpc_traceback(m0, brL, bcL, 0, p.cdna_direction, oL, ct, tb, ln);
+        nopsR = fill.walk(m1, brR, bcR, 1, p.cdna_direction, oR, ln);
+        dpc_count_ops(m1, brR, bcR, oR, nopsR, ct, tb, ln);
+        nopsL = fill.walk(m0, brL, bcL, 0, p.cdna_direction, oL, ln);
+        dpc_count_ops(m0, brL, bcL, oL, nopsL, ct, tb, ln);
         opsL = oL; opsR = oR;
       }
     }
@@ -665,9 +717,12 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
 }
 
 struct GenericFill {
-  enum { needs_state = 1 };
+  enum { fillmode = 1 };
   DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
     dpc_fill_generic(m, st, score, es, ln);
+  }
+  DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {
+    return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);
   }
 };
 #endif /* DPC_CORE_H */

@@ -1,0 +1,202 @@
+/* dpc_rows.h -- banded Gotoh fill as a ROW sweep, one warp per matrix, and the lane-parallel traceback walk.
+ *
+ * Lane l of chunk j owns diagonal k = 32 j + l (k = c - r + lband) for the whole matrix.  Going from row r-1
+ * to row r along a diagonal is the recurrence's diagonal move, so
+ *   nogap[r][c]  needs the lane's OWN three values of the previous row            (no communication),
+ *   gap2 [r][c]  needs nogap/gap2 of (r-1, c)   = diagonal k+1 of the previous row (one shuffle down),
+ *   gap1 [r][c]  needs nogap/gap1 of (r, c-1)   = diagonal k-1 of the SAME row: the serial chain
+ *                gap1[k] = max(nogap[k-1] + open, gap1[k-1]) + extend unrolls to
+ *                gap1[k] = k*extend + max_{j<k} (nogap[j] + open - j*extend),
+ *                an exclusive prefix maximum over the lanes: five shuffle+max steps per 32 diagonals.
+ * Every lane works on every row (no wavefront ramp, no idle half-warp, no per-lane row bookkeeping) and the
+ * control flow is uniform.  Direction bits leave the warp as four ballots per chunk (bit planes) -- 4 bits
+ * per cell, written by one 16-byte store per row and chunk.
+ *
+ * Exactness: max is exact, so the prefix maximum yields exactly the reference's gap1 values; the direction
+ * of gap1[k+1] is better(gap1[k], nogap[k] + open), which lane k can evaluate by itself (plane 2 therefore
+ * holds the bit of cell k+1 at position k).  Cells left of column 1 / outside the matrix feed the scan with
+ * NEG - k*extend, which reproduces the reference's forced NEG cell (1507-1513) and column 0 (1477-1488).
+ *
+ * Written against dpc_vec.h, so tests/emul runs the same source as a lock-step 32-lane simulation.
+ * Reference recurrence: compute_scores_lookup_fwd/_rev/_fwd_12/_rev_12, dynprog.c:1424-2044.
+ */
+#ifndef DPC_ROWS_H
+#define DPC_ROWS_H
+
+#include "dpc_core.h"
+#include "dpc_vec.h"
+
+#ifdef __CUDACC__
+#define DPC_VFN __device__ __forceinline__
+#else
+#define DPC_VFN static inline
+#endif
+
+template <int CPL, bool LATE>
+DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
+  using namespace vec;
+  const int L1 = m.L1, L2 = m.L2, lband = m.lband, W = m.W;
+  const int open = m.open, extend = m.extend;
+  const VI lane = lane_index();
+  VI Np[CPL], G1p[CPL], G2p[CPL], kE[CPL], cI[CPL], c[CPL];
+  VM kvalid[CPL], ebok[CPL];
+  VI bs = splat(es.best.score), bk = splat(es.best.key);
+
+#pragma unroll
+  for (int j = 0; j < CPL; j++) {
+    const VI k = lane + 32 * j;
+    kvalid[j] = k < W;
+    kE[j] = k * extend;
+    cI[j] = DPC_NEG - kE[j];
+    ebok[j] = vand(k >= lband - es.eb, k <= lband + es.eb);
+    /* row 0 (1460-1475): (0,0) nogap 0; (0,c) gap1 = open + c*extend for 1 <= c <= min(rband, L2) */
+    const VI c0 = k - lband;
+    c[j] = c0;
+    Np[j] = vsel(c0 == 0, 0, DPC_NEG);
+    G1p[j] = vsel(vand(vand(c0 >= 1, c0 <= L2), kvalid[j]), open + c0 * extend, DPC_NEG);
+    G2p[j] = splat(DPC_NEG);
+  }
+
+  for (int r = 1; r <= L1; r++) {
+    const int prof = m.query_rows ? (int)m.prof[r - 1] : 0;
+    const int rowg = m.query_rows ? 0 : (int)m.rowch[r - 1];
+    const int col0 = open + r * extend;                 /* gap2 of (r,0), 1477-1488 */
+    int carry = DPC_NEG + extend;                       /* the forced / column-0 cell left of diagonal 0 */
+#pragma unroll
+    for (int j = 0; j < CPL; j++) {
+      c[j] = c[j] + 1;
+      const VM valid = vand(kvalid[j], vlt_u(c[j] - 1, L2));
+      const VI ch = load_u8(m.colch, vsel(valid, c[j] - 1, 0));
+      VI P;
+      if (m.query_rows) P = (((prof >> (ch << 2)) & 15) ^ 8) - 8;
+      else P = load_i8(score, ((ch & 127) << 3) + rowg);
+      /* nogap, 1545-1561 */
+      const VM p1 = LATE ? (G1p[j] >= Np[j]) : (G1p[j] > Np[j]);
+      const VI mx = vmax(Np[j], G1p[j]);
+      const VM p2 = LATE ? (G2p[j] >= mx) : (G2p[j] > mx);
+      const VI Nn = vmax(mx, G2p[j]) + P;
+      /* gap2, 1532-1542: (r-1, c) is diagonal k+1 of the previous row */
+      const VI Nu = shfl_down1(Np[j], j + 1 < CPL ? shfl_get(Np[j + 1 < CPL ? j + 1 : j], 0) : DPC_NEG);
+      const VI G2u = shfl_down1(G2p[j], j + 1 < CPL ? shfl_get(G2p[j + 1 < CPL ? j + 1 : j], 0) : DPC_NEG);
+      const VI a = Nu + open;
+      const VM pv = LATE ? (G2u >= a) : (G2u > a);
+      const VI G2n = vmax(a, G2u) + extend;
+      /* gap1, 1519-1529, as an exclusive prefix maximum over the diagonals */
+      const VI a2 = Nn + open;
+      const VI s = vsel(valid, a2 - kE[j], cI[j]);
+      VI t = shfl_up(s, 1, carry);
+      t = vmax(t, shfl_up_keep(t, 1));
+      t = vmax(t, shfl_up_keep(t, 2));
+      t = vmax(t, shfl_up_keep(t, 4));
+      t = vmax(t, shfl_up_keep(t, 8));
+      t = vmax(t, shfl_up_keep(t, 16));
+      if (j + 1 < CPL) carry = shfl_get(vmax(t, s), 31);
+      const VI G1n = t + kE[j];
+      const VM h = LATE ? (G1n >= a2) : (G1n > a2);
+      /* directions: four ballots, one 16-byte store */
+      const uint32_t b1 = vballot(p2), b0 = vballot(p1) & ~b1, b2 = vballot(h), b3 = vballot(pv);
+      store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
+      if (m.nband) store_i32(m.nband, (r - 1) * W + lane + 32 * j, Nn, kvalid[j]);
+      if (es.mode == 1) keep_better(bs, bk, Nn, r * (L2 + 1) + c[j], vand(valid, ebok[j]), LATE);
+      else if (es.mode == 2) { if (r == L1) keep_better(bs, bk, Nn, r * (L2 + 1) + c[j], valid, LATE); }
+      else if (es.mode == 3) { if (r == L1) keep_better(bs, bk, Nn, r * (L2 + 1) + c[j], vand(valid, c[j] == L2), LATE); }
+      /* what the next row sees on this diagonal: the cell, column 0, or nothing */
+      Np[j] = vsel(valid, Nn, DPC_NEG);
+      G1p[j] = vsel(valid, G1n, DPC_NEG);
+      G2p[j] = vsel(valid, G2n, vsel(c[j] == 0, col0, DPC_NEG));
+    }
+  }
+  reduce_better(bs, bk, LATE, &es.best.score, &es.best.key);
+  sync();
+}
+
+/* Lane-parallel traceback walk over bit-plane directions: 32 cells of the current diagonal (or of the current
+ * gap run) are probed at once and a ballot finds where the path turns.  Same ops as dpc_walk_serial. */
+DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_direction, uint16_t *ops) {
+  using namespace vec;
+  const VI lane = lane_index();
+  const int cpl4 = m.cpl * 4;
+  int r = r0, c = c0, run = 0, nops = 0;
+  while (dpc_inband(m, r, c)) {
+    const int k = c - r + m.lband;
+    const VI rr = r - lane;
+    const VM inb = vand(rr >= 1, (c - lane) >= 1);
+    const VI widx = (vsel(inb, rr, 1) - 1) * cpl4 + ((k >> 5) << 2);
+    const VI w0 = load_u32(m.dir, widx), w1 = load_u32(m.dir, widx + 1);
+    const VI turn = ((w0 | w1) >> (k & 31)) & 1;
+    const uint32_t b = vballot(vor(vnot(inb), turn != 0));
+    if (b == 0) { run += 32; r -= 32; c -= 32; continue; }
+    const int f = first_set(b);
+    if (r - f < 1 || c - f < 1) { run += f; r -= f; c -= f; break; }     /* ran into row 0 / column 0: STOP */
+    const int d = ((uint32_t)extract(w1, f) >> (k & 31)) & 1u ? DPC_VERT : DPC_HORIZ;
+    run += f + 1; r -= f + 1; c -= f + 1;
+    store_u16_lane0(&ops[nops++], (run << 2) | DPC_OP_M); run = 0;
+    int dist = 1;
+    if (d == DPC_HORIZ) {
+      /* gap1 chain along row r, leftwards from column c (2672-2679) */
+      for (;;) {
+        VM hz;
+        if (r == 0) hz = vand(vand((c - lane) >= 2, (c - lane) <= m.rband), (c - lane) <= m.L2);
+        else {
+          const VI cc = c - lane, kk = cc - r + m.lband;
+          const VM in = vand(vand(cc >= 1, kk >= 0), vand(cc <= m.L2, kk < m.W));
+          const VI k1 = vsel(in, vmax(kk - 1, 0), 0);
+          const VI w = load_u32(m.dir, ((r - 1) * m.cpl + (k1 >> 5)) * 4 + 2);
+          hz = vand(in, vor(vor(cc == 1, kk == 0), ((w >> (k1 & 31)) & 1) != 0));
+        }
+        const uint32_t nb = vballot(vnot(hz));
+        if (nb == 0) { dist += 32; c -= 32; continue; }
+        const int g = first_set(nb);
+        dist += g; c -= g;
+        break;
+      }
+      c--;
+    } else {
+      /* gap2 chain up column c from row r (2693-2700) */
+      for (;;) {
+        VM vt;
+        const VI rr2 = r - lane;
+        if (c == 0) vt = vand(vand(rr2 >= 2, rr2 <= m.lband), rr2 <= m.L1);
+        else {
+          const VI kk = c - rr2 + m.lband;
+          const VM in = vand(vand(rr2 >= 1, rr2 <= m.L1), vand(kk >= 0, kk < m.W));
+          const VI k1 = vsel(in, kk, 0);
+          const VI w = load_u32(m.dir, ((vsel(in, rr2, 1) - 1) * m.cpl + (k1 >> 5)) * 4 + 3);
+          vt = vand(in, ((w >> (k1 & 31)) & 1) != 0);
+        }
+        const uint32_t nb = vballot(vnot(vt));
+        if (nb == 0) { dist += 32; r -= 32; continue; }
+        const int g = first_set(nb);
+        dist += g; r -= g;
+        break;
+      }
+      r--;
+    }
+    store_u16_lane0(&ops[nops++], (dist << 2) | dpc_run_op(m, d, dist, r, c, revp, cdna_direction));
+  }
+  if (run) store_u16_lane0(&ops[nops++], (run << 2) | DPC_OP_M);
+  sync();
+  return nops;
+}
+
+/* The product's fill policy: row sweep for bands of up to 96 diagonals, memory-state fill beyond. */
+struct RowFill {
+  enum { fillmode = 2 };
+  DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
+    if (!m.planes) { dpc_fill_generic(m, st, score, es, ln); return; }
+    if (m.late) {
+      if (m.cpl == 1) dpc_fill_rows<1, true>(m, score, es);
+      else if (m.cpl == 2) dpc_fill_rows<2, true>(m, score, es);
+      else dpc_fill_rows<3, true>(m, score, es);
+    } else {
+      if (m.cpl == 1) dpc_fill_rows<1, false>(m, score, es);
+      else if (m.cpl == 2) dpc_fill_rows<2, false>(m, score, es);
+      else dpc_fill_rows<3, false>(m, score, es);
+    }
+  }
+  DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {
+    if (!m.planes) return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);
+    return dpc_walk_planes(m, r, c, revp, cdna_direction, ops);
+  }
+};
+#endif /* DPC_ROWS_H */

@@ -19,7 +19,7 @@
 #include <vector>
 
 #include "dpc_host.h"
-#include "dpc_fill_warp.cuh"
+#include "dpc_rows.h"
 
 using namespace dpc;
 
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) dpc_solve_kernel(const KernelArgs a) {
       GenericFill fill;
       dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, &a.res[pi], a.ovf, fill, ln);
     } else {
-      WarpFill fill;
+      RowFill fill;
       dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, &a.res[pi], a.ovf, fill, ln);
     }
     __syncwarp();
@@ -254,7 +254,7 @@ struct Engine {
     if (n == 0) return DPC_OK;
 
     /* bin the problems by arena size; oversize ones get HBM scratch */
-    const int with_state = g_force_generic ? 1 : 2;   /* must match FILL::needs_state of the kernel */
+    const int with_state = g_force_generic ? 1 : 2;   /* must match FILL::fillmode of the kernel */
     const uint32_t smem_limit = (uint32_t)(d.max_smem - (int)sizeof(DevTables) - 2048);
     cls.resize(n);
     size_t count[NCLASS] = { 0 };

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <vector>
 #include "../../gmap-gsnap_b200/csrc/dpc_host.h"
+#include "../../gmap-gsnap_b200/csrc/dpc_rows.h"
 
 extern "C" int emul_init(int maxlookback, int extraquerygap, int maxpeelback, int end, int paired, int mode) {
   return dpc::host_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode);
@@ -19,6 +20,8 @@ extern "C" int emul_setup(const dpc_setup_t *s) {
   g.setup_done = true;
   return 0;
 }
+static int g_force_generic = 0;
+extern "C" int emul_set_fill(int force_generic) { g_force_generic = force_generic; return 0; }
 extern "C" int emul_pairdistance(int type, int c1, int c2) { return dpc::G().P[type & 3][c1 & 127][c2 & 127]; }
 
 extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *results,
@@ -33,16 +36,20 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
   unsigned int used = 0;
   OvfArena ovf; ovf.ops = ovfbuf.data(); ovf.used = &used; ovf.cap = (unsigned int)ovfbuf.size();
   Lanes ln; ln.lane = 0; ln.n = 1;
-  GenericFill fill;
+  GenericFill gfill;     /* single lane: memory-state fill + serial walk */
+  RowFill rfill;         /* 32 simulated lanes: row-sweep fill + lane-parallel walk (dpc_vec.h host build) */
   std::vector<uint8_t> arena;
   b.pool_align(16);
   for (size_t k = 0; k < b.dprobs.size(); k++) {
     ArenaLayout a;
-    dpc_layout(b.dprobs[k], a, 1);
+    dpc_layout(b.dprobs[k], a, g_force_generic ? 1 : 2);
     arena.assign(a.total + 64, 0xAB);
     memset(&dres[k], 0, sizeof(DevRes));
-    dpc_solve_problem(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables,
-                      arena.data(), &dres[k], ovf, fill, ln);
+    uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
+    if (g_force_generic)
+      dpc_solve_problem(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, &dres[k], ovf, gfill, ln);
+    else
+      dpc_solve_problem(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, &dres[k], ovf, rfill, ln);
   }
   int64_t out = 0;
   dpc::Scratch sc;

@@ -35,9 +35,14 @@ def test_restatement_matches_golden(golden, golden_port, name):
     assert not golden.missing
 
 
+@pytest.mark.parametrize("fill", [0, 1], ids=["row_sweep_32_lanes", "memory_fill_1_lane"])
 @pytest.mark.parametrize("name", GOLDEN_SETS)
-def test_device_routines_single_lane_match_golden(golden, golden_emul, name):
-    got = golden_emul.solve(golden.problems(name))
+def test_device_routines_on_cpu_match_golden(golden, golden_emul, name, fill):
+    golden_emul.set_fill(fill)
+    try:
+        got = golden_emul.solve(golden.problems(name))
+    finally:
+        golden_emul.set_fill(0)
     assert not api.compare(*golden.expected(name), *got)
     assert not golden.missing
 
@@ -64,9 +69,27 @@ def test_probability_mode_matches_reference(workload, ref, port, emul):
     assert not api.compare(*want, *emul.solve(probs))
 
 
-def test_device_routines_single_lane_match_oracle(workload, port, emul):
+@pytest.mark.parametrize("fill", [0, 1], ids=["row_sweep_32_lanes", "memory_fill_1_lane"])
+def test_device_routines_on_cpu_match_oracle(workload, port, emul, fill):
     probs = api.arm_probability_mode(mixed_problems(workload, 1500, 9, long_frac=0.03, long_hi=611), port)
-    assert not api.compare(*port.solve(probs), *emul.solve(probs))
+    emul.set_fill(fill)
+    try:
+        got = emul.solve(probs)
+    finally:
+        emul.set_fill(0)
+    assert not api.compare(*port.solve(probs), *got)
+
+
+def test_band_widths_around_the_chunk_limits(workload, port, emul):
+    """Row-sweep chunks hold 32 diagonals: bands of 31..34, 63..66 and 95..98 diagonals (the last ones fall back
+    to the memory-state fill), with and without jump_late_p."""
+    sets = []
+    for eb in (15, 16, 31, 32, 47, 48):
+        p = workload.single_gaps(120, extraband=eb, seed=1000 + eb)
+        p["length2"] = np.maximum(p["length1"] + np.arange(len(p)) % 4 - 1, 1)      # W = 2 eb + 1 + |L2 - L1|
+        sets.append(p)
+    allp = np.concatenate(sets)
+    assert not api.compare(*port.solve(allp), *emul.solve(allp))
 
 
 def test_wide_bands_and_max_sizes(workload, port, emul):
