@@ -123,10 +123,10 @@ struct Mat {
   int query_rows;           /* 1: rows = query, columns = genome (compute_scores_lookup_fwd/_rev, 1424-1736);
                                0: rows = genome, columns = query (_fwd_12/_rev_12, 1741-2044) */
   uint8_t *rowch, *colch;   /* characters in matrix order: raw query bytes / genome codes */
-  int planes, cpl;          /* planes != 0: directions are bit planes, cpl = ceil(W/32) 32-diagonal chunks per row */
+  int planes, cpl, cplsh;   /* planes != 0: directions are bit planes; every lane owns cpl = 1 << cplsh adjacent diagonals */
   uint32_t *prof;           /* planes, query rows: per row the 6 signed 4-bit scores of its query character */
   uint32_t *dir;            /* nibbles: rows 1..L1, nibble (r-1)*wstride*8 + (c-r+lband);
-                               planes:  word ((r-1)*cpl + k/32)*4 + p, bit k%32, k = c-r+lband, with plane
+                               planes:  word ((r-1)*cpl + k%cpl)*4 + p, bit k/cpl, k = c-r+lband, with plane
                                p = 0 nogap came from gap1 (HORIZ), 1 nogap came from gap2 (VERT),
                                    2 gap1 of cell k+1 came from gap1 (HORIZ), 3 gap2 came from gap2 (VERT) */
   int32_t *nband;           /* nogap score of rows 1..L1, (r-1)*W + (c-r+lband); NULL when no bridge follows */
@@ -148,7 +148,7 @@ DPC_HD int dpc_nib(const Mat &m, int r, int c) {
   return (int)((m.dir[idx >> 3] >> ((idx & 7) << 2)) & 15U);
 }
 DPC_HD int dpc_plane_bit(const Mat &m, int r, int k, int p) {
-  return (int)((m.dir[((r - 1) * m.cpl + (k >> 5)) * 4 + p] >> (k & 31)) & 1U);
+  return (int)((m.dir[((r - 1) * m.cpl + (k & (m.cpl - 1))) * 4 + p] >> (k >> m.cplsh)) & 1U);
 }
 /* directions as the reference's matrices hold them, including row 0 / column 0 (1460-1488)
  * and the memset STOP everywhere else (724-751): returns -1 for STOP */
@@ -507,11 +507,11 @@ DPC_HD void dpc_bridge_cdna(Bridge &br, const Mat &mL, const Mat &mR, const DevP
   br.finalscore = bs; br.rL = brL; br.rR = brR; br.cL = bcL; br.cR = bcR; br.introntype = 0;
 }
 
-/* the 6 scores of one query character against A C G T N *, 4 signed bits each (values -5..3) */
+/* the 6 scores of one query character against A C G T N *, 4 bits each, stored as score + 8 (scores are -5..3) */
 DPC_HD uint32_t dpc_pack_prof(const int8_t *score, int q) {
   const int8_t *s = score + (q & 127) * 8;
   uint32_t w = 0;
-  for (int g = 0; g < 6; g++) w |= ((uint32_t)s[g] & 15u) << (4 * g);
+  for (int g = 0; g < 6; g++) w |= ((uint32_t)(s[g] + 8) & 15u) << (4 * g);
   return w;
 }
 
@@ -522,12 +522,12 @@ struct ArenaLayout {
   MatDims d[2];
   uint32_t rowch[2], colch[2], prof[2], dir[2], nband[2], ops[2], state, total;
 };
-#define DPC_MAX_CPL 3                       /* row-sweep fill: bands of up to 96 diagonals */
+#define DPC_MAX_CPL 4                       /* row-sweep fill: 1, 2 or 4 diagonals per lane, bands of up to 128 */
 DPC_HB uint32_t dpc_al(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
 
 /* kind codes as in include/dynprog_cuda.h: 0 single, 1 genome, 2 cdna, 3 end5, 4 end3.
  * fillmode 0: sizes only (stats); 1: every matrix through the memory-state fill (nibble directions +
- * anti-diagonal state); 2: row-sweep fill (bit planes) wherever the band has at most 96 diagonals. */
+ * anti-diagonal state); 2: row-sweep fill (bit planes) wherever the band has at most 128 diagonals. */
 DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
   uint32_t off = 0;
   int maxrows = 0, need_state = fillmode == 1;
@@ -539,8 +539,8 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
     dpc_bands(d.rows, d.cols, p.extraband, (p.flags & DPC_F_WIDEBAND) != 0, &d.lband, &d.rband);
     d.W = d.lband + d.rband + 1;
     d.wstride = dpc_wstride(d.W);
-    d.cpl = (d.W + 31) >> 5;
-    d.planes = fillmode == 2 && d.cpl <= DPC_MAX_CPL;
+    d.cpl = d.W <= 32 ? 1 : d.W <= 64 ? 2 : 4;
+    d.planes = fillmode == 2 && d.W <= 32 * DPC_MAX_CPL;
     if (fillmode == 2 && !d.planes) need_state = 1;
     if (d.rows > maxrows) maxrows = d.rows;
     a.rowch[i] = off; off = dpc_al(off + (uint32_t)d.rows + 2, 4);
@@ -562,7 +562,7 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *arena, co
   m.L1 = d.rows; m.L2 = d.cols; m.lband = d.lband; m.rband = d.rband; m.W = d.W; m.wstride = d.wstride;
   m.open = p.open; m.extend = p.extend; m.late = late; m.query_rows = query_rows;
   m.rowch = arena + a.rowch[i]; m.colch = arena + a.colch[i];
-  m.planes = d.planes; m.cpl = d.cpl;
+  m.planes = d.planes; m.cpl = d.cpl; m.cplsh = d.cpl == 1 ? 0 : d.cpl == 2 ? 1 : 2;
   m.prof = (uint32_t *)(arena + a.prof[i]);
   m.dir = (uint32_t *)(arena + a.dir[i]);
   m.nband = a.nmat == 2 ? (int32_t *)(arena + a.nband[i]) : (int32_t *)0;

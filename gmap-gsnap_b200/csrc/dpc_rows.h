@@ -9,7 +9,7 @@
  *                gap1[k] = k*extend + max_{j<k} (nogap[j] + open - j*extend),
  *                an exclusive prefix maximum over the lanes: five shuffle+max steps per 32 diagonals.
  * Every lane works on every row (no wavefront ramp, no idle half-warp, no per-lane row bookkeeping) and the
- * control flow is uniform.  Direction bits leave the warp as four ballots per chunk (bit planes) -- 4 bits
+ * control flow is uniform.  Direction bits leave the warp as four ballots per owned diagonal (bit planes) -- 4 bits
  * per cell, written by one 16-byte store per row and chunk.
  *
  * Exactness: max is exact, so the prefix maximum yields exactly the reference's gap1 values; the direction
@@ -32,78 +32,109 @@
 #define DPC_VFN static inline
 #endif
 
-template <int CPL, bool LATE>
+/* CPL diagonals per lane (k = CPL*lane + j), LATE = jump_late_p of this matrix, EP = end-point search over all
+ * rows (find_best_endpoint), NBAND = keep the nogap band for a bridge, QROWS = rows are the query.
+ *
+ * Values outside the band only have to stay far below every real score (they can never win a max, and the
+ * direction bits they produce are never read: the traceback only follows real-valued chains and the bridges only
+ * read in-band cells), so they are not kept bit-identical to the reference's NEG arithmetic; what IS kept exact is
+ * everything a valid cell can read: row 0, column 0 (set when a diagonal passes c == 0) and NEG above the band. */
+template <int CPL, bool LATE, bool EP, bool NBAND, bool QROWS>
 DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
   using namespace vec;
   const int L1 = m.L1, L2 = m.L2, lband = m.lband, W = m.W;
   const int open = m.open, extend = m.extend;
   const VI lane = lane_index();
-  VI Np[CPL], G1p[CPL], G2p[CPL], kE[CPL], cI[CPL], c[CPL];
-  VM kvalid[CPL], ebok[CPL];
+  VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL];
+  VM kok[CPL], ebok[CPL];
   VI bs = splat(es.best.score), bk = splat(es.best.key);
 
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
-    const VI k = lane + 32 * j;
-    kvalid[j] = k < W;
+    const VI k = lane * CPL + j;
+    kok[j] = k < W;
     kE[j] = k * extend;
-    cI[j] = DPC_NEG - kE[j];
     ebok[j] = vand(k >= lband - es.eb, k <= lband + es.eb);
+    const VI c0 = k - lband;                              /* column of this diagonal in row 0 */
+    cm1[j] = vsel(kok[j], c0 - 1, 1 << 24);               /* c - 1 = r + cm1; diagonals past the band never become valid */
     /* row 0 (1460-1475): (0,0) nogap 0; (0,c) gap1 = open + c*extend for 1 <= c <= min(rband, L2) */
-    const VI c0 = k - lband;
-    c[j] = c0;
     Np[j] = vsel(c0 == 0, 0, DPC_NEG);
-    G1p[j] = vsel(vand(vand(c0 >= 1, c0 <= L2), kvalid[j]), open + c0 * extend, DPC_NEG);
+    G1p[j] = vsel(vand(vand(c0 >= 1, c0 <= L2), kok[j]), open + c0 * extend, DPC_NEG);
     G2p[j] = splat(DPC_NEG);
+    /* column characters of row 1 (a window that slides one column per row, so it is filled for every
+       diagonal, in or out of the band) */
+    const VI ch = load_u8(m.colch, vsel(vlt_u(c0, L2), c0, 0));
+    sh[j] = QROWS ? (ch << 2) : ((ch & 127) << 3);
   }
 
   for (int r = 1; r <= L1; r++) {
-    const int prof = m.query_rows ? (int)m.prof[r - 1] : 0;
-    const int rowg = m.query_rows ? 0 : (int)m.rowch[r - 1];
-    const int col0 = open + r * extend;                 /* gap2 of (r,0), 1477-1488 */
-    int carry = DPC_NEG + extend;                       /* the forced / column-0 cell left of diagonal 0 */
+    const int prof = QROWS ? (int)m.prof[r - 1] : 0;
+    const int rowg = QROWS ? 0 : (int)m.rowch[r - 1];
+    const int col0 = open + r * extend;                   /* gap2 of (r,0), 1477-1488 */
+    /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */
+    const VI upN = shfl_down1(Np[0], DPC_NEG), upG2 = shfl_down1(G2p[0], DPC_NEG);
+    VI Nn[CPL], G2n[CPL], a2[CPL], li[CPL], x[CPL];
+    VM p1[CPL], p2[CPL], pv[CPL], inval[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; j++) {
-      c[j] = c[j] + 1;
-      const VM valid = vand(kvalid[j], vlt_u(c[j] - 1, L2));
-      const VI ch = load_u8(m.colch, vsel(valid, c[j] - 1, 0));
-      VI P;
-      if (m.query_rows) P = (((prof >> (ch << 2)) & 15) ^ 8) - 8;
-      else P = load_i8(score, ((ch & 127) << 3) + rowg);
+      x[j] = cm1[j] + r;
+      inval[j] = vnot(vlt_u(x[j], L2));
       /* nogap, 1545-1561 */
-      const VM p1 = LATE ? (G1p[j] >= Np[j]) : (G1p[j] > Np[j]);
+      p1[j] = LATE ? (G1p[j] >= Np[j]) : (G1p[j] > Np[j]);
       const VI mx = vmax(Np[j], G1p[j]);
-      const VM p2 = LATE ? (G2p[j] >= mx) : (G2p[j] > mx);
-      const VI Nn = vmax(mx, G2p[j]) + P;
-      /* gap2, 1532-1542: (r-1, c) is diagonal k+1 of the previous row */
-      const VI Nu = shfl_down1(Np[j], j + 1 < CPL ? shfl_get(Np[j + 1 < CPL ? j + 1 : j], 0) : DPC_NEG);
-      const VI G2u = shfl_down1(G2p[j], j + 1 < CPL ? shfl_get(G2p[j + 1 < CPL ? j + 1 : j], 0) : DPC_NEG);
+      p2[j] = LATE ? (G2p[j] >= mx) : (G2p[j] > mx);
+      if (QROWS) Nn[j] = vmax(mx, G2p[j]) + ((prof >> sh[j]) & 15) - 8;
+      else Nn[j] = vmax(mx, G2p[j]) + load_i8(score, sh[j] + rowg);
+      /* gap2, 1532-1542 */
+      const VI Nu = j + 1 < CPL ? Np[j + 1 < CPL ? j + 1 : j] : upN;
+      const VI G2u = j + 1 < CPL ? G2p[j + 1 < CPL ? j + 1 : j] : upG2;
       const VI a = Nu + open;
-      const VM pv = LATE ? (G2u >= a) : (G2u > a);
-      const VI G2n = vmax(a, G2u) + extend;
-      /* gap1, 1519-1529, as an exclusive prefix maximum over the diagonals */
-      const VI a2 = Nn + open;
-      const VI s = vsel(valid, a2 - kE[j], cI[j]);
-      VI t = shfl_up(s, 1, carry);
-      t = vmax(t, shfl_up_keep(t, 1));
-      t = vmax(t, shfl_up_keep(t, 2));
-      t = vmax(t, shfl_up_keep(t, 4));
-      t = vmax(t, shfl_up_keep(t, 8));
-      t = vmax(t, shfl_up_keep(t, 16));
-      if (j + 1 < CPL) carry = shfl_get(vmax(t, s), 31);
-      const VI G1n = t + kE[j];
-      const VM h = LATE ? (G1n >= a2) : (G1n > a2);
+      pv[j] = LATE ? (G2u >= a) : (G2u > a);
+      G2n[j] = vmax(a, G2u) + extend;
+      /* gap1 feed: nogap + open - k*extend, running maximum inside the lane */
+      a2[j] = Nn[j] + open;
+      const VI s = a2[j] - kE[j];
+      li[j] = j == 0 ? s : vmax(li[j > 0 ? j - 1 : 0], s);
+    }
+    /* exclusive prefix maximum of the lane totals (1519-1529 unrolled along the row) */
+    VI t = shfl_up(li[CPL - 1], 1, DPC_NEG + extend);
+    t = vmax(t, shfl_up_keep(t, 1));
+    t = vmax(t, shfl_up_keep(t, 2));
+    t = vmax(t, shfl_up_keep(t, 4));
+    t = vmax(t, shfl_up_keep(t, 8));
+    t = vmax(t, shfl_up_keep(t, 16));
+    /* next row's column characters: every diagonal moves one column to the right */
+    {
+      const int gi = r + 32 * CPL - lband - 1;
+      const int chn = (gi >= 0 && gi < L2) ? (int)m.colch[gi] : 0;
+      const VI nxt = shfl_down1(sh[0], QROWS ? (chn << 2) : ((chn & 127) << 3));
+#pragma unroll
+      for (int j = 0; j + 1 < CPL; j++) sh[j] = sh[j + 1];
+      sh[CPL - 1] = nxt;
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; j++) {
+      const VI G1n = (j == 0 ? t : vmax(t, li[j > 0 ? j - 1 : 0])) + kE[j];
+      const VM h = LATE ? (G1n >= a2[j]) : (G1n > a2[j]);
       /* directions: four ballots, one 16-byte store */
-      const uint32_t b1 = vballot(p2), b0 = vballot(p1) & ~b1, b2 = vballot(h), b3 = vballot(pv);
+      const uint32_t b1 = vballot(p2[j]), b0 = vballot(p1[j]) & ~b1, b2 = vballot(h), b3 = vballot(pv[j]);
       store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
-      if (m.nband) store_i32(m.nband, (r - 1) * W + lane + 32 * j, Nn, kvalid[j]);
-      if (es.mode == 1) keep_better(bs, bk, Nn, r * (L2 + 1) + c[j], vand(valid, ebok[j]), LATE);
-      else if (es.mode == 2) { if (r == L1) keep_better(bs, bk, Nn, r * (L2 + 1) + c[j], valid, LATE); }
-      else if (es.mode == 3) { if (r == L1) keep_better(bs, bk, Nn, r * (L2 + 1) + c[j], vand(valid, c[j] == L2), LATE); }
-      /* what the next row sees on this diagonal: the cell, column 0, or nothing */
-      Np[j] = vsel(valid, Nn, DPC_NEG);
-      G1p[j] = vsel(valid, G1n, DPC_NEG);
-      G2p[j] = vsel(valid, G2n, vsel(c[j] == 0, col0, DPC_NEG));
+      if (NBAND) store_i32(m.nband, lane * CPL + ((r - 1) * W + j), Nn[j], kok[j]);
+      if (EP) keep_better(bs, bk, Nn[j], x[j] + (r * (L2 + 1) + 1), vand(vnot(inval[j]), ebok[j]), LATE);
+      /* what the next row sees on this diagonal: the cell, column 0, or NEG */
+      Np[j] = vsel(inval[j], DPC_NEG, Nn[j]);
+      G1p[j] = G1n;
+      G2p[j] = vsel(x[j] == -1, col0, vsel(inval[j], DPC_NEG, G2n[j]));
+    }
+  }
+  if (es.mode == 2 || es.mode == 3) {
+    /* last row: best of the band (2293-2355) or the corner (4541) */
+#pragma unroll
+    for (int j = 0; j < CPL; j++) {
+      const VI xl = cm1[j] + L1;
+      VM cand = vlt_u(xl, L2);
+      if (es.mode == 3) cand = vand(cand, xl == L2 - 1);
+      keep_better(bs, bk, Np[j], xl + (L1 * (L2 + 1) + 1), cand, LATE);
     }
   }
   reduce_better(bs, bk, LATE, &es.best.score, &es.best.key);
@@ -115,20 +146,20 @@ DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
 DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_direction, uint16_t *ops) {
   using namespace vec;
   const VI lane = lane_index();
-  const int cpl4 = m.cpl * 4;
+  const int cpl4 = m.cpl * 4, cmask = m.cpl - 1, csh = m.cplsh;
   int r = r0, c = c0, run = 0, nops = 0;
   while (dpc_inband(m, r, c)) {
     const int k = c - r + m.lband;
     const VI rr = r - lane;
     const VM inb = vand(rr >= 1, (c - lane) >= 1);
-    const VI widx = (vsel(inb, rr, 1) - 1) * cpl4 + ((k >> 5) << 2);
+    const VI widx = (vsel(inb, rr, 1) - 1) * cpl4 + ((k & cmask) << 2);
     const VI w0 = load_u32(m.dir, widx), w1 = load_u32(m.dir, widx + 1);
-    const VI turn = ((w0 | w1) >> (k & 31)) & 1;
+    const VI turn = ((w0 | w1) >> (k >> csh)) & 1;
     const uint32_t b = vballot(vor(vnot(inb), turn != 0));
     if (b == 0) { run += 32; r -= 32; c -= 32; continue; }
     const int f = first_set(b);
     if (r - f < 1 || c - f < 1) { run += f; r -= f; c -= f; break; }     /* ran into row 0 / column 0: STOP */
-    const int d = ((uint32_t)extract(w1, f) >> (k & 31)) & 1u ? DPC_VERT : DPC_HORIZ;
+    const int d = ((uint32_t)extract(w1, f) >> (k >> csh)) & 1u ? DPC_VERT : DPC_HORIZ;
     run += f + 1; r -= f + 1; c -= f + 1;
     store_u16_lane0(&ops[nops++], (run << 2) | DPC_OP_M); run = 0;
     int dist = 1;
@@ -141,8 +172,8 @@ DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_dir
           const VI cc = c - lane, kk = cc - r + m.lband;
           const VM in = vand(vand(cc >= 1, kk >= 0), vand(cc <= m.L2, kk < m.W));
           const VI k1 = vsel(in, vmax(kk - 1, 0), 0);
-          const VI w = load_u32(m.dir, ((r - 1) * m.cpl + (k1 >> 5)) * 4 + 2);
-          hz = vand(in, vor(vor(cc == 1, kk == 0), ((w >> (k1 & 31)) & 1) != 0));
+          const VI w = load_u32(m.dir, ((r - 1) * m.cpl + (k1 & cmask)) * 4 + 2);
+          hz = vand(in, vor(vor(cc == 1, kk == 0), ((w >> (k1 >> csh)) & 1) != 0));
         }
         const uint32_t nb = vballot(vnot(hz));
         if (nb == 0) { dist += 32; c -= 32; continue; }
@@ -161,8 +192,8 @@ DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_dir
           const VI kk = c - rr2 + m.lband;
           const VM in = vand(vand(rr2 >= 1, rr2 <= m.L1), vand(kk >= 0, kk < m.W));
           const VI k1 = vsel(in, kk, 0);
-          const VI w = load_u32(m.dir, ((vsel(in, rr2, 1) - 1) * m.cpl + (k1 >> 5)) * 4 + 3);
-          vt = vand(in, ((w >> (k1 & 31)) & 1) != 0);
+          const VI w = load_u32(m.dir, ((vsel(in, rr2, 1) - 1) * m.cpl + (k1 & cmask)) * 4 + 3);
+          vt = vand(in, ((w >> (k1 >> csh)) & 1) != 0);
         }
         const uint32_t nb = vballot(vnot(vt));
         if (nb == 0) { dist += 32; r -= 32; continue; }
@@ -179,19 +210,26 @@ DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_dir
   return nops;
 }
 
-/* The product's fill policy: row sweep for bands of up to 96 diagonals, memory-state fill beyond. */
+/* The product's fill policy: row sweep for bands of up to 128 diagonals, memory-state fill beyond. */
 struct RowFill {
   enum { fillmode = 2 };
+  template <int CPL, bool LATE>
+  DPC_HDM void go(const Mat &m, const int8_t *score, EndSearch &es) const {
+    if (!m.query_rows) dpc_fill_rows<CPL, LATE, false, true, false>(m, score, es);          /* cDNA gap */
+    else if (m.nband) dpc_fill_rows<CPL, LATE, false, true, true>(m, score, es);            /* genome gap */
+    else if (es.mode == 1) dpc_fill_rows<CPL, LATE, true, false, true>(m, score, es);       /* end gap, best end point */
+    else dpc_fill_rows<CPL, LATE, false, false, true>(m, score, es);                        /* single gap, end to query end */
+  }
   DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
     if (!m.planes) { dpc_fill_generic(m, st, score, es, ln); return; }
     if (m.late) {
-      if (m.cpl == 1) dpc_fill_rows<1, true>(m, score, es);
-      else if (m.cpl == 2) dpc_fill_rows<2, true>(m, score, es);
-      else dpc_fill_rows<3, true>(m, score, es);
+      if (m.cpl == 1) go<1, true>(m, score, es);
+      else if (m.cpl == 2) go<2, true>(m, score, es);
+      else go<4, true>(m, score, es);
     } else {
-      if (m.cpl == 1) dpc_fill_rows<1, false>(m, score, es);
-      else if (m.cpl == 2) dpc_fill_rows<2, false>(m, score, es);
-      else dpc_fill_rows<3, false>(m, score, es);
+      if (m.cpl == 1) go<1, false>(m, score, es);
+      else if (m.cpl == 2) go<2, false>(m, score, es);
+      else go<4, false>(m, score, es);
     }
   }
   DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {

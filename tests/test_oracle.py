@@ -81,10 +81,10 @@ def test_device_routines_on_cpu_match_oracle(workload, port, emul, fill):
 
 
 def test_band_widths_around_the_chunk_limits(workload, port, emul):
-    """Row-sweep chunks hold 32 diagonals: bands of 31..34, 63..66 and 95..98 diagonals (the last ones fall back
-    to the memory-state fill), with and without jump_late_p."""
+    """The row sweep gives every lane 1, 2 or 4 diagonals: bands of 31..34, 63..66 and 127..130 diagonals (the last
+    ones fall back to the memory-state fill), with and without jump_late_p."""
     sets = []
-    for eb in (15, 16, 31, 32, 47, 48):
+    for eb in (15, 16, 31, 32, 63, 64):
         p = workload.single_gaps(120, extraband=eb, seed=1000 + eb)
         p["length2"] = np.maximum(p["length1"] + np.arange(len(p)) % 4 - 1, 1)      # W = 2 eb + 1 + |L2 - L1|
         sets.append(p)
