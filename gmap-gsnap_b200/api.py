@@ -423,6 +423,14 @@ class CudaLib(_SolverLib):
             L.dpc_result(self.ctx, i, res[i:i + 1].ctypes.data_as(C.c_void_p))
         return res
 
+    def solve_into(self, problems, results, pairs, pair_off):
+        """dpc_solve into caller-owned (reusable) output arrays; returns the number of pair records."""
+        self.refresh_genome()
+        rc = self.lib.dpc_solve(self.ctx, _ptr(problems), len(problems), _ptr(results),
+                                _ptr(pairs) if pairs is not None else None, len(pairs) if pairs is not None else 0, _ptr(pair_off))
+        self.check(rc, "dpc_solve")
+        return int(pair_off[len(problems)])
+
     def stats(self):
         s = Stats()
         self.check(self.lib.dpc_get_stats(self.ctx, C.byref(s)), "dpc_get_stats")

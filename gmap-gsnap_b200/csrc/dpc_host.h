@@ -280,7 +280,8 @@ struct Batch {
     HostProb h;
     h.q0 = h.q1 = h.aux = 0; h.dev = -1; h.L1 = p.length1; h.L2 = p.length2;
     result_init(r, p);
-    DevProb d;
+    dprobs.reserve(dprobs.size() + 1);
+    DevProb &d = dprobs.data()[dprobs.size()];      /* built in place; committed below when it goes to the device */
     memset(&d, 0, sizeof d);
     bool todev = false;
     d.kind = (uint8_t)p.kind; d.endalign = (uint8_t)p.endalign;
@@ -407,7 +408,7 @@ struct Batch {
     if (todev) {
       if (!segment_ok(p)) return DPC_ERR_ARG;
       h.dev = (int32_t)dprobs.size();
-      dprobs.push_back(d);
+      dprobs.grow(1);
       dev2host.push_back((uint32_t)probs.size());
     }
     probs.push_back(h);

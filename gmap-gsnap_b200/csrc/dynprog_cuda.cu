@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -177,9 +178,10 @@ struct Engine {
   int nlaunch;
   float ms_total;
   int64_t h2d_bytes, d2h_bytes;
+  double t_finalize;
 
   Engine() : device(0), stream(0), ev0(0), ev1(0), live(false), ovf_cap(0), flushed(false), waited(false), nlaunch(0),
-             ms_total(0), h2d_bytes(0), d2h_bytes(0) {}
+             ms_total(0), h2d_bytes(0), d2h_bytes(0), t_finalize(0) {}
 
   int open(int dev) {
     device = dev;
@@ -343,11 +345,15 @@ struct Engine {
         CK(cudaStreamSynchronize(stream));
         d2h_bytes += (int64_t)used * 2;
       }
+      struct timespec ta, tb;
+      clock_gettime(CLOCK_MONOTONIC, &ta);
       for (size_t k = 0; k < n; k++) {
         const DevRes &dr = h_res[k];
         if (!(dr.status & DPC_ST_DONE) || (dr.status & DPC_ST_OVF_LOST)) return DPC_ERR_CUDA;
         b.finalize((int)b.dev2host[k], dr, ops_of(dr), scratch);
       }
+      clock_gettime(CLOCK_MONOTONIC, &tb);
+      t_finalize = (tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec);
     }
     waited = true;
     return DPC_OK;
@@ -558,6 +564,12 @@ int dpc_pairs(dpc_ctx_t *c, int ticket, dpc_pair_t *out, int cap) {
 /* Bulk call: the problems are cut into chunks; host threads pack a chunk, queue its copies and kernels on
  * the chunk's own stream, and finalise it when it is back, so packing, PCIe traffic, kernels and Pair
  * rebuild of different chunks overlap.  Results and pairs come out in input order. */
+static double now_s() {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
 int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *results,
               dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off) {
   if (!c || n < 0 || (n > 0 && (!problems || !results))) return DPC_ERR_ARG;
@@ -576,11 +588,16 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
     if (e->open(device) != DPC_OK) { delete e; return DPC_ERR_CUDA; }
     c->subs.push_back(e);
   }
+  static const bool timing = getenv("DPC_TIMING") != NULL;
   std::atomic<int> err(0);
+  std::atomic<int64_t> t_pack(0), t_flush(0), t_wait(0), t_fin(0), t_pairs(0);
+  double tA = 0, tB = 0;
   int64_t pair_base = 0;
+  std::vector<int64_t> chunk_pairs((size_t)wave + 1);
   for (int c0 = 0; c0 < nchunks; c0 += wave) {
     const int nc = std::min(wave, nchunks - c0);
-    /* phase A: pack, solve on the device, finalise */
+    double t0 = now_s();
+    /* phase A: pack, solve on the device, finalise, count the chunk's pairs */
     c->workers->run(nc, [&](int j) {
       if (err.load()) return;
       Engine &e = *c->subs[j];
@@ -588,54 +605,61 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
       int r = 0;
       try {
         cudaSetDevice(device);
+        double a0 = timing ? now_s() : 0;
         e.reset();
         r = e.batch.add_ext(problems + lo, results + lo, cnt);
+        double a1 = timing ? now_s() : 0;
         if (r >= 0) r = e.flush();
+        double a2 = timing ? now_s() : 0;
         if (r >= 0) r = e.wait();
+        double a3 = timing ? now_s() : 0;
+        int64_t s = 0;
+        for (int i = 0; i < cnt; i++) s += results[lo + i].npairs;
+        chunk_pairs[(size_t)j] = s;
+        if (timing) {
+          t_pack += (int64_t)((a1 - a0) * 1e9); t_flush += (int64_t)((a2 - a1) * 1e9);
+          t_wait += (int64_t)((a3 - a2) * 1e9); t_fin += (int64_t)(e.t_finalize * 1e9);
+        }
       } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
       if (r < 0) { int z = 0; err.compare_exchange_strong(z, r); }
     });
     if (err.load()) return err.load();
-    const int lo = c0 * chunk, hi = std::min(n, (c0 + nc) * chunk);
-    const int64_t wave_base = pair_base;
-    if (pair_off) for (int i = lo; i < hi; i++) { pair_off[i] = pair_base; pair_base += results[i].npairs; }
-    else for (int i = lo; i < hi; i++) pair_base += results[i].npairs;
-    if (pairs) {
-      if (pair_base > pair_cap) return DPC_ERR_NOMEM;
-      /* phase B: rebuild the Pair records of each chunk straight into the caller's array */
-      std::vector<int64_t> chunk_base((size_t)nc + 1);
-      chunk_base[0] = wave_base;
-      for (int j = 0; j < nc; j++) {
-        const int l = (c0 + j) * chunk, h = std::min(n, l + chunk);
-        int64_t s = 0;
-        for (int i = l; i < h; i++) s += results[i].npairs;
-        chunk_base[(size_t)j + 1] = chunk_base[(size_t)j] + s;
-      }
+    double t1 = now_s();
+    /* offsets of the chunks' pair blocks */
+    std::vector<int64_t> chunk_base((size_t)nc + 1);
+    chunk_base[0] = pair_base;
+    for (int j = 0; j < nc; j++) chunk_base[(size_t)j + 1] = chunk_base[(size_t)j] + chunk_pairs[(size_t)j];
+    pair_base = chunk_base[(size_t)nc];
+    if (pairs && pair_base > pair_cap) return DPC_ERR_NOMEM;
+    if (pairs || pair_off) {
+      /* phase B: offsets, and the Pair records of each chunk rebuilt straight into the caller's array */
       c->workers->run(nc, [&](int j) {
         if (err.load()) return;
         Engine &e = *c->subs[j];
         const int l = (c0 + j) * chunk, cnt = std::min(chunk, n - l);
         int64_t at = chunk_base[(size_t)j];
+        double b0 = timing ? now_s() : 0;
         try {
           for (int i = 0; i < cnt; i++) {
             const int np = results[l + i].npairs;
-            if (np == 0) continue;
-            int k;
-            if (at + e.batch.max_pairs(i) <= pair_cap) k = e.pairs_into(i, pairs + at);     /* room for the worst case */
-            else {
-              dpc_pair_t *tmp = Batch::fit(e.scratch.out, e.batch.max_pairs(i));
-              k = e.pairs_into(i, tmp);
-              memcpy(pairs + at, tmp, (size_t)k * sizeof(dpc_pair_t));
-            }
+            if (pair_off) pair_off[l + i] = at;
+            if (!pairs || np == 0) { at += np; continue; }
+            int k = e.pairs_into(i, pairs + at);
             if (k != np) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_STATE); return; }
             at += k;
           }
         } catch (const std::bad_alloc &) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_NOMEM); }
+        if (timing) t_pairs += (int64_t)((now_s() - b0) * 1e9);
       });
       if (err.load()) return err.load();
     }
+    double t2 = now_s();
+    tA += t1 - t0; tB += t2 - t1;
   }
   if (pair_off) pair_off[n] = pair_base;
+  if (timing)
+    fprintf(stderr, "dpc_solve n=%d chunks=%d x %d threads=%d: phaseA %.1f ms phaseB %.1f ms | thread-sum pack %.1f flush %.1f wait %.1f (finalize %.1f) pairs %.1f ms\n",
+            n, nchunks, chunk, T, tA * 1e3, tB * 1e3, t_pack / 1e6, t_flush / 1e6, t_wait / 1e6, t_fin / 1e6, t_pairs / 1e6);
   return DPC_OK;
 }
 
