@@ -20,7 +20,7 @@ oracle:
 # single-lane CPU build of the device routines: test scaffolding only (tests/emul/dpc_emul.cpp)
 emul: tests/emul/libdpc_emul.so
 tests/emul/libdpc_emul.so: tests/emul/dpc_emul.cpp $(PKG)/csrc/dpc_core.h $(PKG)/csrc/dpc_host.h include/dynprog_cuda.h
-	g++ -O2 -fPIC -Wall -Wextra -shared -o $@ tests/emul/dpc_emul.cpp
+	g++ -O2 -fPIC -Wall -Wextra -Wno-unknown-pragmas -shared -o $@ tests/emul/dpc_emul.cpp
 
 clean:
 	rm -f $(PKG)/csrc/*.so $(PKG)/host/*.so $(PKG)/csrc/ptxas.log tests/emul/*.so

@@ -14,6 +14,9 @@
 #include <string.h>
 #include <ctype.h>
 #include <stdlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <new>
 #include <vector>
 #include "../../include/dynprog_cuda.h"
@@ -168,10 +171,18 @@ struct HostProb {
 /* pair records are written through a bare cursor: every caller sizes the destination first */
 struct Out {
   dpc_pair_t *p; int n;
+  bool stream;          /* destination is the caller's big array: write around the cache when the record is 16-aligned */
   void push(int qpos, int gpos, char cdna, char comp, char genome, int idx, int gapp) {
-    dpc_pair_t &pr = p[n++];
-    pr.querypos = qpos; pr.genomepos = gpos; pr.dynprogindex = idx;
-    pr.cdna = cdna; pr.comp = comp; pr.genome = genome; pr.gapp = (uint8_t)gapp;
+    dpc_pair_t *pr = &p[n++];
+#if defined(__SSE2__)
+    const uint32_t tail = (uint32_t)(uint8_t)cdna | ((uint32_t)(uint8_t)comp << 8) | ((uint32_t)(uint8_t)genome << 16) | ((uint32_t)(uint8_t)gapp << 24);
+    const __m128i v = _mm_set_epi32((int)tail, idx, gpos, qpos);
+    if (stream && (((uintptr_t)pr) & 15) == 0) _mm_stream_si128((__m128i *)pr, v);
+    else _mm_storeu_si128((__m128i *)pr, v);
+#else
+    pr->querypos = qpos; pr->genomepos = gpos; pr->dynprogindex = idx;
+    pr->cdna = cdna; pr->comp = comp; pr->genome = genome; pr->gapp = (uint8_t)gapp;
+#endif
   }
   void push_gapholder() { push(-1, -1, ' ', ' ', ' ', 0, 1); }       /* pairpool.c:352-401 */
 };
@@ -430,7 +441,7 @@ struct Batch {
           char c1 = qch[qi], c2 = gch[gi];
           if (!genome_rows && c2 == '*') continue;                    /* 2644 */
           char comp = '*';
-          if ((char)dpc_query_uc(c1) != c2) {
+          if (c1 != c2 && (char)dpc_query_uc(c1) != c2) {
             bool consistent = genome_rows ? g.CONS[c2 & 127][c1 & 127] : g.CONS[c1 & 127][c2 & 127];   /* 2654 vs 2752 */
             comp = consistent ? ':' : ' ';
           }
@@ -478,12 +489,12 @@ struct Batch {
     default: return h.L1 + h.L2 + 8;
     }
   }
-  int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s) const {
+  int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s, bool stream_dst = false) const {
     const HostProb &h = probs[i];
     const dpc_problem_t &p = P(i);
     const uint32_t *blocks = G().setup.genome_blocks;
     const char *q = (const char *)&pool[h.q0];
-    Out out; out.p = dst; out.n = 0;
+    Out out; out.p = dst; out.n = 0; out.stream = stream_dst;
     switch (p.kind) {
     case DPC_SINGLE_GAP: {
       char *ga = fit(s.ga, h.L2);
@@ -497,7 +508,7 @@ struct Batch {
       char *qa = fit(s.qa, h.L1), *ga = fit(s.ga, h.L2);
       for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
       gather_genome(p, blocks, p.offset2, h.L2, five, ga);
-      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0;
+      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0; sL.stream = false;
       replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex);
       if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) break;   /* 5259 */
       int first = 0;                                                   /* 5265-5268 */
@@ -512,7 +523,7 @@ struct Batch {
       for (int k = 0; k < L1; k++) qb[k] = q[L1 - 1 - k];
       gather_genome(p, blocks, p.offset2, L2L, false, ga);
       gather_genome(p, blocks, p.offset2R, L2R, true, gb);
-      Out sR, sL; sR.p = fit(s.sR, L1 + L2R + 2); sR.n = 0; sL.p = fit(s.sL, L1 + L2L + 2); sL.n = 0;
+      Out sR, sL; sR.p = fit(s.sR, L1 + L2R + 2); sR.n = 0; sL.p = fit(s.sL, L1 + L2L + 2); sL.n = 0; sR.stream = sL.stream = false;
       replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, revoffset1, p.offset2R, true, false, p.dynprogindex);
       replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex);
       if (sR.n + sL.n > 0) {                                           /* List_length == 1 -> NULL, 5051 */
@@ -530,9 +541,9 @@ struct Batch {
       for (int k = 0; k < L1R; k++) qb[k] = q[span - 1 - k];
       gather_genome(p, blocks, p.offset2, L2, false, ga);
       gather_genome(p, blocks, revoffset2, L2, true, gb);
-      Out sR, sL; sR.p = fit(s.sR, L1R + L2 + 2); sR.n = 0; sL.p = fit(s.sL, L1L + L2 + 2); sL.n = 0;
+      Out sR, sL; sR.p = fit(s.sR, L1R + L2 + 2); sR.n = 0; sL.p = fit(s.sL, L1L + L2 + 2); sL.n = 0; sR.stream = sL.stream = false;
       dpc_pair_t midbuf[24];
-      Out mid; mid.p = midbuf; mid.n = 0;
+      Out mid; mid.p = midbuf; mid.n = 0; mid.stream = false;
       replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, p.offset1R, revoffset2, true, true, p.dynprogindex);
       int queryjump = (p.offset1R - dr.bestcR) - (p.offset1 + dr.bestcL) + 1;     /* 4725-4726 */
       int genomejump = (revoffset2 - dr.bestrR) - (p.offset2 + dr.bestrL) + 1;

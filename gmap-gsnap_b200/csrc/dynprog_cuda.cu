@@ -359,11 +359,11 @@ struct Engine {
     return DPC_OK;
   }
 
-  int pairs_into(int ticket, dpc_pair_t *dst) {
+  int pairs_into(int ticket, dpc_pair_t *dst, bool stream_dst = false) {
     const HostProb &h = batch.probs[ticket];
     if (h.dev < 0) return 0;
     const DevRes &dr = h_res[h.dev];
-    return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch);
+    return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch, stream_dst);
   }
 };
 
@@ -580,86 +580,85 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
   if (!c->workers) c->workers = new Workers(T);
   int chunk = n / (4 * T) + 1;
   if (chunk < 2048) chunk = 2048;
-  if (chunk > 32768) chunk = 32768;
+  if (chunk > 16384) chunk = 16384;
   const int nchunks = (n + chunk - 1) / chunk;
-  const int wave = 4 * T;                                     /* engines (chunks in flight) per wave */
-  while ((int)c->subs.size() < std::min(nchunks, wave)) {
+  const int nengines = std::min(nchunks, 4 * T);              /* chunks in flight */
+  while ((int)c->subs.size() < nengines) {
     Engine *e = new Engine();
     if (e->open(device) != DPC_OK) { delete e; return DPC_ERR_CUDA; }
     c->subs.push_back(e);
   }
   static const bool timing = getenv("DPC_TIMING") != NULL;
   std::atomic<int> err(0);
-  std::atomic<int64_t> t_pack(0), t_flush(0), t_wait(0), t_fin(0), t_pairs(0);
-  double tA = 0, tB = 0;
-  int64_t pair_base = 0;
-  std::vector<int64_t> chunk_pairs((size_t)wave + 1);
-  for (int c0 = 0; c0 < nchunks; c0 += wave) {
-    const int nc = std::min(wave, nchunks - c0);
-    double t0 = now_s();
-    /* phase A: pack, solve on the device, finalise, count the chunk's pairs */
-    c->workers->run(nc, [&](int j) {
-      if (err.load()) return;
-      Engine &e = *c->subs[j];
-      const int lo = (c0 + j) * chunk, cnt = std::min(chunk, n - lo);
-      int r = 0;
+  std::atomic<int64_t> t_pack(0), t_flush(0), t_wait(0), t_fin(0), t_pairs(0), t_stall(0);
+  /* chunk j publishes the end offset of its pair block once every chunk before it has; a chunk's engine is
+   * free again when the chunk's pairs are out */
+  std::vector<std::atomic<int64_t>> chunk_end((size_t)nchunks);
+  std::vector<std::atomic<int>> chunk_done((size_t)nchunks);
+  for (int j = 0; j < nchunks; j++) { chunk_end[(size_t)j].store(-1); chunk_done[(size_t)j].store(0); }
+  const double t0 = now_s();
+  c->workers->run(nchunks, [&](int j) {
+    Engine &e = *c->subs[(size_t)(j % nengines)];
+    const int lo = j * chunk, cnt = std::min(chunk, n - lo);
+    int r = 0;
+    int64_t mine = 0;
+    double a0 = timing ? now_s() : 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    if (j >= nengines) while (!chunk_done[(size_t)(j - nengines)].load(std::memory_order_acquire)) std::this_thread::yield();
+    if (!err.load()) {
       try {
         cudaSetDevice(device);
-        double a0 = timing ? now_s() : 0;
+        if (timing) a0 = now_s();
         e.reset();
         r = e.batch.add_ext(problems + lo, results + lo, cnt);
-        double a1 = timing ? now_s() : 0;
+        if (timing) a1 = now_s();
         if (r >= 0) r = e.flush();
-        double a2 = timing ? now_s() : 0;
+        if (timing) a2 = now_s();
         if (r >= 0) r = e.wait();
-        double a3 = timing ? now_s() : 0;
-        int64_t s = 0;
-        for (int i = 0; i < cnt; i++) s += results[lo + i].npairs;
-        chunk_pairs[(size_t)j] = s;
-        if (timing) {
-          t_pack += (int64_t)((a1 - a0) * 1e9); t_flush += (int64_t)((a2 - a1) * 1e9);
-          t_wait += (int64_t)((a3 - a2) * 1e9); t_fin += (int64_t)(e.t_finalize * 1e9);
-        }
+        if (timing) a3 = now_s();
+        if (r >= 0) for (int i = 0; i < cnt; i++) mine += results[lo + i].npairs;
       } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
       if (r < 0) { int z = 0; err.compare_exchange_strong(z, r); }
-    });
-    if (err.load()) return err.load();
-    double t1 = now_s();
-    /* offsets of the chunks' pair blocks */
-    std::vector<int64_t> chunk_base((size_t)nc + 1);
-    chunk_base[0] = pair_base;
-    for (int j = 0; j < nc; j++) chunk_base[(size_t)j + 1] = chunk_base[(size_t)j] + chunk_pairs[(size_t)j];
-    pair_base = chunk_base[(size_t)nc];
-    if (pairs && pair_base > pair_cap) return DPC_ERR_NOMEM;
-    if (pairs || pair_off) {
-      /* phase B: offsets, and the Pair records of each chunk rebuilt straight into the caller's array */
-      c->workers->run(nc, [&](int j) {
-        if (err.load()) return;
-        Engine &e = *c->subs[j];
-        const int l = (c0 + j) * chunk, cnt = std::min(chunk, n - l);
-        int64_t at = chunk_base[(size_t)j];
-        double b0 = timing ? now_s() : 0;
+    }
+    /* my block starts where the previous chunk's ends */
+    int64_t at = 0;
+    if (j > 0) {
+      int64_t prev;
+      while ((prev = chunk_end[(size_t)(j - 1)].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+      at = prev;
+    }
+    chunk_end[(size_t)j].store(at + mine, std::memory_order_release);
+    if (timing) a4 = now_s();
+    if (!err.load() && (pairs || pair_off)) {
+      if (pairs && at + mine > pair_cap) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_NOMEM); }
+      else {
         try {
           for (int i = 0; i < cnt; i++) {
-            const int np = results[l + i].npairs;
-            if (pair_off) pair_off[l + i] = at;
+            const int np = results[lo + i].npairs;
+            if (pair_off) pair_off[lo + i] = at;
             if (!pairs || np == 0) { at += np; continue; }
-            int k = e.pairs_into(i, pairs + at);
-            if (k != np) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_STATE); return; }
+            int k = e.pairs_into(i, pairs + at, true);
+            if (k != np) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_STATE); break; }
             at += k;
           }
         } catch (const std::bad_alloc &) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_NOMEM); }
-        if (timing) t_pairs += (int64_t)((now_s() - b0) * 1e9);
-      });
-      if (err.load()) return err.load();
+      }
     }
-    double t2 = now_s();
-    tA += t1 - t0; tB += t2 - t1;
-  }
-  if (pair_off) pair_off[n] = pair_base;
+    chunk_done[(size_t)j].store(1, std::memory_order_release);
+    if (timing) {
+      double a5 = now_s();
+      t_pack += (int64_t)((a1 - a0) * 1e9); t_flush += (int64_t)((a2 - a1) * 1e9);
+      t_wait += (int64_t)((a3 - a2) * 1e9); t_fin += (int64_t)(e.t_finalize * 1e9);
+      t_stall += (int64_t)((a4 - a3) * 1e9); t_pairs += (int64_t)((a5 - a4) * 1e9);
+    }
+  });
+#if defined(__SSE2__)
+  _mm_sfence();
+#endif
+  if (err.load()) return err.load();
+  if (pair_off) pair_off[n] = nchunks ? chunk_end[(size_t)nchunks - 1].load() : 0;
   if (timing)
-    fprintf(stderr, "dpc_solve n=%d chunks=%d x %d threads=%d: phaseA %.1f ms phaseB %.1f ms | thread-sum pack %.1f flush %.1f wait %.1f (finalize %.1f) pairs %.1f ms\n",
-            n, nchunks, chunk, T, tA * 1e3, tB * 1e3, t_pack / 1e6, t_flush / 1e6, t_wait / 1e6, t_fin / 1e6, t_pairs / 1e6);
+    fprintf(stderr, "dpc_solve n=%d chunks=%d x %d threads=%d engines=%d: %.1f ms | thread-sum pack %.1f flush %.1f wait %.1f (finalize %.1f) stall %.1f pairs %.1f ms\n",
+            n, nchunks, chunk, T, nengines, (now_s() - t0) * 1e3, t_pack / 1e6, t_flush / 1e6, t_wait / 1e6, t_fin / 1e6, t_stall / 1e6, t_pairs / 1e6);
   return DPC_OK;
 }
 
