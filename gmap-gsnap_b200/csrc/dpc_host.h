@@ -14,9 +14,6 @@
 #include <string.h>
 #include <ctype.h>
 #include <stdlib.h>
-#if defined(__SSE2__)
-#include <emmintrin.h>
-#endif
 #include <new>
 #include <vector>
 #include "../../include/dynprog_cuda.h"
@@ -115,16 +112,41 @@ inline char host_genomic_nt(const dpc_problem_t &p, int genomicpos) {   /* get_g
   return compl_nt[dpc_genome_code(blocks, p.chroffset + p.chrpos + (p.genomiclength - 1) - (uint32_t)genomicpos)];
 }
 
-/* gathers get_genomic_nt(start +/- k) for k = 0..len-1 */
+/* gathers get_genomic_nt(start +/- k) for k = 0..len-1 (dynprog.c:403-441): positions outside the segment give
+ * '*'; inside, the bases come 32 at a time out of the (high, low, flags) blocks of genome.c:9325-9362 */
 inline void gather_genome(const dpc_problem_t &p, const uint32_t *blocks, int start, int len, bool rev, char *out) {
-  static const char fwd_nt[6] = { 'A', 'C', 'G', 'T', 'N', '*' }, compl_nt[6] = { 'T', 'G', 'C', 'A', 'N', '*' };
-  const bool star = allstar(p);
-  const uint32_t glen = p.genomiclength, base = p.chroffset + p.chrpos;
-  for (int k = 0; k < len; k++) {
-    int pos = rev ? start - k : start + k;
-    if (star || pos < 0 || (uint32_t)pos >= glen) out[k] = '*';
-    else if (p.watsonp) out[k] = fwd_nt[dpc_genome_code(blocks, base + (uint32_t)pos)];
-    else out[k] = compl_nt[dpc_genome_code(blocks, base + (glen - 1) - (uint32_t)pos)];
+  static const char fwd_nt[4] = { 'A', 'C', 'G', 'T' }, compl_nt[4] = { 'T', 'G', 'C', 'A' };
+  if (len <= 0) return;
+  /* segment positions covered, ascending: [lo, lo+len) ; out index of position pos is rev ? start-pos : pos-start */
+  const int lo = rev ? start - (len - 1) : start;
+  if (allstar(p)) { memset(out, '*', (size_t)len); return; }
+  const int64_t glen = p.genomiclength;
+  const uint32_t base = p.chroffset + p.chrpos;
+  const bool watson = p.watsonp != 0;
+  const char *nt = watson ? fwd_nt : compl_nt;
+  /* as the genomic coordinate ascends, the output index moves by dir */
+  for (int pos = lo; pos < lo + len;) {
+    const int oi = rev ? start - pos : pos - start;
+    if (pos < 0 || pos >= glen) { out[oi] = '*'; pos++; continue; }
+    const uint32_t g = watson ? base + (uint32_t)pos : base + (uint32_t)(glen - 1 - pos);   /* absolute genome position */
+    const uint32_t *b = blocks + (uint64_t)(g >> 5) * 3;
+    const uint64_t bits = ((uint64_t)b[0] << 32) | b[1];
+    const uint32_t flags = b[2];
+    /* run inside this block: the absolute position ascends with pos on Watson, descends on Crick */
+    int bit = (int)(g & 31);
+    int run = watson ? 32 - bit : bit + 1;
+    if (run > lo + len - pos) run = lo + len - pos;
+    if ((int64_t)pos + run > glen) run = (int)(glen - pos);
+    const int od = rev ? -1 : 1;
+    int o = oi;
+    if (watson) {
+      for (int k = 0; k < run; k++, bit++, o += od)
+        out[o] = ((flags >> bit) & 1u) ? 'N' : nt[(bits >> (2 * bit)) & 3u];
+    } else {
+      for (int k = 0; k < run; k++, bit--, o += od)
+        out[o] = ((flags >> bit) & 1u) ? 'N' : nt[(bits >> (2 * bit)) & 3u];
+    }
+    pos += run;
   }
 }
 
@@ -171,18 +193,13 @@ struct HostProb {
 /* pair records are written through a bare cursor: every caller sizes the destination first */
 struct Out {
   dpc_pair_t *p; int n;
-  bool stream;          /* destination is the caller's big array: write around the cache when the record is 16-aligned */
   void push(int qpos, int gpos, char cdna, char comp, char genome, int idx, int gapp) {
-    dpc_pair_t *pr = &p[n++];
-#if defined(__SSE2__)
-    const uint32_t tail = (uint32_t)(uint8_t)cdna | ((uint32_t)(uint8_t)comp << 8) | ((uint32_t)(uint8_t)genome << 16) | ((uint32_t)(uint8_t)gapp << 24);
-    const __m128i v = _mm_set_epi32((int)tail, idx, gpos, qpos);
-    if (stream && (((uintptr_t)pr) & 15) == 0) _mm_stream_si128((__m128i *)pr, v);
-    else _mm_storeu_si128((__m128i *)pr, v);
-#else
-    pr->querypos = qpos; pr->genomepos = gpos; pr->dynprogindex = idx;
-    pr->cdna = cdna; pr->comp = comp; pr->genome = genome; pr->gapp = (uint8_t)gapp;
-#endif
+    /* dpc_pair_t is 16 bytes: {querypos, genomepos} and {dynprogindex, cdna, comp, genome, gapp}: two 8-byte stores */
+    uint64_t lo = (uint32_t)qpos | ((uint64_t)(uint32_t)gpos << 32);
+    uint64_t hi = (uint32_t)idx | ((uint64_t)(uint8_t)cdna << 32) | ((uint64_t)(uint8_t)comp << 40) |
+                  ((uint64_t)(uint8_t)genome << 48) | ((uint64_t)(uint8_t)gapp << 56);
+    uint64_t *w = (uint64_t *)&p[n++];
+    w[0] = lo; w[1] = hi;
   }
   void push_gapholder() { push(-1, -1, ' ', ' ', ' ', 0, 1); }       /* pairpool.c:352-401 */
 };
@@ -429,45 +446,57 @@ struct Batch {
   /* ---- rebuild of the Pair records (dynprog.c:2372-2712 and the assembly in each entry point) */
 
   /* One matrix: replays the ops from (r,c).  qch / gch are in matrix order. */
-  static void replay(Out &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
-                     int q0, int g0, bool revp, bool genome_rows, int idx) {
-    const int step = revp ? -1 : 1;
+  template <bool REV, bool GROWS>
+  static void replay_t(Out &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
+                       int q0, int g0, int idx) {
+    const int step = REV ? -1 : 1;
     const Globals &g = G();
     for (int i = 0; i < nops; i++) {
-      int op = ops[i] & 3, len = ops[i] >> 2;
+      const int op = ops[i] & 3, len = ops[i] >> 2;
       if (op == DPC_OP_M) {
-        for (int j = 0; j < len; j++) {
-          int qi = (genome_rows ? c : r) - 1 - j, gi = (genome_rows ? r : c) - 1 - j;
-          char c1 = qch[qi], c2 = gch[gi];
-          if (!genome_rows && c2 == '*') continue;                    /* 2644 */
+        int qi = (GROWS ? c : r) - 1, gi = (GROWS ? r : c) - 1;
+        int qpos = q0 + step * qi, gpos = g0 + step * gi;
+        for (int j = 0; j < len; j++, qi--, gi--, qpos -= step, gpos -= step) {
+          const char c1 = qch[qi], c2 = gch[gi];
+          if (!GROWS && c2 == '*') continue;                          /* 2644 */
           char comp = '*';
           if (c1 != c2 && (char)dpc_query_uc(c1) != c2) {
-            bool consistent = genome_rows ? g.CONS[c2 & 127][c1 & 127] : g.CONS[c1 & 127][c2 & 127];   /* 2654 vs 2752 */
+            const bool consistent = GROWS ? g.CONS[c2 & 127][c1 & 127] : g.CONS[c1 & 127][c2 & 127];   /* 2654 vs 2752 */
             comp = consistent ? ':' : ' ';
           }
-          st.push(q0 + step * qi, g0 + step * gi, c1, comp, c2, idx, 0);
+          st.push(qpos, gpos, c1, comp, c2, idx, 0);
         }
         r -= len; c -= len;
         continue;
       }
-      bool along_cols = (op == DPC_OP_QSKIP) ? genome_rows : !genome_rows;
+      const bool along_cols = (op == DPC_OP_QSKIP) ? GROWS : !GROWS;
       if (along_cols) c -= len; else r -= len;
       if (op == DPC_OP_GAPHOLDER) { st.push_gapholder(); continue; }  /* 2507 */
       if (op == DPC_OP_GSKIP) {                                       /* add_genomeskip dashes, 2444-2505 */
-        int lo = genome_rows ? r : c, qi2 = genome_rows ? c - 1 : r - 1;
-        int qpos = revp ? q0 - qi2 : q0 + qi2 + 1;
+        const int lo = GROWS ? r : c, qi2 = GROWS ? c - 1 : r - 1;
+        const int qpos = REV ? q0 - qi2 : q0 + qi2 + 1;
         for (int j = 0; j < len; j++) {
-          int gi2 = lo + len - 1 - j;
+          const int gi2 = lo + len - 1 - j;
           st.push(qpos, g0 + step * gi2, ' ', '-', gch[gi2], idx, 0);
         }
       } else {                                                        /* add_queryskip, 2372-2413 */
-        int lo = genome_rows ? c : r, gi2 = genome_rows ? r - 1 : c - 1;
-        int gpos = revp ? g0 - gi2 : g0 + gi2 + 1;
+        const int lo = GROWS ? c : r, gi2 = GROWS ? r - 1 : c - 1;
+        const int gpos = REV ? g0 - gi2 : g0 + gi2 + 1;
         for (int j = 0; j < len; j++) {
-          int qi2 = lo + len - 1 - j;
+          const int qi2 = lo + len - 1 - j;
           st.push(q0 + step * qi2, gpos, qch[qi2], '-', ' ', idx, 0);
         }
       }
+    }
+  }
+  static void replay(Out &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
+                     int q0, int g0, bool revp, bool genome_rows, int idx) {
+    if (revp) {
+      if (genome_rows) replay_t<true, true>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
+      else replay_t<true, false>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
+    } else {
+      if (genome_rows) replay_t<false, true>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
+      else replay_t<false, false>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
     }
   }
 
@@ -489,12 +518,12 @@ struct Batch {
     default: return h.L1 + h.L2 + 8;
     }
   }
-  int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s, bool stream_dst = false) const {
+  int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s) const {
     const HostProb &h = probs[i];
     const dpc_problem_t &p = P(i);
     const uint32_t *blocks = G().setup.genome_blocks;
     const char *q = (const char *)&pool[h.q0];
-    Out out; out.p = dst; out.n = 0; out.stream = stream_dst;
+    Out out; out.p = dst; out.n = 0;
     switch (p.kind) {
     case DPC_SINGLE_GAP: {
       char *ga = fit(s.ga, h.L2);
@@ -508,7 +537,7 @@ struct Batch {
       char *qa = fit(s.qa, h.L1), *ga = fit(s.ga, h.L2);
       for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
       gather_genome(p, blocks, p.offset2, h.L2, five, ga);
-      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0; sL.stream = false;
+      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0;
       replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex);
       if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) break;   /* 5259 */
       int first = 0;                                                   /* 5265-5268 */
@@ -523,7 +552,7 @@ struct Batch {
       for (int k = 0; k < L1; k++) qb[k] = q[L1 - 1 - k];
       gather_genome(p, blocks, p.offset2, L2L, false, ga);
       gather_genome(p, blocks, p.offset2R, L2R, true, gb);
-      Out sR, sL; sR.p = fit(s.sR, L1 + L2R + 2); sR.n = 0; sL.p = fit(s.sL, L1 + L2L + 2); sL.n = 0; sR.stream = sL.stream = false;
+      Out sR, sL; sR.p = fit(s.sR, L1 + L2R + 2); sR.n = 0; sL.p = fit(s.sL, L1 + L2L + 2); sL.n = 0;
       replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, revoffset1, p.offset2R, true, false, p.dynprogindex);
       replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex);
       if (sR.n + sL.n > 0) {                                           /* List_length == 1 -> NULL, 5051 */
@@ -541,9 +570,9 @@ struct Batch {
       for (int k = 0; k < L1R; k++) qb[k] = q[span - 1 - k];
       gather_genome(p, blocks, p.offset2, L2, false, ga);
       gather_genome(p, blocks, revoffset2, L2, true, gb);
-      Out sR, sL; sR.p = fit(s.sR, L1R + L2 + 2); sR.n = 0; sL.p = fit(s.sL, L1L + L2 + 2); sL.n = 0; sR.stream = sL.stream = false;
+      Out sR, sL; sR.p = fit(s.sR, L1R + L2 + 2); sR.n = 0; sL.p = fit(s.sL, L1L + L2 + 2); sL.n = 0;
       dpc_pair_t midbuf[24];
-      Out mid; mid.p = midbuf; mid.n = 0; mid.stream = false;
+      Out mid; mid.p = midbuf; mid.n = 0;
       replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, p.offset1R, revoffset2, true, true, p.dynprogindex);
       int queryjump = (p.offset1R - dr.bestcR) - (p.offset1 + dr.bestcL) + 1;     /* 4725-4726 */
       int genomejump = (revoffset2 - dr.bestrR) - (p.offset2 + dr.bestrL) + 1;

@@ -359,11 +359,11 @@ struct Engine {
     return DPC_OK;
   }
 
-  int pairs_into(int ticket, dpc_pair_t *dst, bool stream_dst = false) {
+  int pairs_into(int ticket, dpc_pair_t *dst) {
     const HostProb &h = batch.probs[ticket];
     if (h.dev < 0) return 0;
     const DevRes &dr = h_res[h.dev];
-    return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch, stream_dst);
+    return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch);
   }
 };
 
@@ -597,29 +597,39 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
   std::vector<std::atomic<int>> chunk_done((size_t)nchunks);
   for (int j = 0; j < nchunks; j++) { chunk_end[(size_t)j].store(-1); chunk_done[(size_t)j].store(0); }
   const double t0 = now_s();
-  c->workers->run(nchunks, [&](int j) {
+  std::atomic<int> next_chunk(0);
+  /* first half of a chunk: pack and queue copies + kernels on the chunk's stream (returns at once) */
+  auto launch = [&](int j) {
     Engine &e = *c->subs[(size_t)(j % nengines)];
     const int lo = j * chunk, cnt = std::min(chunk, n - lo);
-    int r = 0;
-    int64_t mine = 0;
-    double a0 = timing ? now_s() : 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    double a0 = timing ? now_s() : 0;
     if (j >= nengines) while (!chunk_done[(size_t)(j - nengines)].load(std::memory_order_acquire)) std::this_thread::yield();
+    if (err.load()) return;
+    int r = 0;
+    try {
+      e.reset();
+      r = e.batch.add_ext(problems + lo, results + lo, cnt);
+      double a1 = timing ? now_s() : 0;
+      if (r >= 0) r = e.flush();
+      if (timing) { t_pack += (int64_t)((a1 - a0) * 1e9); t_flush += (int64_t)((now_s() - a1) * 1e9); }
+    } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
+    if (r < 0) { int z = 0; err.compare_exchange_strong(z, r); }
+  };
+  /* second half: wait for the device, finalise, take the pair offset from the previous chunk, rebuild the pairs */
+  auto finish = [&](int j) {
+    Engine &e = *c->subs[(size_t)(j % nengines)];
+    const int lo = j * chunk, cnt = std::min(chunk, n - lo);
+    int64_t mine = 0;
+    double a2 = timing ? now_s() : 0, a3 = 0, a4 = 0;
     if (!err.load()) {
+      int r = 0;
       try {
-        cudaSetDevice(device);
-        if (timing) a0 = now_s();
-        e.reset();
-        r = e.batch.add_ext(problems + lo, results + lo, cnt);
-        if (timing) a1 = now_s();
-        if (r >= 0) r = e.flush();
-        if (timing) a2 = now_s();
-        if (r >= 0) r = e.wait();
-        if (timing) a3 = now_s();
+        r = e.wait();
         if (r >= 0) for (int i = 0; i < cnt; i++) mine += results[lo + i].npairs;
       } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
       if (r < 0) { int z = 0; err.compare_exchange_strong(z, r); }
     }
-    /* my block starts where the previous chunk's ends */
+    if (timing) a3 = now_s();
     int64_t at = 0;
     if (j > 0) {
       int64_t prev;
@@ -636,7 +646,7 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
             const int np = results[lo + i].npairs;
             if (pair_off) pair_off[lo + i] = at;
             if (!pairs || np == 0) { at += np; continue; }
-            int k = e.pairs_into(i, pairs + at, true);
+            int k = e.pairs_into(i, pairs + at);
             if (k != np) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_STATE); break; }
             at += k;
           }
@@ -645,15 +655,23 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
     }
     chunk_done[(size_t)j].store(1, std::memory_order_release);
     if (timing) {
-      double a5 = now_s();
-      t_pack += (int64_t)((a1 - a0) * 1e9); t_flush += (int64_t)((a2 - a1) * 1e9);
       t_wait += (int64_t)((a3 - a2) * 1e9); t_fin += (int64_t)(e.t_finalize * 1e9);
-      t_stall += (int64_t)((a4 - a3) * 1e9); t_pairs += (int64_t)((a5 - a4) * 1e9);
+      t_stall += (int64_t)((a4 - a3) * 1e9); t_pairs += (int64_t)((now_s() - a4) * 1e9);
+    }
+  };
+  /* every host thread keeps two chunks in flight: it launches the next one before it waits for the current one */
+  c->workers->run(T, [&](int) {
+    cudaSetDevice(device);
+    int cur = next_chunk.fetch_add(1);
+    if (cur >= nchunks) return;
+    launch(cur);
+    while (cur < nchunks) {
+      int nxt = next_chunk.fetch_add(1);
+      if (nxt < nchunks) launch(nxt);
+      finish(cur);
+      cur = nxt;
     }
   });
-#if defined(__SSE2__)
-  _mm_sfence();
-#endif
   if (err.load()) return err.load();
   if (pair_off) pair_off[n] = nchunks ? chunk_end[(size_t)nchunks - 1].load() : 0;
   if (timing)
