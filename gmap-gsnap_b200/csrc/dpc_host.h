@@ -507,6 +507,22 @@ struct Batch {
   static char *fit(std::vector<char> &v, int n) { if ((int)v.size() < n + 8) v.resize((size_t)n + 64); return v.data(); }
   static dpc_pair_t *fit(std::vector<dpc_pair_t> &v, int n) { if ((int)v.size() < n + 8) v.resize((size_t)n + 64); return v.data(); }
 
+  /* The rebuild reads the genome at an unpredictable place per problem: ask for the lines ahead of time. */
+  void prefetch_genome(int i) const {
+    const dpc_problem_t &p = P(i);
+    const uint32_t *blocks = G().setup.genome_blocks;
+    const uint32_t base = p.chroffset + p.chrpos;
+    const int offs[2] = { p.offset2, p.kind == DPC_GENOME_GAP ? p.offset2R : p.offset2 + p.length2 - 1 };
+    for (int k = 0; k < 2; k++) {
+      int64_t pos = offs[k];
+      if (pos < 0) pos = 0;
+      if (pos >= (int64_t)p.genomiclength) pos = (int64_t)p.genomiclength - 1;
+      if (pos < 0) continue;
+      const uint64_t g = p.watsonp ? (uint64_t)base + (uint64_t)pos : (uint64_t)base + (uint64_t)(p.genomiclength - 1 - pos);
+      if (g < G().genome_nbases) __builtin_prefetch(blocks + (g >> 5) * 3);
+    }
+  }
+
   /* Writes the pairs of problem i, in the order of the List_T the reference returns, to dst (which must
    * hold max_pairs(i) records) and returns their number. */
   int max_pairs(int i) const {

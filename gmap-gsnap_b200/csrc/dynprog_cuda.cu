@@ -644,6 +644,7 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
         try {
           for (int i = 0; i < cnt; i++) {
             const int np = results[lo + i].npairs;
+            if (pairs && i + 8 < cnt) e.batch.prefetch_genome(i + 8);
             if (pair_off) pair_off[lo + i] = at;
             if (!pairs || np == 0) { at += np; continue; }
             int k = e.pairs_into(i, pairs + at);
