@@ -14,6 +14,9 @@
 #include <string.h>
 #include <ctype.h>
 #include <stdlib.h>
+#if defined(__SSE2__) && defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <new>
 #include <vector>
 #include "../../include/dynprog_cuda.h"
@@ -193,12 +196,21 @@ struct HostProb {
 /* pair records are written through a bare cursor: every caller sizes the destination first */
 struct Out {
   dpc_pair_t *p; int n;
+  bool stream;
+  Out() : p(NULL), n(0), stream(false) {}
   void push(int qpos, int gpos, char cdna, char comp, char genome, int idx, int gapp) {
     /* dpc_pair_t is 16 bytes: {querypos, genomepos} and {dynprogindex, cdna, comp, genome, gapp}: two 8-byte stores */
     uint64_t lo = (uint32_t)qpos | ((uint64_t)(uint32_t)gpos << 32);
     uint64_t hi = (uint32_t)idx | ((uint64_t)(uint8_t)cdna << 32) | ((uint64_t)(uint8_t)comp << 40) |
                   ((uint64_t)(uint8_t)genome << 48) | ((uint64_t)(uint8_t)gapp << 56);
     uint64_t *w = (uint64_t *)&p[n++];
+#if defined(__SSE2__) && defined(__x86_64__)
+    if (stream) {        /* the caller's big array: written once, not read back here -- go around the cache */
+      _mm_stream_si64((long long *)w, (long long)lo);
+      _mm_stream_si64((long long *)w + 1, (long long)hi);
+      return;
+    }
+#endif
     w[0] = lo; w[1] = hi;
   }
   void push_gapholder() { push(-1, -1, ' ', ' ', ' ', 0, 1); }       /* pairpool.c:352-401 */
@@ -501,8 +513,10 @@ struct Batch {
   }
 
   static void emit(Out &out, const dpc_pair_t *v, int n, bool reversed) {
-    if (!reversed) { if (n > 0) memcpy(out.p + out.n, v, (size_t)n * sizeof(dpc_pair_t)); out.n += n; }
-    else for (int i = 0; i < n; i++) out.p[out.n++] = v[n - 1 - i];
+    for (int i = 0; i < n; i++) {
+      const dpc_pair_t &pr = v[reversed ? n - 1 - i : i];
+      out.push(pr.querypos, pr.genomepos, pr.cdna, pr.comp, pr.genome, pr.dynprogindex, pr.gapp);
+    }
   }
   static char *fit(std::vector<char> &v, int n) { if ((int)v.size() < n + 8) v.resize((size_t)n + 64); return v.data(); }
   static dpc_pair_t *fit(std::vector<dpc_pair_t> &v, int n) { if ((int)v.size() < n + 8) v.resize((size_t)n + 64); return v.data(); }
@@ -534,12 +548,12 @@ struct Batch {
     default: return h.L1 + h.L2 + 8;
     }
   }
-  int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s) const {
+  int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s, bool stream_dst = false) const {
     const HostProb &h = probs[i];
     const dpc_problem_t &p = P(i);
     const uint32_t *blocks = G().setup.genome_blocks;
     const char *q = (const char *)&pool[h.q0];
-    Out out; out.p = dst; out.n = 0;
+    Out out; out.p = dst; out.n = 0; out.stream = stream_dst;
     switch (p.kind) {
     case DPC_SINGLE_GAP: {
       char *ga = fit(s.ga, h.L2);

@@ -359,11 +359,11 @@ struct Engine {
     return DPC_OK;
   }
 
-  int pairs_into(int ticket, dpc_pair_t *dst) {
+  int pairs_into(int ticket, dpc_pair_t *dst, bool stream_dst = false) {
     const HostProb &h = batch.probs[ticket];
     if (h.dev < 0) return 0;
     const DevRes &dr = h_res[h.dev];
-    return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch);
+    return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch, stream_dst);
   }
 };
 
@@ -589,6 +589,7 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
     c->subs.push_back(e);
   }
   static const bool timing = getenv("DPC_TIMING") != NULL;
+  static const bool stream_pairs = getenv("DPC_NO_STREAM") == NULL;     /* non-temporal stores for the pair records */
   std::atomic<int> err(0);
   std::atomic<int64_t> t_pack(0), t_flush(0), t_wait(0), t_fin(0), t_pairs(0), t_stall(0);
   /* chunk j publishes the end offset of its pair block once every chunk before it has; a chunk's engine is
@@ -647,7 +648,7 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
             if (pairs && i + 8 < cnt) e.batch.prefetch_genome(i + 8);
             if (pair_off) pair_off[lo + i] = at;
             if (!pairs || np == 0) { at += np; continue; }
-            int k = e.pairs_into(i, pairs + at);
+            int k = e.pairs_into(i, pairs + at, stream_pairs);
             if (k != np) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_STATE); break; }
             at += k;
           }
@@ -673,6 +674,9 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
       cur = nxt;
     }
   });
+#if defined(__SSE2__) && defined(__x86_64__)
+  _mm_sfence();
+#endif
   if (err.load()) return err.load();
   if (pair_off) pair_off[n] = nchunks ? chunk_end[(size_t)nchunks - 1].load() : 0;
   if (timing)
