@@ -22,7 +22,11 @@ emul: tests/emul/libdpc_emul.so
 tests/emul/libdpc_emul.so: tests/emul/dpc_emul.cpp $(PKG)/csrc/dpc_core.h $(PKG)/csrc/dpc_host.h include/dynprog_cuda.h
 	g++ -O2 -fPIC -Wall -Wextra -Wno-unknown-pragmas -shared -o $@ tests/emul/dpc_emul.cpp
 
+# reference gmap and gmap with the drop-in solvers (BASELINE config 1); needs /root/reference
+gmap: cuda
+	bash oracle/build_gmap.sh
+
 clean:
 	rm -f $(PKG)/csrc/*.so $(PKG)/host/*.so $(PKG)/csrc/ptxas.log tests/emul/*.so
 	$(MAKE) -C oracle clean
-.PHONY: all cuda synth oracle emul clean
+.PHONY: all cuda synth oracle emul gmap clean

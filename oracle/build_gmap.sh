@@ -1,0 +1,46 @@
+#!/bin/bash
+# oracle/build_gmap.sh -- ORACLE / INTEGRATION SCAFFOLDING (build container only; needs /root/reference).
+#
+# Builds two GMAP binaries from a scratch copy of the reference tree (nothing is written to /root/reference and no
+# reference source is copied into this repository):
+#   oracle/_ref/gmap_ref    the unmodified reference + oracle/genome_hr_standin.c (the checkout lacks genome_hr.c)
+#   oracle/_ref/gmap_cuda   the same objects, except that the five gap-fill solvers of dynprog.c (and
+#                           Dynprog_init/_setup/_term) are renamed *_cpu with objcopy and replaced by
+#                           gmap-gsnap_b200/host/dynprog_dropin.c on top of libdynprog_cuda.so, and that gmap.c gets
+#                           the ONE added line INTEGRATION.md describes (registering a user segment's genome blocks).
+# It also stages the reference's own align.test inputs and golden output next to the binaries (git-ignored, but
+# they travel to the GPU box) so that tests/test_gpu_gmap.py can run BASELINE config 1 there.
+set -euo pipefail
+REPO="$(cd "$(dirname "$0")/.." && pwd)"
+REF="${REF:-/root/reference}"
+WORK="${WORK:-/tmp/gmap_build}"
+OUT="$REPO/oracle/_ref"
+[ -d "$REF/src" ] || { echo "build_gmap.sh: $REF absent; keeping prebuilt binaries"; exit 0; }
+mkdir -p "$OUT"
+if [ ! -f "$WORK/src/Makefile" ]; then
+  rm -rf "$WORK"; cp -r "$REF" "$WORK"; chmod -R u+w "$WORK"
+  (cd "$WORK" && ./configure > configure.log 2>&1)
+fi
+cd "$WORK/src"
+cp "$REPO/oracle/genome_hr_standin.c" genome_hr.c
+make -j"$(nproc)" gmap > make.log 2>&1
+cp gmap "$OUT/gmap_ref"
+
+CC="${CC:-gcc}"
+CFLAGS=(-DHAVE_CONFIG_H -I. -mpopcnt '-DTARGET="x86_64-unknown-linux-gnu"' '-DGMAPDB="/usr/share/gmapdb"' -O3)
+SYMS="Dynprog_init Dynprog_setup Dynprog_term Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap"
+ARGS=""; for s in $SYMS; do ARGS="$ARGS --redefine-sym $s=${s}_cpu"; done
+objcopy $ARGS gmap-dynprog.o cuda-dynprog_cpu.o
+$CC "${CFLAGS[@]}" -I"$REPO/include" -Wall -c "$REPO/gmap-gsnap_b200/host/dynprog_dropin.c" -o cuda-dynprog_dropin.o
+# the one-line change to gmap.c: hand the user segment's blocks to the library
+sed 's|^    Genome_user_setup(genome_blocks);|    Genome_user_setup(genome_blocks);\n    { extern void Dynprog_cuda_register_blocks (UINT4 *blocks, unsigned int nwords); Dynprog_cuda_register_blocks(genome_blocks,((Sequence_fulllength(usersegment) + 31)/32U)*3 + 4); }|' gmap.c > cuda-gmap.c
+grep -q Dynprog_cuda_register_blocks cuda-gmap.c
+$CC "${CFLAGS[@]}" -c cuda-gmap.c -o cuda-gmap.o
+OBJS=$(ls gmap-*.o | grep -v -e '^gmap-dynprog.o$' -e '^gmap-gmap.o$')
+$CC -O3 -o "$OUT/gmap_cuda" $OBJS cuda-dynprog_cpu.o cuda-dynprog_dropin.o cuda-gmap.o \
+    -L"$REPO/gmap-gsnap_b200/csrc" -ldynprog_cuda -Wl,-rpath,'$ORIGIN/../../gmap-gsnap_b200/csrc' -lz -lm -lpthread
+mkdir -p "$OUT/align_test"
+cp "$REF/tests/ss.her2" "$REF/tests/ss.chr17test" "$REF/tests/align.test.ok" "$OUT/align_test/"
+# sanity: the unmodified build reproduces the reference's golden output
+"$OUT/gmap_ref" -A -g "$OUT/align_test/ss.chr17test" "$OUT/align_test/ss.her2" 2>/dev/null | diff -q - "$OUT/align_test/align.test.ok"
+echo "build_gmap.sh: gmap_ref (align.test identical) and gmap_cuda built in $OUT"
