@@ -175,6 +175,10 @@ def main():
     lib.open(local_rank)
     L = lib.lib
     n = len(probs)
+    # the ranks of one box share its host cores: split them (packing / Pair rebuild threads of dpc_solve)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, local_world))
+    lib.check(L.dpc_set_threads(lib.ctx, min(64, host_threads)), "dpc_set_threads")
 
     # results for the sanity checks (bulk call), then the whole batch resident in HBM on the context's own stream
     if args.kernel_only:
@@ -246,7 +250,7 @@ def main():
                    "cells_per_gpu": cells, "l2": "inputs larger than L2 (descriptors + sequences + results = %.0f MB per step)" % (algo_bytes / 1e6)},
         "e2e": {"value": total_cells / e2e_s / 1e9, "unit": UNIT, "fills_per_s": total_fills / e2e_s, "ms_per_step": 1e3 * e2e_s,
                 "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
-                "host_threads": os.cpu_count(),
+                "host_threads_per_rank": host_threads,
                 "includes": "dpc_solve: pack, H2D, kernels, D2H, result finalisation, Pair-record rebuild (%d records)" % len(pairs)},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),

@@ -414,7 +414,8 @@ struct dpc_ctx {
   std::vector<Engine *> subs;        /* bulk API: one engine per chunk in flight */
   Workers *workers;
   int nthreads;
-  dpc_ctx() : workers(NULL), nthreads(1) {}
+  std::atomic<int64_t> solve_h2d, solve_d2h, solve_launches, solve_problems;   /* totals of the last dpc_solve */
+  dpc_ctx() : workers(NULL), nthreads(1), solve_h2d(0), solve_d2h(0), solve_launches(0), solve_problems(0) {}
 };
 
 /* ---- C ABI ---------------------------------------------------------------------------------- */
@@ -598,6 +599,7 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
   std::vector<std::atomic<int>> chunk_done((size_t)nchunks);
   for (int j = 0; j < nchunks; j++) { chunk_end[(size_t)j].store(-1); chunk_done[(size_t)j].store(0); }
   const double t0 = now_s();
+  c->solve_h2d = 0; c->solve_d2h = 0; c->solve_launches = 0; c->solve_problems = n;
   std::atomic<int> next_chunk(0);
   /* first half of a chunk: pack and queue copies + kernels on the chunk's stream (returns at once) */
   auto launch = [&](int j) {
@@ -655,6 +657,7 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
         } catch (const std::bad_alloc &) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_NOMEM); }
       }
     }
+    c->solve_h2d += e.h2d_bytes; c->solve_d2h += e.d2h_bytes; c->solve_launches += e.nlaunch;
     chunk_done[(size_t)j].store(1, std::memory_order_release);
     if (timing) {
       t_wait += (int64_t)((a3 - a2) * 1e9); t_fin += (int64_t)(e.t_finalize * 1e9);
@@ -746,7 +749,12 @@ int dpc_get_stats(dpc_ctx_t *c, dpc_stats_t *out) {
   if (!c || !out) return DPC_ERR_ARG;
   memset(out, 0, sizeof *out);
   if (!c->main.batch.probs.empty()) add_stats(c->main, out);
-  else for (size_t i = 0; i < c->subs.size(); i++) add_stats(*c->subs[i], out);
+  else {
+    /* after dpc_solve: cells / bytes of the chunks still held by the engines, transfer totals of the whole call */
+    for (size_t i = 0; i < c->subs.size(); i++) add_stats(*c->subs[i], out);
+    out->nproblems = c->solve_problems;
+    out->h2d_bytes = c->solve_h2d; out->d2h_bytes = c->solve_d2h; out->launches = (int32_t)c->solve_launches;
+  }
   return DPC_OK;
 }
 
