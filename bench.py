@@ -90,9 +90,21 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_workload(rank, n):
+WORKLOADS = {
+    "single": "Dynprog_single_gap, 1M synthetic 10-100 bp gap fills, band 30, on 1 B200 per rank (BASELINE configs[1])",
+    "genome": "Dynprog_genome_gap, synthetic cDNA/genomic gaps across GT-AG/GC-AG/AT-AC introns 50 bp-20 kb, band 7, 10% long (BASELINE configs[2], finalp off)",
+    "end": "Dynprog_end5_gap/end3_gap, synthetic 250-bp read ends, tails 1-40 + 11 peeled, band 3 (BASELINE configs[3])",
+}
+
+
+def make_workload(rank, n, kind="single"):
     w = api.Workload(GENOME_BASES, seed=0x9E3779B9 + rank, nchr=4)
-    probs = w.single_gaps(n, extraband=EXTRABAND, seed=0x5EED0002 + 1000 * rank)
+    if kind == "genome":
+        probs = w.genome_gaps(n, extraband=7, seed=0x5EED0003 + 1000 * rank, finalp_mode=0, long_frac=0.1, long_hi=600)
+    elif kind == "end":
+        probs = w.end_gaps(n, extraband=3, seed=0x5EED0004 + 1000 * rank)
+    else:
+        probs = w.single_gaps(n, extraband=EXTRABAND, seed=0x5EED0002 + 1000 * rank)
     return w, probs
 
 
@@ -137,6 +149,7 @@ def main():
     ap.add_argument("--problems", type=int, default=N_PROBLEMS)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="single", choices=sorted(WORKLOADS), help="single = the headline config; genome / end = the other hot-path configs")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: load the batch, run the timed kernel steps, print their times, exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
@@ -168,7 +181,7 @@ def main():
         dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
 
-    w, probs = make_workload(rank, args.problems)
+    w, probs = make_workload(rank, args.problems, args.workload)
     lib = api.CudaLib()
     lib.init()
     lib.setup(w.make_setup())
@@ -195,8 +208,9 @@ def main():
     lib.load(probs)
     stats = lib.stats()
     cells = int(stats.cells)
-    assert cells == int(band_cells(probs).sum()), "cell count mismatch"
-    assert (res["null_list"] == 0).all()
+    if args.workload == "single":
+        assert cells == int(band_cells(probs).sum()), "cell count mismatch"
+        assert (res["null_list"] == 0).all()
 
     def step():
         lib.check(L.dpc_relaunch(lib.ctx), "dpc_relaunch")
@@ -245,8 +259,8 @@ def main():
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "fills_per_s": total_fills / (step_ms * 1e-3),
-        "config": {"workload": "Dynprog_single_gap, 1M synthetic 10-100 bp gap fills, band 30, on 1 B200 per rank (BASELINE configs[1])",
-                   "problems_per_gpu": n, "extraband_single": EXTRABAND, "genome_bases": GENOME_BASES,
+        "config": {"workload": WORKLOADS[args.workload],
+                   "problems_per_gpu": n, "extraband": int(probs["extraband"][0]), "genome_bases": GENOME_BASES,
                    "cells_per_gpu": cells, "l2": "inputs larger than L2 (descriptors + sequences + results = %.0f MB per step)" % (algo_bytes / 1e6)},
         "e2e": {"value": total_cells / e2e_s / 1e9, "unit": UNIT, "fills_per_s": total_fills / e2e_s, "ms_per_step": 1e3 * e2e_s,
                 "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
@@ -266,6 +280,8 @@ def main():
     line["roofline"]["achieved"] = algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9
     line["alu_roofline"]["frac"] = line["alu_roofline"]["achieved_gcups_per_gpu"] / line["alu_roofline"]["peak_gcups"]
 
+    if args.workload != "single":
+        line["metric"] = "banded_dp_gcups_%s_gap" % args.workload
     if rank == 0 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdynprog_ref.so")):
         ref = api.RefOracle()
         ref.init()
@@ -273,10 +289,10 @@ def main():
         cores = os.cpu_count() or 1
         sample = min(n, max(20000, 40000 * cores))
         _, secs = ref.solve_mt(probs[:sample], cores)
-        scells = int(band_cells(probs[:sample]).sum())
+        scells = int(band_cells(probs[:sample]).sum()) if args.workload == "single" else int(round(cells * sample / n))
         line["cpu_baseline"] = {"value": scells / secs / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
                                 "fills_per_s": sample / secs,
-                                "sample": "first %d of the 1M problems, unmodified reference dynprog.c (-O3), %d threads" % (sample, cores)}
+                                "sample": "first %d of the %d problems, unmodified reference dynprog.c (-O3), %d threads" % (sample, n, cores)}
     lib.close()
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -129,7 +129,8 @@ struct Mat {
                                planes:  word ((r-1)*cpl + k%cpl)*4 + p, bit k/cpl, k = c-r+lband, with plane
                                p = 0 nogap came from gap1 (HORIZ), 1 nogap came from gap2 (VERT),
                                    2 gap1 of cell k+1 came from gap1 (HORIZ), 3 gap2 came from gap2 (VERT) */
-  int32_t *nband;           /* nogap score of rows 1..L1, (r-1)*W + (c-r+lband); NULL when no bridge follows */
+  int16_t *nband;           /* nogap score of rows 1..L1, (r-1)*W + (c-r+lband), 16 bit (real scores are within
+                               +-28000 for any size dpc_init accepts); NULL when no bridge follows */
 };
 
 DPC_HB void dpc_bands(int L1, int L2, int extraband, int widebandp, int *lband, int *rband) {
@@ -270,7 +271,7 @@ DPC_HD void dpc_fill_generic(const Mat &m, int32_t *st, const int8_t *score /* [
       cur[r] = N; cur[R + r] = G1; cur[2 * R + r] = G2;
       int idx = (r - 1) * (m.wstride << 3) + (k + m.lband), sh = (idx & 7) << 2;
       m.dir[idx >> 3] = (m.dir[idx >> 3] & ~(15U << sh)) | ((uint32_t)nib << sh);
-      if (m.nband) m.nband[(r - 1) * m.W + (k + m.lband)] = N;
+      if (m.nband) m.nband[(r - 1) * m.W + (k + m.lband)] = (int16_t)(N < -32768 ? -32768 : N);
       if (es.mode == 1) {
         if (k >= -es.eb && k <= es.eb && dpc_better(N, r * (L2 + 1) + c, es.best, m.late)) { es.best.score = N; es.best.key = r * (L2 + 1) + c; }
       } else if (es.mode == 2) {
@@ -520,7 +521,12 @@ struct MatDims { int rows, cols, lband, rband, W, wstride, planes, cpl; };
 struct ArenaLayout {
   int nmat;
   MatDims d[2];
-  uint32_t rowch[2], colch[2], prof[2], dir[2], nband[2], ops[2], state, total;
+  /* two regions: `small` (characters, profiles, op strings: read on the fill's critical path, always in shared
+   * memory when the problem runs in a shared-memory class) and `bulk` (direction bits, nogap bands, fallback-fill
+   * state: written once per row, read by bridge and traceback; goes to HBM scratch when it does not fit) */
+  uint32_t rowch[2], colch[2], prof[2], ops[2], small;
+  uint32_t dir[2], nband[2], state, bulk;
+  uint32_t total;                        /* small + bulk */
 };
 #define DPC_MAX_CPL 4                       /* row-sweep fill: 1, 2 or 4 diagonals per lane, bands of up to 128 */
 DPC_HB uint32_t dpc_al(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); }
@@ -529,7 +535,7 @@ DPC_HB uint32_t dpc_al(uint32_t x, uint32_t a) { return (x + a - 1) & ~(a - 1); 
  * fillmode 0: sizes only (stats); 1: every matrix through the memory-state fill (nibble directions +
  * anti-diagonal state); 2: row-sweep fill (bit planes) wherever the band has at most 128 diagonals. */
 DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
-  uint32_t off = 0;
+  uint32_t so = 0, bo = 0;
   int maxrows = 0, need_state = fillmode == 1;
   a.nmat = (p.kind == 1 || p.kind == 2) ? 2 : 1;
   for (int i = 0; i < a.nmat; i++) {
@@ -543,29 +549,31 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
     d.planes = fillmode == 2 && d.W <= 32 * DPC_MAX_CPL;
     if (fillmode == 2 && !d.planes) need_state = 1;
     if (d.rows > maxrows) maxrows = d.rows;
-    a.rowch[i] = off; off = dpc_al(off + (uint32_t)d.rows + 2, 4);
-    a.colch[i] = off; off = dpc_al(off + (uint32_t)d.cols + 2, 4);
-    a.prof[i] = off;
-    if (d.planes && p.kind != 2) off += (uint32_t)d.rows * 4;
-    if (d.planes) { off = dpc_al(off, 16); a.dir[i] = off; off += (uint32_t)d.rows * (uint32_t)d.cpl * 16; }
-    else { a.dir[i] = off; off += (uint32_t)d.rows * (uint32_t)d.wstride * 4; }
-    if (a.nmat == 2) { a.nband[i] = off; off += (uint32_t)d.rows * (uint32_t)d.W * 4; } else a.nband[i] = 0;
-    a.ops[i] = off; off = dpc_al(off + 2 * (uint32_t)(d.rows + d.cols + 2), 4);
+    a.rowch[i] = so; so = dpc_al(so + (uint32_t)d.rows + 2, 4);
+    a.colch[i] = so; so = dpc_al(so + (uint32_t)d.cols + 2, 4);
+    a.prof[i] = so;
+    if (d.planes && p.kind != 2) so += (uint32_t)d.rows * 4;
+    a.ops[i] = so; so = dpc_al(so + 2 * (uint32_t)(d.rows + d.cols + 2), 4);
+    a.dir[i] = bo;
+    if (d.planes) bo += (uint32_t)d.rows * (uint32_t)d.cpl * 16; else bo += (uint32_t)d.rows * (uint32_t)d.wstride * 4;
+    if (a.nmat == 2) { a.nband[i] = bo; bo = dpc_al(bo + (uint32_t)d.rows * (uint32_t)d.W * 2, 16); } else a.nband[i] = 0;
   }
-  a.state = off;
-  if (need_state) off += 9 * (uint32_t)(maxrows + 1) * 4;
-  a.total = dpc_al(off, 16);
+  a.state = bo;
+  if (need_state) bo += 9 * (uint32_t)(maxrows + 1) * 4;
+  a.small = dpc_al(so, 16);
+  a.bulk = dpc_al(bo, 16);
+  a.total = a.small + a.bulk;
 }
 
-DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *arena, const DevProb &p, int late, int query_rows) {
+DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *small, uint8_t *bulk, const DevProb &p, int late, int query_rows) {
   const MatDims &d = a.d[i];
   m.L1 = d.rows; m.L2 = d.cols; m.lband = d.lband; m.rband = d.rband; m.W = d.W; m.wstride = d.wstride;
   m.open = p.open; m.extend = p.extend; m.late = late; m.query_rows = query_rows;
-  m.rowch = arena + a.rowch[i]; m.colch = arena + a.colch[i];
+  m.rowch = small + a.rowch[i]; m.colch = small + a.colch[i];
   m.planes = d.planes; m.cpl = d.cpl; m.cplsh = d.cpl == 1 ? 0 : d.cpl == 2 ? 1 : 2;
-  m.prof = (uint32_t *)(arena + a.prof[i]);
-  m.dir = (uint32_t *)(arena + a.dir[i]);
-  m.nband = a.nmat == 2 ? (int32_t *)(arena + a.nband[i]) : (int32_t *)0;
+  m.prof = (uint32_t *)(small + a.prof[i]);
+  m.dir = (uint32_t *)(bulk + a.dir[i]);
+  m.nband = a.nmat == 2 ? (int16_t *)(bulk + a.nband[i]) : (int16_t *)0;
 }
 
 /* ---- one problem ------------------------------------------------------------------------------ */
@@ -596,7 +604,10 @@ DPC_HD void dpc_emit_ops(DevRes *res, const uint16_t *opsL, int nL, const uint16
  * register/shuffle fill for narrow bands).  `arena` must hold dpc_layout(p).total bytes. */
 template <class FILL>
 DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint32_t *blocks, const DevTables *tb,
-                              uint8_t *arena, DevRes *res, const OvfArena &ovf, FILL &fill, const Lanes &ln) {
+                              uint8_t *arena, uint32_t arena_bytes, uint8_t *scratch, DevRes *res, const OvfArena &ovf,
+                              FILL &fill, const Lanes &ln) {
+  /* arena: this warp's shared-memory (or HBM) arena of arena_bytes; scratch: this problem's HBM scratch, used for
+   * the bulk region when small + bulk does not fit the arena (the host sized both with the same dpc_layout) */
   /* FILL provides: fillmode (layout), operator() = the matrix fill, walk() = the traceback walk */
   uint32_t status = DPC_ST_DONE;
   Counts ct; ct.nmatches = ct.nmismatches = ct.nopens = ct.nindels = ct.star = 0;
@@ -626,11 +637,12 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
     ArenaLayout a;
     dpc_layout(p, a, FILL::fillmode);
     Mat m0, m1;
-    int32_t *st = (int32_t *)(arena + a.state);
+    uint8_t *bulk = a.total <= arena_bytes ? arena + a.small : scratch;
+    int32_t *st = (int32_t *)(bulk + a.state);
     if (p.kind == 0 || p.kind == 3 || p.kind == 4) {
       /* Dynprog_single_gap 4450-4572, Dynprog_end5_gap 5094-5284, Dynprog_end3_gap 5556-5741 */
       const int five = p.kind == 3;
-      dpc_make_mat(m0, a, 0, arena, p, five ? !late : late, 1);
+      dpc_make_mat(m0, a, 0, arena, bulk, p, five ? !late : late, 1);
       for (int i = ln.lane; i < p.L1; i += ln.n) {
         int q = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
         m0.rowch[i] = (uint8_t)q;
@@ -653,8 +665,8 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       status |= DPC_ST_HAVE | DPC_ST_OK;
     } else {
       const int cdna = p.kind == 2;
-      dpc_make_mat(m0, a, 0, arena, p, late, !cdna);
-      dpc_make_mat(m1, a, 1, arena, p, !late, !cdna);
+      dpc_make_mat(m0, a, 0, arena, bulk, p, late, !cdna);
+      dpc_make_mat(m1, a, 1, arena, bulk, p, !late, !cdna);
       if (!cdna) {
         /* Dynprog_genome_gap 4798-5061: L = fwd(query, genome @ offset2L), R = rev(query, genome @ revoffset2R) */
         for (int i = ln.lane; i < p.L1; i += ln.n) {

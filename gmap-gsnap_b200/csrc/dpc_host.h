@@ -92,7 +92,8 @@ inline int host_init(int maxlookback, int extraquerygap, int maxpeelback, int ex
   if (m1 < 500) m1 = 500;
   int m2 = m1 + extraquerygap + (extramaterial_end > extramaterial_paired ? extramaterial_end : extramaterial_paired);
   if (m2 < 2000) m2 = 2000;
-  if (m1 > 4000 || m2 > 4000) return DPC_ERR_ARG;   /* traceback ops carry 14-bit lengths, bridge keys 13-bit columns */
+  if (m1 > 1300 || m2 > 3000) return DPC_ERR_ARG;   /* nogap bands are kept in 16 bits (worst real score -7*3000 - 5*1300),
+                                                        traceback ops carry 14-bit lengths, bridge keys 13-bit columns */
   g.maxlength1 = m1; g.maxlength2 = m2; g.mode = mode;
   build_tables(g, mode);
   g.inited = true;

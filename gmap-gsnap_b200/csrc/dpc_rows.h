@@ -119,7 +119,7 @@ DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
       /* directions: four ballots, one 16-byte store */
       const uint32_t b1 = vballot(p2[j]), b0 = vballot(p1[j]) & ~b1, b2 = vballot(h), b3 = vballot(pv[j]);
       store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
-      if (NBAND) store_i32(m.nband, lane * CPL + ((r - 1) * W + j), Nn[j], kok[j]);
+      if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), kok[j]);
       if (EP) keep_better(bs, bk, Nn[j], x[j] + (r * (L2 + 1) + 1), vand(vnot(inval[j]), ebok[j]), LATE);
       /* what the next row sees on this diagonal: the cell, column 0, or NEG */
       Np[j] = vsel(inval[j], DPC_NEG, Nn[j]);

@@ -59,14 +59,18 @@ __global__ void __launch_bounds__(256) dpc_solve_kernel(const KernelArgs a) {
     if (i >= a.n) break;
     const uint32_t pi = a.list[i];
     const DevProb p = a.probs[pi];
-    uint8_t *arena = SMEM ? smem + (size_t)warp * a.arena_bytes
-                          : a.scratch + (((uint64_t)p.scratch_hi << 32) | p.scratch_lo);
+    /* shared-memory classes: the warp's arena holds the small region and, when it fits, the bulk region too;
+       otherwise the bulk region (direction planes, nogap bands) lives in this problem's HBM scratch.  The
+       scratch-only class (SMEM == false) keeps both regions in HBM. */
+    uint8_t *scratch = a.scratch + (((uint64_t)p.scratch_hi << 32) | p.scratch_lo);
+    uint8_t *arena = SMEM ? smem + (size_t)warp * a.arena_bytes : scratch;
+    const uint32_t arena_bytes = SMEM ? a.arena_bytes : 0xffffffffu;
     if (a.force_generic) {
       GenericFill fill;
-      dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, &a.res[pi], a.ovf, fill, ln);
+      dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
     } else {
       RowFill fill;
-      dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, &a.res[pi], a.ovf, fill, ln);
+      dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
     }
     __syncwarp();
   }
@@ -149,9 +153,12 @@ struct ClassLaunch {
   int n;
 };
 
-#define NCLASS 8
-static const uint32_t k_class_bytes[NCLASS] = { 3 << 10, 6 << 10, 12 << 10, 24 << 10, 48 << 10, 96 << 10, 192 << 10, 0 };
-#define SCRATCH_BUDGET (6ull << 30)
+/* per-warp shared-memory arena classes: with 8 warps per block and the 2 blocks per SM the register file allows,
+ * 13 KB per warp is what fits in 227 KB; problems whose bulk region does not fit keep it in HBM scratch, problems
+ * whose small region alone does not fit run entirely from HBM scratch (last class) */
+#define NCLASS 4
+static const uint32_t k_class_bytes[NCLASS] = { 3 << 10, 6 << 10, 13 << 10, 0 };
+#define SCRATCH_BUDGET (16ull << 30)
 
 /* ---- engine: one stream, its device buffers and the batch in flight on it -------------------- */
 struct Engine {
@@ -267,11 +274,17 @@ struct Engine {
       if (!((p.kind == DPC_END5_GAP || p.kind == DPC_END3_GAP) && p.endalign == DPC_QUERYEND_NOGAPS)) {
         ArenaLayout a;
         dpc_layout(p, a, with_state);
+        uint64_t need = 0;                 /* HBM scratch of this problem */
         for (k = 0; k < NCLASS - 1; k++) if (a.total <= k_class_bytes[k] && k_class_bytes[k] <= smem_limit) break;
         if (k == NCLASS - 1) {
-          if (scratch_total + a.total > SCRATCH_BUDGET) return DPC_ERR_NOMEM;
+          need = a.bulk;
+          for (k = 0; k < NCLASS - 1; k++) if (a.small <= k_class_bytes[k] && k_class_bytes[k] <= smem_limit) break;
+          if (k == NCLASS - 1) need = a.total;
+        }
+        if (need) {
+          if (scratch_total + need > SCRATCH_BUDGET) return DPC_ERR_NOMEM;
           p.scratch_lo = (uint32_t)scratch_total; p.scratch_hi = (uint32_t)(scratch_total >> 32);
-          scratch_total += a.total;
+          scratch_total += need;
         }
         uint64_t worst = 0;
         for (int m = 0; m < a.nmat; m++) worst += (uint64_t)(a.d[m].rows + a.d[m].cols + 2);
@@ -295,8 +308,6 @@ struct Engine {
       L.smem = k < NCLASS - 1;
       L.arena_bytes = k_class_bytes[k];
       L.wpb = 8;
-      if (L.smem) { while (L.wpb > 1 && (uint64_t)L.wpb * L.arena_bytes > smem_limit) L.wpb >>= 1; }
-      else L.wpb = 4;
       L.list_off = off[k]; L.n = (int)count[k];
       launches.push_back(L);
     }
