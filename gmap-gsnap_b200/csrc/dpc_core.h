@@ -160,6 +160,13 @@ DPC_HD int dpc_dirN(const Mat &m, int r, int c) {
   if (dpc_plane_bit(m, r, k, 1)) return DPC_VERT;
   return dpc_plane_bit(m, r, k, 0) ? DPC_HORIZ : DPC_DIAG;
 }
+/* 1 when the nogap direction of an IN-BAND cell is HORIZ or VERT (the bridges' -1, dynprog.c:3724) */
+DPC_HD int dpc_nondiag(const Mat &m, int r, int c) {
+  const int k = c - r + m.lband;
+  if (!m.planes) return (dpc_nib(m, r, c) & 3) != DPC_DIAG;
+  const uint32_t *w = m.dir + ((r - 1) * m.cpl + (k & (m.cpl - 1))) * 4;
+  return (int)(((w[0] | w[1]) >> (k >> m.cplsh)) & 1U);
+}
 DPC_HD bool dpc_g1_horiz(const Mat &m, int r, int c) {
   if (r == 0) return c >= 2 && c <= m.rband && c <= m.L2;
   if (!dpc_inband(m, r, c)) return false;
@@ -395,10 +402,14 @@ struct Bridge { int have, finalscore, rL, cL, rR, cR, introntype; };
 
 /* mL: rows = query forward, columns = genome from offset2L; mR: rows = query backward, columns =
  * genome backward from revoffset2R.  lknown / rknown: 1 where a known splice site sits (NULL =
- * none); lp / rp: per-position probabilities for use_probabilities_p (3829-4081). */
+ * none); lp / rp: per-position probabilities for use_probabilities_p (3829-4081).
+ * ldi / rdi (length2L / length2R bytes) and itab (64 bytes) are scratch: the dinucleotide codes of every column
+ * (3331-3373) and intron_score for every (leftdi & rightdi) value are tabulated once, so one candidate costs two
+ * byte loads, an AND and a table load instead of two compare chains and a switch.  Candidates are in band by
+ * construction (their column ranges are clipped to the band, 3545-3549), so the nogap band is read directly. */
 DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const DevProb &p,
                               const uint8_t *lknown, const uint8_t *rknown, const double *lp, const double *rp,
-                              const Lanes &ln) {
+                              uint8_t *ldi, uint8_t *rdi, int8_t *itab, const Lanes &ln) {
   const int L1 = mL.L1, L2L = mL.L2, L2R = mR.L2, eb = p.extraband;
   const int rbandL = L2L - L1 + eb, lbandL = eb, rbandR = L2R - L1 + eb, lbandR = eb;   /* 3545-3549 */
   const int finalp = (p.flags & DPC_F_FINALP) != 0, halfp = (p.flags & DPC_F_HALFP) != 0;
@@ -407,6 +418,10 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
   Best best; best.score = DPC_BRIDGE_FLOOR; best.key = 0x7fffffff;
   double bestprob = 0.0; int probkey = 0x7fffffff;
   int it;
+  for (int c = ln.lane; c < L2L; c += ln.n) ldi[c] = (uint8_t)dpc_leftdi(gL[c], gL[c + 1]);
+  for (int c = ln.lane; c < L2R; c += ln.n) rdi[c] = (uint8_t)dpc_rightdi(gR[c + 1], gR[c]);
+  for (int t = ln.lane; t < 64; t += ln.n) itab[t] = (int8_t)dpc_intron_score(&it, t, t, p.cdna_direction, p.reward, finalp);
+  DPC_SYNC();
   for (int rL = 1; rL < L1; rL++) {
     const int rR = L1 - rL;
     int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
@@ -414,20 +429,33 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
     int nL = chighL - cloL + 1, nR = chighR - cloR + 1;
     if (nL < 0) nL = 0;
     if (nR < 0) nR = 0;
-    for (int j = ln.lane; j < nL + nR; j += ln.n) {
-      int left = j < nL, cL = left ? cloL + j : rL, cR = left ? rR : cloR + (j - nL);
-      if (!(left ? cR < p.gap - cL : cL < p.gap - cR)) continue;
-      int key = rL * 8192 + j;
-      if (probmode && lp[cL] + rp[cR] <= bestprob) continue;            /* 3918, 3971 */
-      int sL = dpc_nscore(mL, rL, cL) + (lknown && lknown[cL] ? 20 : 0);
-      int sR = dpc_nscore(mR, rR, cR) + (rknown && rknown[cR] ? 20 : 0);
-      if (left) { if (dpc_dirN(mL, rL, cL) > 0) sL -= 1; }              /* 3724-3727 */
-      else { if (dpc_dirN(mR, rR, cR) > 0) sR -= 1; }                   /* 3774-3777 */
-      int sI = dpc_intron_score(&it, dpc_leftdi(gL[cL], gL[cL + 1]), dpc_rightdi(gR[cR + 1], gR[cR]), p.cdna_direction, p.reward, finalp);
-      int s = sL + sI + sR;
-      if (probmode) {
-        if (s >= p.score_threshold) { bestprob = lp[cL] + rp[cR]; probkey = key; }
-      } else if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+    /* the two main-diagonal cells every candidate of this row pair is combined with */
+    const int dR = dpc_nscore(mR, rR, rR) + (rknown && rknown[rR] ? 20 : 0);
+    const int dL = dpc_nscore(mL, rL, rL) + (lknown && lknown[rL] ? 20 : 0);
+    const int diR = rdi[rR], diL = ldi[rL];
+    const int16_t *rowL = mL.nband + (rL - 1) * mL.W + (mL.lband - rL);     /* rowL[cL] = nogap[rL][cL] */
+    const int16_t *rowR = mR.nband + (rR - 1) * mR.W + (mR.lband - rR);
+    /* left scan (3700-3766): cL over the band of row rL, cR = rR */
+    for (int j = ln.lane; j < nL; j += ln.n) {
+      const int cL = cloL + j;
+      if (!(rR < p.gap - cL)) continue;
+      if (probmode && lp[cL] + rp[rR] <= bestprob) continue;            /* 3918 */
+      const int s = rowL[cL] + (lknown && lknown[cL] ? 20 : 0) - dpc_nondiag(mL, rL, cL)                /* 3724-3727 */
+                    + itab[ldi[cL] & diR] + dR;
+      const int key = rL * 8192 + j;
+      if (probmode) { if (s >= p.score_threshold) { bestprob = lp[cL] + rp[rR]; probkey = key; } }
+      else if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+    }
+    /* right scan (3768-3816): cR over the band of row rR, cL = rL */
+    for (int j = ln.lane; j < nR; j += ln.n) {
+      const int cR = cloR + j;
+      if (!(rL < p.gap - cR)) continue;
+      if (probmode && lp[rL] + rp[cR] <= bestprob) continue;            /* 3971 */
+      const int s = rowR[cR] + (rknown && rknown[cR] ? 20 : 0) - dpc_nondiag(mR, rR, cR)                /* 3774-3777 */
+                    + itab[diL & rdi[cR]] + dL;
+      const int key = rL * 8192 + nL + j;
+      if (probmode) { if (s >= p.score_threshold) { bestprob = lp[rL] + rp[cR]; probkey = key; } }
+      else if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
     }
   }
   if (probmode) {
@@ -524,7 +552,7 @@ struct ArenaLayout {
   /* two regions: `small` (characters, profiles, op strings: read on the fill's critical path, always in shared
    * memory when the problem runs in a shared-memory class) and `bulk` (direction bits, nogap bands, fallback-fill
    * state: written once per row, read by bridge and traceback; goes to HBM scratch when it does not fit) */
-  uint32_t rowch[2], colch[2], prof[2], ops[2], small;
+  uint32_t rowch[2], colch[2], prof[2], ops[2], di[2], itab, small;
   uint32_t dir[2], nband[2], state, bulk;
   uint32_t total;                        /* small + bulk */
 };
@@ -554,12 +582,16 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
     a.prof[i] = so;
     if (d.planes && p.kind != 2) so += (uint32_t)d.rows * 4;
     a.ops[i] = so; so = dpc_al(so + 2 * (uint32_t)(d.rows + d.cols + 2), 4);
+    a.di[i] = so;
+    if (p.kind == 1) so = dpc_al(so + (uint32_t)d.cols + 2, 4);         /* dinucleotide code per column (intron bridge) */
     a.dir[i] = bo;
     if (d.planes) bo += (uint32_t)d.rows * (uint32_t)d.cpl * 16; else bo += (uint32_t)d.rows * (uint32_t)d.wstride * 4;
     if (a.nmat == 2) { a.nband[i] = bo; bo = dpc_al(bo + (uint32_t)d.rows * (uint32_t)d.W * 2, 16); } else a.nband[i] = 0;
   }
   a.state = bo;
   if (need_state) bo += 9 * (uint32_t)(maxrows + 1) * 4;
+  a.itab = so;
+  if (p.kind == 1) so += 64;
   a.small = dpc_al(so, 16);
   a.bulk = dpc_al(bo, 16);
   a.total = a.small + a.bulk;
@@ -698,7 +730,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         const double *lp = 0, *rp = 0;
         if (p.flags & DPC_F_PROBMODE) { lp = (const double *)aux; rp = lp + p.L2; aux += 8 * (uint32_t)(p.L2 + p.L2R); }
         if (p.flags & DPC_F_KNOWN) { lknown = aux; rknown = aux + p.L2; }
-        dpc_bridge_intron(br, m0, m1, p, lknown, rknown, lp, rp, ln);
+        dpc_bridge_intron(br, m0, m1, p, lknown, rknown, lp, rp, arena + a.di[0], arena + a.di[1], (int8_t *)(arena + a.itab), ln);
         ok = br.have && br.finalscore >= 0;                               /* 4083-4101 */
         if (ok && !(p.flags & DPC_F_NOVEL) && (p.flags & DPC_F_KNOWN) && (!lknown[br.cL] || !rknown[br.cR])) ok = 0;
       } else {
