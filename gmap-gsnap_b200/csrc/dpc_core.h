@@ -124,7 +124,8 @@ struct Mat {
                                0: rows = genome, columns = query (_fwd_12/_rev_12, 1741-2044) */
   uint8_t *rowch, *colch;   /* characters in matrix order: raw query bytes / genome codes */
   int planes, cpl, cplsh;   /* planes != 0: directions are bit planes; every lane owns cpl = 1 << cplsh adjacent diagonals */
-  uint32_t *prof;           /* planes, query rows: per row the 6 signed 4-bit scores of its query character */
+  uint32_t *prof;           /* planes, query rows: per row the 6 biased 4-bit scores of its query character */
+  int prof_rev;             /* the profile array belongs to the forward query: row r reads prof[L1 - r] */
   uint32_t *dir;            /* nibbles: rows 1..L1, nibble (r-1)*wstride*8 + (c-r+lband);
                                planes:  word ((r-1)*cpl + k%cpl)*4 + p, bit k/cpl, k = c-r+lband, with plane
                                p = 0 nogap came from gap1 (HORIZ), 1 nogap came from gap2 (VERT),
@@ -549,11 +550,11 @@ struct MatDims { int rows, cols, lband, rband, W, wstride, planes, cpl; };
 struct ArenaLayout {
   int nmat;
   MatDims d[2];
-  /* two regions: `small` (characters, profiles, op strings: read on the fill's critical path, always in shared
-   * memory when the problem runs in a shared-memory class) and `bulk` (direction bits, nogap bands, fallback-fill
-   * state: written once per row, read by bridge and traceback; goes to HBM scratch when it does not fit) */
-  uint32_t rowch[2], colch[2], prof[2], ops[2], di[2], itab, small;
-  uint32_t dir[2], nband[2], state, bulk;
+  /* two regions: `small` (characters, profiles, bridge tables: read on the fill's critical path, always in shared
+   * memory when the problem runs in the shared-memory class) and `bulk` (direction bits, nogap bands, op strings,
+   * fallback-fill state: written once per row, read by bridge and traceback; goes to HBM scratch when it does not fit) */
+  uint32_t rowch[2], colch[2], prof[2], di[2], itab, small;
+  uint32_t dir[2], nband[2], ops[2], state, bulk;
   uint32_t total;                        /* small + bulk */
 };
 #define DPC_MAX_CPL 4                       /* row-sweep fill: 1, 2 or 4 diagonals per lane, bands of up to 128 */
@@ -579,14 +580,14 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
     if (d.rows > maxrows) maxrows = d.rows;
     a.rowch[i] = so; so = dpc_al(so + (uint32_t)d.rows + 2, 4);
     a.colch[i] = so; so = dpc_al(so + (uint32_t)d.cols + 2, 4);
-    a.prof[i] = so;
-    if (d.planes && p.kind != 2) so += (uint32_t)d.rows * 4;
-    a.ops[i] = so; so = dpc_al(so + 2 * (uint32_t)(d.rows + d.cols + 2), 4);
+    if (i == 1 && p.kind == 1) a.prof[1] = a.prof[0];                 /* R rows are the same query, reversed */
+    else { a.prof[i] = so; if ((d.planes || (p.kind == 1 && fillmode == 2)) && p.kind != 2) so += (uint32_t)d.rows * 4; }
     a.di[i] = so;
     if (p.kind == 1) so = dpc_al(so + (uint32_t)d.cols + 2, 4);         /* dinucleotide code per column (intron bridge) */
     a.dir[i] = bo;
     if (d.planes) bo += (uint32_t)d.rows * (uint32_t)d.cpl * 16; else bo += (uint32_t)d.rows * (uint32_t)d.wstride * 4;
     if (a.nmat == 2) { a.nband[i] = bo; bo = dpc_al(bo + (uint32_t)d.rows * (uint32_t)d.W * 2, 16); } else a.nband[i] = 0;
+    a.ops[i] = bo; bo = dpc_al(bo + 2 * (uint32_t)(d.rows + d.cols + 2), 16);
   }
   a.state = bo;
   if (need_state) bo += 9 * (uint32_t)(maxrows + 1) * 4;
@@ -604,6 +605,7 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *small, ui
   m.rowch = small + a.rowch[i]; m.colch = small + a.colch[i];
   m.planes = d.planes; m.cpl = d.cpl; m.cplsh = d.cpl == 1 ? 0 : d.cpl == 2 ? 1 : 2;
   m.prof = (uint32_t *)(small + a.prof[i]);
+  m.prof_rev = i == 1 && p.kind == 1;
   m.dir = (uint32_t *)(bulk + a.dir[i]);
   m.nband = a.nmat == 2 ? (int16_t *)(bulk + a.nband[i]) : (int16_t *)0;
 }
@@ -690,7 +692,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       dpc_warp_best(es.best, m0.late, ln);
       finalscore = es.best.score;
       brL = es.best.key / (p.L2 + 1); bcL = es.best.key % (p.L2 + 1);
-      uint16_t *ops = (uint16_t *)(arena + a.ops[0]);
+      uint16_t *ops = (uint16_t *)(bulk + a.ops[0]);
       nopsL = fill.walk(m0, brL, bcL, five, p.cdna_direction, ops, ln);
       dpc_count_ops(m0, brL, bcL, ops, nopsL, ct, tb, ln);
       opsL = ops;
@@ -704,8 +706,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         for (int i = ln.lane; i < p.L1; i += ln.n) {
           int qf = pool[p.q0 + (uint32_t)i], qr = pool[p.q0 + (uint32_t)(p.L1 - 1 - i)];
           m0.rowch[i] = (uint8_t)qf; m1.rowch[i] = (uint8_t)qr;
-          if (m0.planes) m0.prof[i] = dpc_pack_prof(score, qf);
-          if (m1.planes) m1.prof[i] = dpc_pack_prof(score, qr);
+          if (m0.planes || m1.planes) m0.prof[i] = dpc_pack_prof(score, qf);      /* m1 reads the same array backwards */
         }
         for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2 + i);
         for (int i = ln.lane; i < p.L2R; i += ln.n) m1.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2R - i);
@@ -741,7 +742,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       if (br.have) status |= DPC_ST_HAVE;
       if (ok) {
         status |= DPC_ST_OK;
-        uint16_t *oR = (uint16_t *)(arena + a.ops[1]), *oL = (uint16_t *)(arena + a.ops[0]);
+        uint16_t *oR = (uint16_t *)(bulk + a.ops[1]), *oL = (uint16_t *)(bulk + a.ops[0]);
         nopsR = fill.walk(m1, brR, bcR, 1, p.cdna_direction, oR, ln);
         dpc_count_ops(m1, brR, bcR, oR, nopsR, ct, tb, ln);
         nopsL = fill.walk(m0, brL, bcL, 0, p.cdna_direction, oL, ln);

@@ -153,11 +153,12 @@ struct ClassLaunch {
   int n;
 };
 
-/* per-warp shared-memory arena classes: with 8 warps per block and the 2 blocks per SM the register file allows,
- * 13 KB per warp is what fits in 227 KB; problems whose bulk region does not fit keep it in HBM scratch, problems
- * whose small region alone does not fit run entirely from HBM scratch (last class) */
-#define NCLASS 4
-static const uint32_t k_class_bytes[NCLASS] = { 3 << 10, 6 << 10, 13 << 10, 0 };
+/* The register file allows 2 blocks of 8 warps per SM, so one shared-memory class is enough: 13 KB per warp
+ * (2 x (8 x 13 KB + tables) fits in 227 KB).  A problem whose bulk region does not fit keeps it in HBM scratch; a
+ * problem whose small region alone does not fit runs entirely from HBM scratch (second class). */
+#define NCLASS 2
+static const uint32_t k_class_bytes[NCLASS] = { 13 << 10, 0 };
+#define NBUCKET 64                       /* work buckets for longest-first scheduling */
 #define SCRATCH_BUDGET (16ull << 30)
 
 /* ---- engine: one stream, its device buffers and the batch in flight on it -------------------- */
@@ -262,53 +263,61 @@ struct Engine {
     h2d_bytes = d2h_bytes = 0;
     if (n == 0) return DPC_OK;
 
-    /* bin the problems by arena size; oversize ones get HBM scratch */
     const int with_state = g_force_generic ? 1 : 2;   /* must match FILL::fillmode of the kernel */
     const uint32_t smem_limit = (uint32_t)(d.max_smem - (int)sizeof(DevTables) - 2048);
+    /* class (shared-memory arena or HBM only) and a work bucket per problem: within a class the list is ordered
+       by descending work so that the long problems start first and the tail of the launch is made of short ones */
     cls.resize(n);
-    size_t count[NCLASS] = { 0 };
+    size_t count[NCLASS * NBUCKET] = { 0 };
     uint64_t scratch_total = 0, ovf_worst = 0;
     for (size_t i = 0; i < n; i++) {
       DevProb &p = b.dprobs[i];
-      int k = 0;
+      int k = 0, bucket = NBUCKET - 1;
       if (!((p.kind == DPC_END5_GAP || p.kind == DPC_END3_GAP) && p.endalign == DPC_QUERYEND_NOGAPS)) {
         ArenaLayout a;
         dpc_layout(p, a, with_state);
         uint64_t need = 0;                 /* HBM scratch of this problem */
-        for (k = 0; k < NCLASS - 1; k++) if (a.total <= k_class_bytes[k] && k_class_bytes[k] <= smem_limit) break;
-        if (k == NCLASS - 1) {
-          need = a.bulk;
-          for (k = 0; k < NCLASS - 1; k++) if (a.small <= k_class_bytes[k] && k_class_bytes[k] <= smem_limit) break;
-          if (k == NCLASS - 1) need = a.total;
+        if (!(a.total <= k_class_bytes[0] && k_class_bytes[0] <= smem_limit)) {
+          if (a.small <= k_class_bytes[0] && k_class_bytes[0] <= smem_limit) need = a.bulk;
+          else { need = a.total; k = 1; }
         }
         if (need) {
           if (scratch_total + need > SCRATCH_BUDGET) return DPC_ERR_NOMEM;
           p.scratch_lo = (uint32_t)scratch_total; p.scratch_hi = (uint32_t)(scratch_total >> 32);
           scratch_total += need;
         }
-        uint64_t worst = 0;
-        for (int m = 0; m < a.nmat; m++) worst += (uint64_t)(a.d[m].rows + a.d[m].cols + 2);
+        uint64_t worst = 0, work = 0;
+        for (int m = 0; m < a.nmat; m++) {
+          worst += (uint64_t)(a.d[m].rows + a.d[m].cols + 2);
+          work += (uint64_t)a.d[m].rows * (uint64_t)a.d[m].cpl;             /* row-sweep iterations x diagonals per lane */
+        }
         if (worst > DPC_INLINE_OPS) ovf_worst += worst;
+        /* bucket 0 = most work: 8 rows per bucket up to 504 lane-rows, everything longer in bucket 0 */
+        int wb = (int)(work >> 3);
+        if (wb > NBUCKET - 1) wb = NBUCKET - 1;
+        bucket = NBUCKET - 1 - wb;
       }
-      cls[i] = (uint8_t)k;
-      count[k]++;
+      cls[i] = (uint8_t)(k * NBUCKET + bucket);
+      count[k * NBUCKET + bucket]++;
     }
     list.clear();
     list.grow(n);
-    size_t off[NCLASS], at = 0;
-    for (int k = 0; k < NCLASS; k++) { off[k] = at; at += count[k]; }
+    size_t off[NCLASS * NBUCKET], at = 0;
+    for (int k = 0; k < NCLASS * NBUCKET; k++) { off[k] = at; at += count[k]; }
     {
-      size_t cur[NCLASS];
-      for (int k = 0; k < NCLASS; k++) cur[k] = off[k];
+      size_t cur[NCLASS * NBUCKET];
+      for (int k = 0; k < NCLASS * NBUCKET; k++) cur[k] = off[k];
       for (size_t i = 0; i < n; i++) list[cur[cls[i]]++] = (uint32_t)i;
     }
     for (int k = 0; k < NCLASS; k++) {
-      if (!count[k]) continue;
+      size_t cnt = 0;
+      for (int q = 0; q < NBUCKET; q++) cnt += count[k * NBUCKET + q];
+      if (!cnt) continue;
       ClassLaunch L;
-      L.smem = k < NCLASS - 1;
+      L.smem = k == 0;
       L.arena_bytes = k_class_bytes[k];
       L.wpb = 8;
-      L.list_off = off[k]; L.n = (int)count[k];
+      L.list_off = off[k * NBUCKET]; L.n = (int)cnt;
       launches.push_back(L);
     }
     /* ops overflow arena: problems whose worst case exceeds the inline slots (bounded) */
