@@ -153,11 +153,13 @@ struct ClassLaunch {
   int n;
 };
 
-/* The register file allows 2 blocks of 8 warps per SM, so one shared-memory class is enough: 13 KB per warp
- * (2 x (8 x 13 KB + tables) fits in 227 KB).  A problem whose bulk region does not fit keeps it in HBM scratch; a
- * problem whose small region alone does not fit runs entirely from HBM scratch (second class). */
-#define NCLASS 2
-static const uint32_t k_class_bytes[NCLASS] = { 13 << 10, 0 };
+/* The register file allows 2 blocks of 8 warps per SM, so shared memory never limits occupancy below 13 KB per
+ * warp (2 x (8 x 13 KB + tables) fits in 227 KB).  Two shared-memory classes: 6 KB per warp leaves most of the
+ * 228 KB to L1 (descriptors, genome blocks and query bytes are read through it), 13 KB takes what is bigger.  A
+ * problem whose bulk region does not fit keeps it in HBM scratch; a problem whose small region alone does not fit
+ * runs entirely from HBM scratch (last class). */
+#define NCLASS 3
+static const uint32_t k_class_bytes[NCLASS] = { 6 << 10, 13 << 10, 0 };
 #define NBUCKET 64                       /* work buckets for longest-first scheduling */
 #define SCRATCH_BUDGET (16ull << 30)
 
@@ -264,7 +266,6 @@ struct Engine {
     if (n == 0) return DPC_OK;
 
     const int with_state = g_force_generic ? 1 : 2;   /* must match FILL::fillmode of the kernel */
-    const uint32_t smem_limit = (uint32_t)(d.max_smem - (int)sizeof(DevTables) - 2048);
     /* class (shared-memory arena or HBM only) and a work bucket per problem: within a class the list is ordered
        by descending work so that the long problems start first and the tail of the launch is made of short ones */
     cls.resize(n);
@@ -277,10 +278,10 @@ struct Engine {
         ArenaLayout a;
         dpc_layout(p, a, with_state);
         uint64_t need = 0;                 /* HBM scratch of this problem */
-        if (!(a.total <= k_class_bytes[0] && k_class_bytes[0] <= smem_limit)) {
-          if (a.small <= k_class_bytes[0] && k_class_bytes[0] <= smem_limit) need = a.bulk;
-          else { need = a.total; k = 1; }
-        }
+        if (a.total <= k_class_bytes[0]) k = 0;
+        else if (a.total <= k_class_bytes[1]) k = 1;
+        else if (a.small <= k_class_bytes[1]) { k = 1; need = a.bulk; }
+        else { k = 2; need = a.total; }
         if (need) {
           if (scratch_total + need > SCRATCH_BUDGET) return DPC_ERR_NOMEM;
           p.scratch_lo = (uint32_t)scratch_total; p.scratch_hi = (uint32_t)(scratch_total >> 32);
@@ -314,7 +315,7 @@ struct Engine {
       for (int q = 0; q < NBUCKET; q++) cnt += count[k * NBUCKET + q];
       if (!cnt) continue;
       ClassLaunch L;
-      L.smem = k == 0;
+      L.smem = k < NCLASS - 1;
       L.arena_bytes = k_class_bytes[k];
       L.wpb = 8;
       L.list_off = off[k * NBUCKET]; L.n = (int)cnt;
