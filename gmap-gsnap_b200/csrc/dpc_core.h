@@ -125,7 +125,8 @@ struct Mat {
   uint8_t *rowch, *colch;   /* characters in matrix order: raw query bytes / genome codes */
   int planes, cpl, cplsh;   /* planes != 0: directions are bit planes; every lane owns cpl = 1 << cplsh adjacent diagonals */
   uint32_t *prof;           /* planes, query rows: per row the 6 biased 4-bit scores of its query character */
-  int prof_rev;             /* the profile array belongs to the forward query: row r reads prof[L1 - r] */
+  int prof_base, prof_step; /* row r reads prof[prof_base + r * prof_step]: (-1, 1), or (L1, -1) when the array belongs to
+                               the forward query and this matrix runs over the reversed one */
   uint32_t *dir;            /* nibbles: rows 1..L1, nibble (r-1)*wstride*8 + (c-r+lband);
                                planes:  word ((r-1)*cpl + k%cpl)*4 + p, bit k/cpl, k = c-r+lband, with plane
                                p = 0 nogap came from gap1 (HORIZ), 1 nogap came from gap2 (VERT),
@@ -605,7 +606,7 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *small, ui
   m.rowch = small + a.rowch[i]; m.colch = small + a.colch[i];
   m.planes = d.planes; m.cpl = d.cpl; m.cplsh = d.cpl == 1 ? 0 : d.cpl == 2 ? 1 : 2;
   m.prof = (uint32_t *)(small + a.prof[i]);
-  m.prof_rev = i == 1 && p.kind == 1;
+  if (i == 1 && p.kind == 1) { m.prof_base = d.rows; m.prof_step = -1; } else { m.prof_base = -1; m.prof_step = 1; }
   m.dir = (uint32_t *)(bulk + a.dir[i]);
   m.nband = a.nmat == 2 ? (int16_t *)(bulk + a.nband[i]) : (int16_t *)0;
 }

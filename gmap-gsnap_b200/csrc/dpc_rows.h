@@ -68,7 +68,7 @@ DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
   }
 
   for (int r = 1; r <= L1; r++) {
-    const int prof = QROWS ? (int)m.prof[m.prof_rev ? L1 - r : r - 1] : 0;
+    const int prof = QROWS ? (int)m.prof[m.prof_base + r * m.prof_step] : 0;
     const int rowg = QROWS ? 0 : (int)m.rowch[r - 1];
     const int col0 = open + r * extend;                   /* gap2 of (r,0), 1477-1488 */
     /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */

@@ -52,12 +52,22 @@ __global__ void __launch_bounds__(256) dpc_solve_kernel(const KernelArgs a) {
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   Lanes ln; ln.lane = threadIdx.x & 31; ln.n = 32;
+  /* work items are claimed one ahead, so the next problem's descriptor is already on its way
+     from HBM while the current problem is being solved (the list is ordered by work, not by address) */
+  int nxt = 0;
+  if (ln.lane == 0) nxt = (int)atomicAdd(a.counter, 1u);
+  nxt = __shfl_sync(0xffffffffu, nxt, 0);
   for (;;) {
-    int i = 0;
-    if (ln.lane == 0) i = (int)atomicAdd(a.counter, 1u);
-    i = __shfl_sync(0xffffffffu, i, 0);
+    const int i = nxt;
     if (i >= a.n) break;
     const uint32_t pi = a.list[i];
+    if (ln.lane == 0) nxt = (int)atomicAdd(a.counter, 1u);
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    if (nxt < a.n) {
+      const uint32_t pn = a.list[nxt];
+      const char *d = (const char *)&a.probs[pn];
+      if (ln.lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + 64 * ln.lane));
+    }
     const DevProb p = a.probs[pi];
     /* shared-memory classes: the warp's arena holds the small region and, when it fits, the bulk region too;
        otherwise the bulk region (direction planes, nogap bands) lives in this problem's HBM scratch.  The
