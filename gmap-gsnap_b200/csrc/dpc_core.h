@@ -637,7 +637,10 @@ DPC_HD void dpc_emit_ops(DevRes *res, const uint16_t *opsL, int nL, const uint16
 
 /* Solves problem `p` with the fill routine `FILL` (generic here; the CUDA build also has the
  * register/shuffle fill for narrow bands).  `arena` must hold dpc_layout(p).total bytes. */
-template <class FILL>
+/* KG selects what is compiled in: 0 the one-matrix solvers (single gap, end gaps), 1 genome gap, 2 cDNA gap,
+ * -1 everything (the CPU simulation).  The CUDA build instantiates one kernel per group so that each carries only
+ * its own code and register needs. */
+template <class FILL, int KG>
 DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint32_t *blocks, const DevTables *tb,
                               uint8_t *arena, uint32_t arena_bytes, uint8_t *scratch, DevRes *res, const OvfArena &ovf,
                               FILL &fill, const Lanes &ln) {
@@ -651,7 +654,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
   const int8_t *score = &tb->score[p.type][0][0];
   const uint16_t *opsL = 0, *opsR = 0;
 
-  if ((p.kind == 3 || p.kind == 4) && p.endalign == 2) {
+  if ((KG == 0 || KG == -1) && (p.kind == 3 || p.kind == 4) && p.endalign == 2) {
     /* QUERYEND_NOGAPS: find_best_endpoint_to_queryend_nogaps 2358-2369 + traceback_nogaps 2815-2872 */
     int n = p.L1 < p.L2 ? p.L1 : p.L2, nm = 0, nmm = 0, star = 0, five = p.kind == 3;
     for (int i = ln.lane; i < n; i += ln.n) {
@@ -674,7 +677,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
     Mat m0, m1;
     uint8_t *bulk = a.total <= arena_bytes ? arena + a.small : scratch;
     int32_t *st = (int32_t *)(bulk + a.state);
-    if (p.kind == 0 || p.kind == 3 || p.kind == 4) {
+    if (KG == 0 || (KG == -1 && (p.kind == 0 || p.kind == 3 || p.kind == 4))) {
       /* Dynprog_single_gap 4450-4572, Dynprog_end5_gap 5094-5284, Dynprog_end3_gap 5556-5741 */
       const int five = p.kind == 3;
       dpc_make_mat(m0, a, 0, arena, bulk, p, five ? !late : late, 1);
@@ -699,7 +702,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       opsL = ops;
       status |= DPC_ST_HAVE | DPC_ST_OK;
     } else {
-      const int cdna = p.kind == 2;
+      const int cdna = KG == 2 || (KG == -1 && p.kind == 2);
       dpc_make_mat(m0, a, 0, arena, bulk, p, late, !cdna);
       dpc_make_mat(m1, a, 1, arena, bulk, p, !late, !cdna);
       if (!cdna) {

@@ -37,10 +37,11 @@ struct KernelArgs {
   uint8_t *scratch;            /* HBM arenas (SMEM == false) */
   uint32_t arena_bytes;        /* per-warp shared-memory arena (SMEM == true) */
   unsigned int *counter;       /* dynamic work distribution */
-  int force_generic;
 };
 
-template <bool SMEM>
+/* SMEM: arenas in shared memory (else everything in HBM scratch); KG: kind group (0 one-matrix solvers, 1 genome
+ * gap, 2 cDNA gap); GEN: route every matrix through the memory-state fill (test hook) */
+template <bool SMEM, int KG, bool GEN>
 __global__ void __launch_bounds__(256) dpc_solve_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DevTables s_tables;
@@ -75,15 +76,28 @@ __global__ void __launch_bounds__(256) dpc_solve_kernel(const KernelArgs a) {
     uint8_t *scratch = a.scratch + (((uint64_t)p.scratch_hi << 32) | p.scratch_lo);
     uint8_t *arena = SMEM ? smem + (size_t)warp * a.arena_bytes : scratch;
     const uint32_t arena_bytes = SMEM ? a.arena_bytes : 0xffffffffu;
-    if (a.force_generic) {
+    if (GEN) {
       GenericFill fill;
-      dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
+      dpc_solve_problem<GenericFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
     } else {
       RowFill fill;
-      dpc_solve_problem(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
+      dpc_solve_problem<RowFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
     }
     __syncwarp();
   }
+}
+
+typedef void (*kernel_fn)(const KernelArgs);
+/* [smem][kind group][generic] */
+static kernel_fn kernel_of(bool smem, int kg, bool gen) {
+  static const kernel_fn tab[2][3][2] = {
+    { { dpc_solve_kernel<false, 0, false>, dpc_solve_kernel<false, 0, true> },
+      { dpc_solve_kernel<false, 1, false>, dpc_solve_kernel<false, 1, true> },
+      { dpc_solve_kernel<false, 2, false>, dpc_solve_kernel<false, 2, true> } },
+    { { dpc_solve_kernel<true, 0, false>, dpc_solve_kernel<true, 0, true> },
+      { dpc_solve_kernel<true, 1, false>, dpc_solve_kernel<true, 1, true> },
+      { dpc_solve_kernel<true, 2, false>, dpc_solve_kernel<true, 2, true> } } };
+  return tab[smem ? 1 : 0][kg][gen ? 1 : 0];
 }
 
 /* ---- process-wide device state ------------------------------------------------------------ */
@@ -126,7 +140,10 @@ static int ensure_device(int dev) {
   CK(cudaMemcpy(d.d_blocks, g.setup.genome_blocks, g.setup.genome_nwords * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d.d_tables, sizeof(DevTables)));
   CK(cudaMemcpy(d.d_tables, &g.tables, sizeof(DevTables), cudaMemcpyHostToDevice));
-  CK(cudaFuncSetAttribute(dpc_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem - (int)sizeof(DevTables) - 1024));
+  for (int kg = 0; kg < 3; kg++)
+    for (int gen = 0; gen < 2; gen++)
+      CK(cudaFuncSetAttribute((const void *)kernel_of(true, kg, gen != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              d.max_smem - (int)sizeof(DevTables) - 1024));
   d.version = g_version;
   d.ready = true;
   return DPC_OK;
@@ -157,6 +174,7 @@ static Alloc pinned() { Alloc a = { pinned_alloc, pinned_release }; return a; }
 
 struct ClassLaunch {
   bool smem;
+  int kg;
   uint32_t arena_bytes;
   int wpb;
   size_t list_off;
@@ -169,7 +187,7 @@ struct ClassLaunch {
  * problem whose bulk region does not fit keeps it in HBM scratch; a problem whose small region alone does not fit
  * runs entirely from HBM scratch (last class). */
 #define NCLASS 3
-static const uint32_t k_class_bytes[NCLASS] = { 6 << 10, 13 << 10, 0 };
+static uint32_t k_class_bytes[NCLASS] = { 6 << 10, 13 << 10, 0 };
 #define NBUCKET 64                       /* work buckets for longest-first scheduling */
 #define SCRATCH_BUDGET (16ull << 30)
 
@@ -190,7 +208,7 @@ struct Engine {
   PBuf<uint16_t> h_ovf;
   PBuf<unsigned int> h_counters;
   PBuf<uint32_t> list;
-  std::vector<uint8_t> cls;
+  std::vector<uint16_t> cls;
   std::vector<ClassLaunch> launches;
   Scratch scratch;
   size_t ovf_cap;
@@ -245,17 +263,15 @@ struct Engine {
       a.pool = d_pool.p; a.blocks = d.d_blocks; a.tables = d.d_tables; a.res = d_res.p;
       a.ovf.ops = d_ovf.p; a.ovf.used = d_counters.p; a.ovf.cap = (unsigned int)ovf_cap;
       a.scratch = d_scratch.p; a.arena_bytes = L.arena_bytes; a.counter = d_counters.p + 1 + k;
-      a.force_generic = g_force_generic;
       const int threads = L.wpb * 32;
       const size_t smem = L.smem ? (size_t)L.wpb * L.arena_bytes : 0;
       int per_sm = 1;
-      if (L.smem) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dpc_solve_kernel<true>, threads, smem)); }
-      else { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dpc_solve_kernel<false>, threads, 0)); }
+      const kernel_fn fn = kernel_of(L.smem, L.kg, g_force_generic != 0);
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, threads, smem));
       if (per_sm < 1) per_sm = 1;
       int grid = (L.n + L.wpb - 1) / L.wpb;
       if (grid > d.sm_count * per_sm) grid = d.sm_count * per_sm;
-      if (L.smem) dpc_solve_kernel<true><<<grid, threads, smem, stream>>>(a);
-      else dpc_solve_kernel<false><<<grid, threads, 0, stream>>>(a);
+      fn<<<grid, threads, smem, stream>>>(a);
       CK(cudaGetLastError());
       nlaunch++;
     }
@@ -279,7 +295,7 @@ struct Engine {
     /* class (shared-memory arena or HBM only) and a work bucket per problem: within a class the list is ordered
        by descending work so that the long problems start first and the tail of the launch is made of short ones */
     cls.resize(n);
-    size_t count[NCLASS * NBUCKET] = { 0 };
+    size_t count[NCLASS * 3 * NBUCKET] = { 0 };
     uint64_t scratch_total = 0, ovf_worst = 0;
     for (size_t i = 0; i < n; i++) {
       DevProb &p = b.dprobs[i];
@@ -307,26 +323,30 @@ struct Engine {
         int wb = (int)(work >> 3);
         if (wb > NBUCKET - 1) wb = NBUCKET - 1;
         bucket = NBUCKET - 1 - wb;
+        static const bool nosort = getenv("DPC_NO_SORT") != NULL;
+        if (nosort) bucket = 0;
       }
-      cls[i] = (uint8_t)(k * NBUCKET + bucket);
-      count[k * NBUCKET + bucket]++;
+      const int kg = p.kind == DPC_GENOME_GAP ? 1 : p.kind == DPC_CDNA_GAP ? 2 : 0;
+      cls[i] = (uint16_t)((k * 3 + kg) * NBUCKET + bucket);
+      count[cls[i]]++;
     }
     list.clear();
     list.grow(n);
-    size_t off[NCLASS * NBUCKET], at = 0;
-    for (int k = 0; k < NCLASS * NBUCKET; k++) { off[k] = at; at += count[k]; }
+    size_t off[NCLASS * 3 * NBUCKET], at = 0;
+    for (int k = 0; k < NCLASS * 3 * NBUCKET; k++) { off[k] = at; at += count[k]; }
     {
-      size_t cur[NCLASS * NBUCKET];
-      for (int k = 0; k < NCLASS * NBUCKET; k++) cur[k] = off[k];
+      size_t cur[NCLASS * 3 * NBUCKET];
+      for (int k = 0; k < NCLASS * 3 * NBUCKET; k++) cur[k] = off[k];
       for (size_t i = 0; i < n; i++) list[cur[cls[i]]++] = (uint32_t)i;
     }
-    for (int k = 0; k < NCLASS; k++) {
+    for (int k = 0; k < NCLASS * 3; k++) {       /* one launch per (arena class, kind group) that has work */
       size_t cnt = 0;
       for (int q = 0; q < NBUCKET; q++) cnt += count[k * NBUCKET + q];
       if (!cnt) continue;
       ClassLaunch L;
-      L.smem = k < NCLASS - 1;
-      L.arena_bytes = k_class_bytes[k];
+      L.smem = k / 3 < NCLASS - 1;
+      L.kg = k % 3;
+      L.arena_bytes = k_class_bytes[k / 3];
       L.wpb = 8;
       L.list_off = off[k * NBUCKET]; L.n = (int)cnt;
       launches.push_back(L);
@@ -338,11 +358,11 @@ struct Engine {
     b.pool_align(16);
     int rc;
     if ((rc = d_probs.need(n)) || (rc = d_pool.need(b.pool.size())) || (rc = d_res.need(n)) ||
-        (rc = d_list.need(n)) || (rc = d_ovf.need(ovf_cap)) || (rc = d_counters.need(NCLASS + 2)) ||
+        (rc = d_list.need(n)) || (rc = d_ovf.need(ovf_cap)) || (rc = d_counters.need(NCLASS * 3 + 2)) ||
         (rc = d_scratch.need((size_t)scratch_total + 16)))
       return rc;
     h_res.clear(); h_res.grow(n);
-    h_counters.clear(); h_counters.grow(NCLASS + 2);
+    h_counters.clear(); h_counters.grow(NCLASS * 3 + 2);
     CK(cudaMemcpyAsync(d_probs.p, b.dprobs.data(), n * sizeof(DevProb), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_pool.p, b.pool.data(), b.pool.size(), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_list.p, list.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
@@ -456,6 +476,8 @@ int dpc_init(int maxlookback, int extraquerygap, int maxpeelback, int extramater
   std::lock_guard<std::mutex> lock(g_mu);
   int rc = host_init(maxlookback, extraquerygap, maxpeelback, extramaterial_end, extramaterial_paired, mode);
   g_version++;
+  const char *kb = getenv("DPC_CLASS0_KB");          /* tuning aid: size of the small shared-memory class */
+  if (kb && atoi(kb) >= 1 && atoi(kb) <= 13) k_class_bytes[0] = (uint32_t)atoi(kb) << 10;
   const char *e = getenv("DPC_FORCE_GENERIC_FILL");
   g_force_generic = (e && *e && *e != '0') ? 1 : 0;
   return rc;

@@ -51,9 +51,9 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
     uint8_t *sbase = scratch.data() + ((16 - ((uintptr_t)scratch.data() & 15)) & 15);
     const uint32_t arena_bytes = (k & 1) ? a.total : a.small;
     if (g_force_generic)
-      dpc_solve_problem(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gfill, ln);
+      dpc_solve_problem<GenericFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gfill, ln);
     else
-      dpc_solve_problem(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, rfill, ln);
+      dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, rfill, ln);
   }
   int64_t out = 0;
   dpc::Scratch sc;
