@@ -326,7 +326,7 @@ class CudaLib(_SolverLib):
     """gmap-gsnap_b200/csrc/libdynprog_cuda.so -- THE PRODUCT."""
 
     def __init__(self, path=None):
-        path = path or os.path.join(HERE, "csrc", "libdynprog_cuda.so")
+        path = path or os.environ.get("DPC_LIB") or os.path.join(HERE, "csrc", "libdynprog_cuda.so")
         if not os.path.exists(path):
             raise RuntimeError("libdynprog_cuda.so is not built (run __graft_entry__.build()); there is no CPU fallback")
         super().__init__(path)

@@ -687,6 +687,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         if (m0.planes) m0.prof[i] = dpc_pack_prof(score, q);
       }
       for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+      if (ln.lane == 0) m0.colch[p.L2] = 7;                               /* sentinel one past the last column */
       DPC_SYNC();
       EndSearch es; es.eb = p.extraband;
       if (p.kind == 0) { es.mode = 3; es.best.score = -2147483647; es.best.key = 0; }
@@ -723,6 +724,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         }
         for (int i = ln.lane; i < p.L1; i += ln.n) m0.colch[i] = pool[p.q0 + (uint32_t)i];
         for (int i = ln.lane; i < p.L1R; i += ln.n) m1.colch[i] = pool[p.q1 - (uint32_t)i];
+        if (ln.lane == 0) { m0.colch[p.L1] = 0; m1.colch[p.L1R] = 0; }   /* sentinel one past the last column */
       }
       DPC_SYNC();
       EndSearch es; es.mode = 0; es.eb = 0; es.best.score = 0; es.best.key = 0;

@@ -105,8 +105,10 @@ DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
     t = vmax(t, shfl_up_keep(t, 16));
     /* next row's column characters: every diagonal moves one column to the right */
     {
+      /* column index entering at the last diagonal: r + 32*CPL - lband - 1 >= 1 because lband < W <= 32*CPL;
+         past the matrix the staged sentinel colch[L2] is read (those diagonals are out of the matrix anyway) */
       const int gi = r + 32 * CPL - lband - 1;
-      const int chn = (gi >= 0 && gi < L2) ? (int)m.colch[gi] : 0;
+      const int chn = (int)m.colch[gi < L2 ? gi : L2];
       const VI nxt = shfl_down1(sh[0], QROWS ? (chn << 2) : ((chn & 127) << 3));
 #pragma unroll
       for (int j = 0; j + 1 < CPL; j++) sh[j] = sh[j + 1];

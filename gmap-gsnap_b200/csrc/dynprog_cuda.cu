@@ -39,10 +39,15 @@ struct KernelArgs {
   unsigned int *counter;       /* dynamic work distribution */
 };
 
+/* resident blocks per SM the compiler must leave room for: the one-matrix kernels fit DPC_MIN_BLOCKS_1M x 256
+ * threads (3 -> 80 registers, no spills in the row loop); the two-matrix kernels keep 2 (128 registers) */
+#ifndef DPC_MIN_BLOCKS_1M
+#define DPC_MIN_BLOCKS_1M 3
+#endif
 /* SMEM: arenas in shared memory (else everything in HBM scratch); KG: kind group (0 one-matrix solvers, 1 genome
  * gap, 2 cDNA gap); GEN: route every matrix through the memory-state fill (test hook) */
 template <bool SMEM, int KG, bool GEN>
-__global__ void __launch_bounds__(256) dpc_solve_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(256, (KG == 0 ? DPC_MIN_BLOCKS_1M : 2)) dpc_solve_kernel(const KernelArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DevTables s_tables;
   {
