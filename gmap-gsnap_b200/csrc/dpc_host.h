@@ -116,19 +116,43 @@ inline char host_genomic_nt(const dpc_problem_t &p, int genomicpos) {   /* get_g
   return compl_nt[dpc_genome_code(blocks, p.chroffset + p.chrpos + (p.genomiclength - 1) - (uint32_t)genomicpos)];
 }
 
+/* four bases per table entry: index = one byte of the 2-bit words (base i in bits 2i..2i+1);
+ * [0] ACGT in ascending order, [1] the same four reversed, [2] complemented ascending, [3] complemented reversed */
+struct NtLut {
+  uint32_t t[4][256];
+  NtLut() {
+    static const char f[4] = { 'A', 'C', 'G', 'T' }, c[4] = { 'T', 'G', 'C', 'A' };
+    for (int b = 0; b < 256; b++) {
+      uint32_t a = 0, ar = 0, k = 0, kr = 0;
+      for (int i = 0; i < 4; i++) {
+        int code = (b >> (2 * i)) & 3;
+        a |= (uint32_t)(uint8_t)f[code] << (8 * i);  ar |= (uint32_t)(uint8_t)f[code] << (8 * (3 - i));
+        k |= (uint32_t)(uint8_t)c[code] << (8 * i);  kr |= (uint32_t)(uint8_t)c[code] << (8 * (3 - i));
+      }
+      t[0][b] = a; t[1][b] = ar; t[2][b] = k; t[3][b] = kr;
+    }
+  }
+};
+inline const NtLut &nt_lut() { static const NtLut l; return l; }
+
 /* gathers get_genomic_nt(start +/- k) for k = 0..len-1 (dynprog.c:403-441): positions outside the segment give
- * '*'; inside, the bases come 32 at a time out of the (high, low, flags) blocks of genome.c:9325-9362 */
+ * '*'; inside, the bases come out of the (high, low, flags) blocks of genome.c:9325-9362, four at a time through a
+ * byte table where a block has no N flags */
 inline void gather_genome(const dpc_problem_t &p, const uint32_t *blocks, int start, int len, bool rev, char *out) {
   static const char fwd_nt[4] = { 'A', 'C', 'G', 'T' }, compl_nt[4] = { 'T', 'G', 'C', 'A' };
   if (len <= 0) return;
-  /* segment positions covered, ascending: [lo, lo+len) ; out index of position pos is rev ? start-pos : pos-start */
-  const int lo = rev ? start - (len - 1) : start;
+  const int lo = rev ? start - (len - 1) : start;          /* segment positions covered, ascending: [lo, lo+len) */
   if (allstar(p)) { memset(out, '*', (size_t)len); return; }
   const int64_t glen = p.genomiclength;
   const uint32_t base = p.chroffset + p.chrpos;
   const bool watson = p.watsonp != 0;
   const char *nt = watson ? fwd_nt : compl_nt;
-  /* as the genomic coordinate ascends, the output index moves by dir */
+  const NtLut &lut = nt_lut();
+  /* bases come out in ascending genome order on Watson and descending on Crick; the output index ascends unless
+     rev: the table gives the four characters of a byte in output order */
+  const bool out_desc = rev;
+  const bool bit_desc = !watson;
+  const uint32_t *tab = lut.t[(watson ? 0 : 2) + ((out_desc != bit_desc) ? 1 : 0)];
   for (int pos = lo; pos < lo + len;) {
     const int oi = rev ? start - pos : pos - start;
     if (pos < 0 || pos >= glen) { out[oi] = '*'; pos++; continue; }
@@ -136,20 +160,24 @@ inline void gather_genome(const dpc_problem_t &p, const uint32_t *blocks, int st
     const uint32_t *b = blocks + (uint64_t)(g >> 5) * 3;
     const uint64_t bits = ((uint64_t)b[0] << 32) | b[1];
     const uint32_t flags = b[2];
-    /* run inside this block: the absolute position ascends with pos on Watson, descends on Crick */
     int bit = (int)(g & 31);
-    int run = watson ? 32 - bit : bit + 1;
+    int run = watson ? 32 - bit : bit + 1;                  /* bases of this block on the way */
     if (run > lo + len - pos) run = lo + len - pos;
     if ((int64_t)pos + run > glen) run = (int)(glen - pos);
-    const int od = rev ? -1 : 1;
-    int o = oi;
-    if (watson) {
-      for (int k = 0; k < run; k++, bit++, o += od)
-        out[o] = ((flags >> bit) & 1u) ? 'N' : nt[(bits >> (2 * bit)) & 3u];
-    } else {
-      for (int k = 0; k < run; k++, bit--, o += od)
-        out[o] = ((flags >> bit) & 1u) ? 'N' : nt[(bits >> (2 * bit)) & 3u];
+    const int od = rev ? -1 : 1, bd = watson ? 1 : -1;
+    int o = oi, k = 0;
+    if (flags == 0) {
+      /* scalar until the bit index reaches a byte boundary in the direction of travel, then four at a time */
+      while (k < run && (watson ? (bit & 3) != 0 : (bit & 3) != 3)) { out[o] = nt[(bits >> (2 * bit)) & 3u]; k++; bit += bd; o += od; }
+      while (run - k >= 4) {
+        const int byte = watson ? bit >> 2 : (bit - 3) >> 2;
+        const uint32_t four = tab[(bits >> (8 * byte)) & 0xffu];
+        memcpy(rev ? out + o - 3 : out + o, &four, 4);
+        k += 4; bit += 4 * bd; o += 4 * od;
+      }
     }
+    for (; k < run; k++, bit += bd, o += od)
+      out[o] = ((flags >> bit) & 1u) ? 'N' : nt[(bits >> (2 * bit)) & 3u];
     pos += run;
   }
 }

@@ -66,3 +66,36 @@ def test_no_cpu_fallback():
 def test_python_package_refuses_without_library(tmp_path):
     with pytest.raises(RuntimeError):
         api.CudaLib(path=str(tmp_path / "missing.so"))
+
+
+def test_argument_errors_mirror_the_reference_aborts():
+    """The reference abort()s on non-positive matrix sizes (dynprog.c:495-498) and on an unknown Endalign_T
+    (5215); the host side of the library (shared with tests/emul) returns an error code instead of solving."""
+    w = api.Workload(200_000, seed=9)
+    em = api.EmulLib()
+    em.init()
+    em.setup(w.make_setup())
+
+    def code(p):
+        res = np.zeros(len(p), dtype=api.RESULT_DT)
+        off = np.zeros(len(p) + 1, dtype=np.int64)
+        return em.lib.emul_solve(p.ctypes.data_as(C.c_void_p), len(p), res.ctypes.data_as(C.c_void_p), None, 0,
+                                 off.ctypes.data_as(C.c_void_p))
+
+    p = w.single_gaps(1)
+    assert code(p) == 0
+    q = p.copy(); q["length1"] = 0
+    assert code(q) == -2                                    # DPC_ERR_ARG
+    q = p.copy(); q["kind"] = 9
+    assert code(q) == -2
+    q = p.copy(); q["extraband"] = -1
+    assert code(q) == -2
+    q = p.copy(); q["chroffset"] = 0; q["chrhigh"] = 10**9; q["chrpos"] = 190_000; q["genomiclength"] = 60_000    # past the registered genome
+    assert code(q) == -2
+    e = w.end_gaps(1); e["endalign"] = 7
+    assert code(e) == -2
+    g = w.genome_gaps(1, finalp_mode=1)                     # finalp needs the MaxEnt hook, none registered here
+    assert code(g) == -5                                    # DPC_ERR_STATE
+    buf = np.frombuffer(bytes([200] * 64), dtype=np.uint8).copy()
+    q = p.copy(); q["seq1"] = buf.ctypes.data; q["length1"] = 20
+    assert code(q) == -3                                    # DPC_ERR_ALPHABET
