@@ -15,7 +15,8 @@
 #include <ctype.h>
 #include <stdlib.h>
 #if defined(__SSE2__) && defined(__x86_64__)
-#include <emmintrin.h>
+#include <immintrin.h>
+#define DPC_X86_SIMD 1
 #endif
 #include <new>
 #include <vector>
@@ -249,7 +250,58 @@ struct Out {
 struct Scratch {
   std::vector<char> qa, ga, qb, gb;
   std::vector<dpc_pair_t> sL, sR, out;
+  unsigned long long cyc_gather, cyc_replay;      /* only maintained with -DDPC_PROFILE_REBUILD */
+  Scratch() : cyc_gather(0), cyc_replay(0) {}
 };
+
+#ifdef DPC_X86_SIMD
+/* Eight aligned columns at a time (the long diagonal runs are where the rebuild spends its time): characters are
+ * read backwards, positions are an arithmetic sequence, records are interleaved with unpacks.  Columns whose
+ * characters differ get '?' here and are fixed by the caller (it knows the case / ambiguity rules).  No column may
+ * be '*' (the caller checks the device's flag).  Returns the number of columns written (a multiple of 8). */
+__attribute__((target("avx2"))) inline int mrun_avx2(dpc_pair_t *dst, const char *qlast, const char *glast, int len,
+                                                     int qpos, int gpos, int step, int idx, bool stream, uint32_t *diffmask) {
+  /* qlast / glast point at the characters of the run's FIRST column; column j reads qlast[-j] */
+  const __m256i rev = _mm256_setr_epi32(7, 6, 5, 4, 3, 2, 1, 0);
+  const __m256i iota = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+  const __m256i vstep = _mm256_set1_epi32(step);
+  __m256i vq = _mm256_sub_epi32(_mm256_set1_epi32(qpos), _mm256_mullo_epi32(iota, vstep));
+  __m256i vg = _mm256_sub_epi32(_mm256_set1_epi32(gpos), _mm256_mullo_epi32(iota, vstep));
+  const __m256i dec = _mm256_slli_epi32(vstep, 3);
+  const __m256i vidx = _mm256_set1_epi32(idx);
+  const __m256i star = _mm256_set1_epi32('*' << 8), qm = _mm256_set1_epi32('?' << 8);
+  int j = 0, w = 0;
+  for (; j + 8 <= len; j += 8, w++) {
+    __m256i q = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i *)(qlast - j - 7)));
+    __m256i g = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i *)(glast - j - 7)));
+    q = _mm256_permutevar8x32_epi32(q, rev);
+    g = _mm256_permutevar8x32_epi32(g, rev);
+    const __m256i eq = _mm256_cmpeq_epi32(q, g);
+    diffmask[w] = ~(uint32_t)_mm256_movemask_ps(_mm256_castsi256_ps(eq)) & 0xffu;
+    const __m256i tail = _mm256_or_si256(_mm256_or_si256(q, _mm256_slli_epi32(g, 16)), _mm256_blendv_epi8(qm, star, eq));
+    const __m256i ab_lo = _mm256_unpacklo_epi32(vq, vg), ab_hi = _mm256_unpackhi_epi32(vq, vg);
+    const __m256i cd_lo = _mm256_unpacklo_epi32(vidx, tail), cd_hi = _mm256_unpackhi_epi32(vidx, tail);
+    const __m256i r04 = _mm256_unpacklo_epi64(ab_lo, cd_lo), r15 = _mm256_unpackhi_epi64(ab_lo, cd_lo);
+    const __m256i r26 = _mm256_unpacklo_epi64(ab_hi, cd_hi), r37 = _mm256_unpackhi_epi64(ab_hi, cd_hi);
+    __m128i *o = (__m128i *)(dst + j);
+    if (stream) {
+      _mm_stream_si128(o + 0, _mm256_castsi256_si128(r04)); _mm_stream_si128(o + 1, _mm256_castsi256_si128(r15));
+      _mm_stream_si128(o + 2, _mm256_castsi256_si128(r26)); _mm_stream_si128(o + 3, _mm256_castsi256_si128(r37));
+      _mm_stream_si128(o + 4, _mm256_extracti128_si256(r04, 1)); _mm_stream_si128(o + 5, _mm256_extracti128_si256(r15, 1));
+      _mm_stream_si128(o + 6, _mm256_extracti128_si256(r26, 1)); _mm_stream_si128(o + 7, _mm256_extracti128_si256(r37, 1));
+    } else {
+      _mm_storeu_si128(o + 0, _mm256_castsi256_si128(r04)); _mm_storeu_si128(o + 1, _mm256_castsi256_si128(r15));
+      _mm_storeu_si128(o + 2, _mm256_castsi256_si128(r26)); _mm_storeu_si128(o + 3, _mm256_castsi256_si128(r37));
+      _mm_storeu_si128(o + 4, _mm256_extracti128_si256(r04, 1)); _mm_storeu_si128(o + 5, _mm256_extracti128_si256(r15, 1));
+      _mm_storeu_si128(o + 6, _mm256_extracti128_si256(r26, 1)); _mm_storeu_si128(o + 7, _mm256_extracti128_si256(r37, 1));
+    }
+    vq = _mm256_sub_epi32(vq, dec);
+    vg = _mm256_sub_epi32(vg, dec);
+  }
+  return j;
+}
+inline bool have_avx2() { static const bool h = __builtin_cpu_supports("avx2"); return h; }
+#endif
 
 struct Batch {
   std::vector<HostProb> probs;
@@ -489,7 +541,7 @@ struct Batch {
   /* One matrix: replays the ops from (r,c).  qch / gch are in matrix order. */
   template <bool REV, bool GROWS>
   static void replay_t(Out &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
-                       int q0, int g0, int idx) {
+                       int q0, int g0, int idx, bool nostar) {
     const int step = REV ? -1 : 1;
     const Globals &g = G();
     for (int i = 0; i < nops; i++) {
@@ -497,7 +549,30 @@ struct Batch {
       if (op == DPC_OP_M) {
         int qi = (GROWS ? c : r) - 1, gi = (GROWS ? r : c) - 1;
         int qpos = q0 + step * qi, gpos = g0 + step * gi;
-        for (int j = 0; j < len; j++, qi--, gi--, qpos -= step, gpos -= step) {
+        int j = 0;
+#ifdef DPC_X86_SIMD
+        if (!GROWS && nostar && len >= 8 && have_avx2()) {
+          /* the bulk of the run eight columns at a time; differing columns are patched with the exact rule */
+          uint32_t diff[512];
+          dpc_pair_t *base = st.p + st.n;
+          const bool stream = st.stream && (((uintptr_t)base) & 15) == 0;
+          const int done = mrun_avx2(base, qch + qi, gch + gi, len > 4096 ? 4096 : len, qpos, gpos, step, idx, stream, diff);
+          for (int w = 0; w < done / 8; w++)
+            for (uint32_t mask = diff[w]; mask; mask &= mask - 1) {
+              const int jj = 8 * w + __builtin_ctz(mask);
+              const char c1 = qch[qi - jj], c2 = gch[gi - jj];
+              char comp = '*';
+              if ((char)dpc_query_uc(c1) != c2) comp = g.CONS[c1 & 127][c2 & 127] ? ':' : ' ';
+              if (stream) {        /* the record went around the cache: rewrite it whole */
+                Out one; one.p = base + jj; one.n = 0; one.stream = true;
+                one.push(qpos - step * jj, gpos - step * jj, c1, comp, c2, idx, 0);
+              } else base[jj].comp = comp;
+            }
+          st.n += done;
+          j = done; qi -= done; gi -= done; qpos -= step * done; gpos -= step * done;
+        }
+#endif
+        for (; j < len; j++, qi--, gi--, qpos -= step, gpos -= step) {
           const char c1 = qch[qi], c2 = gch[gi];
           if (!GROWS && c2 == '*') continue;                          /* 2644 */
           char comp = '*';
@@ -531,13 +606,13 @@ struct Batch {
     }
   }
   static void replay(Out &st, const uint16_t *ops, int nops, int r, int c, const char *qch, const char *gch,
-                     int q0, int g0, bool revp, bool genome_rows, int idx) {
+                     int q0, int g0, bool revp, bool genome_rows, int idx, bool nostar = false) {
     if (revp) {
-      if (genome_rows) replay_t<true, true>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
-      else replay_t<true, false>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
+      if (genome_rows) replay_t<true, true>(st, ops, nops, r, c, qch, gch, q0, g0, idx, nostar);
+      else replay_t<true, false>(st, ops, nops, r, c, qch, gch, q0, g0, idx, nostar);
     } else {
-      if (genome_rows) replay_t<false, true>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
-      else replay_t<false, false>(st, ops, nops, r, c, qch, gch, q0, g0, idx);
+      if (genome_rows) replay_t<false, true>(st, ops, nops, r, c, qch, gch, q0, g0, idx, nostar);
+      else replay_t<false, false>(st, ops, nops, r, c, qch, gch, q0, g0, idx, nostar);
     }
   }
 
@@ -583,12 +658,22 @@ struct Batch {
     const uint32_t *blocks = G().setup.genome_blocks;
     const char *q = (const char *)&pool[h.q0];
     Out out; out.p = dst; out.n = 0; out.stream = stream_dst;
+    const bool nostar = !(dr.status & DPC_ST_STAR);
     switch (p.kind) {
     case DPC_SINGLE_GAP: {
       char *ga = fit(s.ga, h.L2);
+#ifdef DPC_PROFILE_REBUILD
+      unsigned long long t0 = __rdtsc();
+#endif
       gather_genome(p, blocks, p.offset2, h.L2, false, ga);
+#ifdef DPC_PROFILE_REBUILD
+      unsigned long long t1 = __rdtsc();
+#endif
       /* List_reverse of the pushed list (4571) = push order */
-      replay(out, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex);
+      replay(out, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex, nostar);
+#ifdef DPC_PROFILE_REBUILD
+      s.cyc_gather += t1 - t0; s.cyc_replay += __rdtsc() - t1;
+#endif
       break;
     }
     case DPC_END5_GAP: case DPC_END3_GAP: {
@@ -597,7 +682,7 @@ struct Batch {
       for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
       gather_genome(p, blocks, p.offset2, h.L2, five, ga);
       Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0;
-      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex);
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex, nostar);
       if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) break;   /* 5259 */
       int first = 0;                                                   /* 5265-5268 */
       while (first < sL.n && sL.p[first].comp == '-') first++;
@@ -612,8 +697,8 @@ struct Batch {
       gather_genome(p, blocks, p.offset2, L2L, false, ga);
       gather_genome(p, blocks, p.offset2R, L2R, true, gb);
       Out sR, sL; sR.p = fit(s.sR, L1 + L2R + 2); sR.n = 0; sL.p = fit(s.sL, L1 + L2L + 2); sL.n = 0;
-      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, revoffset1, p.offset2R, true, false, p.dynprogindex);
-      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex);
+      replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, revoffset1, p.offset2R, true, false, p.dynprogindex, nostar);
+      replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex, nostar);
       if (sR.n + sL.n > 0) {                                           /* List_length == 1 -> NULL, 5051 */
         emit(out, sR.p, sR.n, true);
         out.push_gapholder();

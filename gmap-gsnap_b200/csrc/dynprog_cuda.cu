@@ -740,6 +740,13 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
 #endif
   if (err.load()) return err.load();
   if (pair_off) pair_off[n] = nchunks ? chunk_end[(size_t)nchunks - 1].load() : 0;
+#ifdef DPC_PROFILE_REBUILD
+  {
+    unsigned long long cg = 0, cr = 0;
+    for (size_t i = 0; i < c->subs.size(); i++) { cg += c->subs[i]->scratch.cyc_gather; cr += c->subs[i]->scratch.cyc_replay; c->subs[i]->scratch.cyc_gather = c->subs[i]->scratch.cyc_replay = 0; }
+    fprintf(stderr, "rebuild cycles (thread-sum, tsc): gather %.1f M, replay %.1f M\n", cg / 1e6, cr / 1e6);
+  }
+#endif
   if (timing)
     fprintf(stderr, "dpc_solve n=%d chunks=%d x %d threads=%d engines=%d: %.1f ms | thread-sum pack %.1f flush %.1f wait %.1f (finalize %.1f) stall %.1f pairs %.1f ms\n",
             n, nchunks, chunk, T, nengines, (now_s() - t0) * 1e3, t_pack / 1e6, t_flush / 1e6, t_wait / 1e6, t_fin / 1e6, t_stall / 1e6, t_pairs / 1e6);
