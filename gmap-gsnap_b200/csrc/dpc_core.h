@@ -754,8 +754,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       }
       DPC_SYNC();
       EndSearch es; es.mode = 0; es.eb = 0; es.best.score = 0; es.best.key = 0;
-      fill(m0, st, score, es, ln);
-      fill(m1, st, score, es, ln);
+      fill.pair(m0, m1, st, score, es, ln);
       Bridge br;
       int ok;
       if (!cdna) {
@@ -797,6 +796,10 @@ struct GenericFill {
   enum { fillmode = 1 };
   DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
     dpc_fill_generic(m, st, score, es, ln);
+  }
+  DPC_HDM void pair(const Mat &mA, const Mat &mB, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
+    dpc_fill_generic(mA, st, score, es, ln);
+    dpc_fill_generic(mB, st, score, es, ln);
   }
   DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {
     return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);

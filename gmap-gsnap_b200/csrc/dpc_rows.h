@@ -39,108 +39,145 @@
  * direction bits they produce are never read: the traceback only follows real-valued chains and the bridges only
  * read in-band cells), so they are not kept bit-identical to the reference's NEG arithmetic; what IS kept exact is
  * everything a valid cell can read: row 0, column 0 (set when a diagonal passes c == 0) and NEG above the band. */
-template <int CPL, bool LATE, bool EP, bool NBAND, bool QROWS>
-DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
-  using namespace vec;
-  const int L1 = m.L1, L2 = m.L2, lband = m.lband, W = m.W;
-  const int open = m.open, extend = m.extend;
-  const VI lane = lane_index();
-  VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL];
-  VM kok[CPL], ebok[CPL];
-  VI bs = splat(es.best.score), bk = splat(es.best.key);
+template <int CPL> struct RowState {
+  vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL];
+  vec::VM kok[CPL], ebok[CPL];
+  vec::VI bs, bk;
+};
 
+template <int CPL, bool QROWS>
+DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) {
+  using namespace vec;
+  const int L2 = m.L2, lband = m.lband, W = m.W, open = m.open, extend = m.extend;
+  const VI lane = lane_index();
+  s.bs = splat(es.best.score); s.bk = splat(es.best.key);
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
     const VI k = lane * CPL + j;
-    kok[j] = k < W;
-    kE[j] = k * extend;
-    ebok[j] = vand(k >= lband - es.eb, k <= lband + es.eb);
+    s.kok[j] = k < W;
+    s.kE[j] = k * extend;
+    s.ebok[j] = vand(k >= lband - es.eb, k <= lband + es.eb);
     const VI c0 = k - lband;                              /* column of this diagonal in row 0 */
-    cm1[j] = vsel(kok[j], c0 - 1, 1 << 24);               /* c - 1 = r + cm1; diagonals past the band never become valid */
+    s.cm1[j] = vsel(s.kok[j], c0 - 1, 1 << 24);           /* c - 1 = r + cm1; diagonals past the band never become valid */
     /* row 0 (1460-1475): (0,0) nogap 0; (0,c) gap1 = open + c*extend for 1 <= c <= min(rband, L2) */
-    Np[j] = vsel(c0 == 0, 0, DPC_NEG);
-    G1p[j] = vsel(vand(vand(c0 >= 1, c0 <= L2), kok[j]), open + c0 * extend, DPC_NEG);
-    G2p[j] = splat(DPC_NEG);
+    s.Np[j] = vsel(c0 == 0, 0, DPC_NEG);
+    s.G1p[j] = vsel(vand(vand(c0 >= 1, c0 <= L2), s.kok[j]), open + c0 * extend, DPC_NEG);
+    s.G2p[j] = splat(DPC_NEG);
     /* column characters of row 1 (a window that slides one column per row, so it is filled for every
        diagonal, in or out of the band) */
     const VI ch = load_u8(m.colch, vsel(vlt_u(c0, L2), c0, 0));
-    sh[j] = QROWS ? (ch << 2) : ((ch & 127) << 3);
+    s.sh[j] = QROWS ? (ch << 2) : ((ch & 127) << 3);
   }
+}
 
-  for (int r = 1; r <= L1; r++) {
-    const int prof = QROWS ? (int)m.prof[m.prof_base + r * m.prof_step] : 0;
-    const int rowg = QROWS ? 0 : (int)m.rowch[r - 1];
-    const int col0 = open + r * extend;                   /* gap2 of (r,0), 1477-1488 */
-    /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */
-    const VI upN = shfl_down1(Np[0], DPC_NEG), upG2 = shfl_down1(G2p[0], DPC_NEG);
-    VI Nn[CPL], G2n[CPL], a2[CPL], li[CPL], x[CPL];
-    VM p1[CPL], p2[CPL], pv[CPL], inval[CPL];
+/* one row of one matrix */
+template <int CPL, bool LATE, bool EP, bool NBAND, bool QROWS>
+DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, const int r) {
+  using namespace vec;
+  const int L1 = m.L1, L2 = m.L2, lband = m.lband, W = m.W, open = m.open, extend = m.extend;
+  const VI lane = lane_index();
+  const int prof = QROWS ? (int)m.prof[m.prof_base + r * m.prof_step] : 0;
+  const int rowg = QROWS ? 0 : (int)m.rowch[r - 1];
+  const int col0 = open + r * extend;                   /* gap2 of (r,0), 1477-1488 */
+  (void)L1;
+  /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */
+  const VI upN = shfl_down1(s.Np[0], DPC_NEG), upG2 = shfl_down1(s.G2p[0], DPC_NEG);
+  VI Nn[CPL], G2n[CPL], a2[CPL], li[CPL], x[CPL];
+  VM p1[CPL], p2[CPL], pv[CPL], inval[CPL];
 #pragma unroll
-    for (int j = 0; j < CPL; j++) {
-      x[j] = cm1[j] + r;
-      inval[j] = vnot(vlt_u(x[j], L2));
-      /* nogap, 1545-1561 */
-      p1[j] = LATE ? (G1p[j] >= Np[j]) : (G1p[j] > Np[j]);
-      const VI mx = vmax(Np[j], G1p[j]);
-      p2[j] = LATE ? (G2p[j] >= mx) : (G2p[j] > mx);
-      if (QROWS) Nn[j] = vmax(mx, G2p[j]) + ((prof >> sh[j]) & 15) - 8;
-      else Nn[j] = vmax(mx, G2p[j]) + load_i8(score, sh[j] + rowg);
-      /* gap2, 1532-1542 */
-      const VI Nu = j + 1 < CPL ? Np[j + 1 < CPL ? j + 1 : j] : upN;
-      const VI G2u = j + 1 < CPL ? G2p[j + 1 < CPL ? j + 1 : j] : upG2;
-      const VI a = Nu + open;
-      pv[j] = LATE ? (G2u >= a) : (G2u > a);
-      G2n[j] = vmax(a, G2u) + extend;
-      /* gap1 feed: nogap + open - k*extend, running maximum inside the lane */
-      a2[j] = Nn[j] + open;
-      const VI s = a2[j] - kE[j];
-      li[j] = j == 0 ? s : vmax(li[j > 0 ? j - 1 : 0], s);
-    }
-    /* exclusive prefix maximum of the lane totals (1519-1529 unrolled along the row) */
-    VI t = shfl_up(li[CPL - 1], 1, DPC_NEG + extend);
-    t = vmax(t, shfl_up_keep(t, 1));
-    t = vmax(t, shfl_up_keep(t, 2));
-    t = vmax(t, shfl_up_keep(t, 4));
-    t = vmax(t, shfl_up_keep(t, 8));
-    t = vmax(t, shfl_up_keep(t, 16));
-    /* next row's column characters: every diagonal moves one column to the right */
-    {
-      /* column index entering at the last diagonal: r + 32*CPL - lband - 1 >= 1 because lband < W <= 32*CPL;
-         past the matrix the staged sentinel colch[L2] is read (those diagonals are out of the matrix anyway) */
-      const int gi = r + 32 * CPL - lband - 1;
-      const int chn = (int)m.colch[gi < L2 ? gi : L2];
-      const VI nxt = shfl_down1(sh[0], QROWS ? (chn << 2) : ((chn & 127) << 3));
-#pragma unroll
-      for (int j = 0; j + 1 < CPL; j++) sh[j] = sh[j + 1];
-      sh[CPL - 1] = nxt;
-    }
-#pragma unroll
-    for (int j = 0; j < CPL; j++) {
-      const VI G1n = (j == 0 ? t : vmax(t, li[j > 0 ? j - 1 : 0])) + kE[j];
-      const VM h = LATE ? (G1n >= a2[j]) : (G1n > a2[j]);
-      /* directions: four ballots, one 16-byte store */
-      const uint32_t b1 = vballot(p2[j]), b0 = vballot(p1[j]) & ~b1, b2 = vballot(h), b3 = vballot(pv[j]);
-      store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
-      if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), kok[j]);
-      if (EP) keep_better(bs, bk, Nn[j], x[j] + (r * (L2 + 1) + 1), vand(vnot(inval[j]), ebok[j]), LATE);
-      /* what the next row sees on this diagonal: the cell, column 0, or NEG */
-      Np[j] = vsel(inval[j], DPC_NEG, Nn[j]);
-      G1p[j] = G1n;
-      G2p[j] = vsel(x[j] == -1, col0, vsel(inval[j], DPC_NEG, G2n[j]));
-    }
+  for (int j = 0; j < CPL; j++) {
+    x[j] = s.cm1[j] + r;
+    inval[j] = vnot(vlt_u(x[j], L2));
+    /* nogap, 1545-1561 */
+    p1[j] = LATE ? (s.G1p[j] >= s.Np[j]) : (s.G1p[j] > s.Np[j]);
+    const VI mx = vmax(s.Np[j], s.G1p[j]);
+    p2[j] = LATE ? (s.G2p[j] >= mx) : (s.G2p[j] > mx);
+    if (QROWS) Nn[j] = vmax(mx, s.G2p[j]) + ((prof >> s.sh[j]) & 15) - 8;
+    else Nn[j] = vmax(mx, s.G2p[j]) + load_i8(score, s.sh[j] + rowg);
+    /* gap2, 1532-1542 */
+    const VI Nu = j + 1 < CPL ? s.Np[j + 1 < CPL ? j + 1 : j] : upN;
+    const VI G2u = j + 1 < CPL ? s.G2p[j + 1 < CPL ? j + 1 : j] : upG2;
+    const VI a = Nu + open;
+    pv[j] = LATE ? (G2u >= a) : (G2u > a);
+    G2n[j] = vmax(a, G2u) + extend;
+    /* gap1 feed: nogap + open - k*extend, running maximum inside the lane */
+    a2[j] = Nn[j] + open;
+    const VI sv = a2[j] - s.kE[j];
+    li[j] = j == 0 ? sv : vmax(li[j > 0 ? j - 1 : 0], sv);
   }
+  /* exclusive prefix maximum of the lane totals (1519-1529 unrolled along the row) */
+  VI t = shfl_up(li[CPL - 1], 1, DPC_NEG + extend);
+  t = vmax(t, shfl_up_keep(t, 1));
+  t = vmax(t, shfl_up_keep(t, 2));
+  t = vmax(t, shfl_up_keep(t, 4));
+  t = vmax(t, shfl_up_keep(t, 8));
+  t = vmax(t, shfl_up_keep(t, 16));
+  /* next row's column characters: every diagonal moves one column to the right */
+  {
+    /* column index entering at the last diagonal: r + 32*CPL - lband - 1 >= 1 because lband < W <= 32*CPL;
+       past the matrix the staged sentinel colch[L2] is read (those diagonals are out of the matrix anyway) */
+    const int gi = r + 32 * CPL - lband - 1;
+    const int chn = (int)m.colch[gi < L2 ? gi : L2];
+    const VI nxt = shfl_down1(s.sh[0], QROWS ? (chn << 2) : ((chn & 127) << 3));
+#pragma unroll
+    for (int j = 0; j + 1 < CPL; j++) s.sh[j] = s.sh[j + 1];
+    s.sh[CPL - 1] = nxt;
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; j++) {
+    const VI G1n = (j == 0 ? t : vmax(t, li[j > 0 ? j - 1 : 0])) + s.kE[j];
+    const VM h = LATE ? (G1n >= a2[j]) : (G1n > a2[j]);
+    /* directions: four ballots, one 16-byte store */
+    const uint32_t b1 = vballot(p2[j]), b0 = vballot(p1[j]) & ~b1, b2 = vballot(h), b3 = vballot(pv[j]);
+    store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
+    if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), s.kok[j]);
+    if (EP) keep_better(s.bs, s.bk, Nn[j], x[j] + (r * (L2 + 1) + 1), vand(vnot(inval[j]), s.ebok[j]), LATE);
+    /* what the next row sees on this diagonal: the cell, column 0, or NEG */
+    s.Np[j] = vsel(inval[j], DPC_NEG, Nn[j]);
+    s.G1p[j] = G1n;
+    s.G2p[j] = vsel(x[j] == -1, col0, vsel(inval[j], DPC_NEG, G2n[j]));
+  }
+}
+
+template <int CPL, bool LATE>
+DPC_VFN void dpc_rows_finish(RowState<CPL> &s, const Mat &m, EndSearch &es) {
+  using namespace vec;
+  const int L1 = m.L1, L2 = m.L2;
   if (es.mode == 2 || es.mode == 3) {
     /* last row: best of the band (2293-2355) or the corner (4541) */
 #pragma unroll
     for (int j = 0; j < CPL; j++) {
-      const VI xl = cm1[j] + L1;
+      const VI xl = s.cm1[j] + L1;
       VM cand = vlt_u(xl, L2);
       if (es.mode == 3) cand = vand(cand, xl == L2 - 1);
-      keep_better(bs, bk, Np[j], xl + (L1 * (L2 + 1) + 1), cand, LATE);
+      keep_better(s.bs, s.bk, s.Np[j], xl + (L1 * (L2 + 1) + 1), cand, LATE);
     }
   }
-  reduce_better(bs, bk, LATE, &es.best.score, &es.best.key);
-  sync();
+  reduce_better(s.bs, s.bk, LATE, &es.best.score, &es.best.key);
+}
+
+template <int CPL, bool LATE, bool EP, bool NBAND, bool QROWS>
+DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
+  RowState<CPL> s;
+  dpc_rows_init<CPL, QROWS>(s, m, es);
+  for (int r = 1; r <= m.L1; r++) dpc_rows_step<CPL, LATE, EP, NBAND, QROWS>(s, m, score, r);
+  dpc_rows_finish<CPL, LATE>(s, m, es);
+  vec::sync();
+}
+
+/* The two matrices of a genome / cDNA gap have the same rows: sweeping them in ONE loop gives the scheduler two
+ * independent dependency chains per iteration (the fill is latency-bound at the 16 warps per SM this kernel has).
+ * mA runs with LATE, mB with !LATE (4965-4987, 4683-4694). */
+template <int CPL, bool LATE, bool QROWS>
+DPC_VFN void dpc_fill_rows2(const Mat &mA, const Mat &mB, const int8_t *score, EndSearch &es) {
+  RowState<CPL> a, b;
+  dpc_rows_init<CPL, QROWS>(a, mA, es);
+  dpc_rows_init<CPL, QROWS>(b, mB, es);
+  for (int r = 1; r <= mA.L1; r++) {
+    dpc_rows_step<CPL, LATE, false, true, QROWS>(a, mA, score, r);
+    dpc_rows_step<CPL, !LATE, false, true, QROWS>(b, mB, score, r);
+  }
+  vec::sync();
 }
 
 /* Lane-parallel traceback walk over bit-plane directions: 32 cells of the current diagonal (or of the current
@@ -233,6 +270,22 @@ struct RowFill {
       else if (m.cpl == 2) go<2, false>(m, score, es);
       else go<4, false>(m, score, es);
     }
+  }
+  /* both matrices of a genome / cDNA gap (mA.late == !mB.late, same rows) */
+  DPC_HDM void pair(const Mat &mA, const Mat &mB, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
+    if (mA.planes && mB.planes && mA.cpl == mB.cpl && mA.cpl <= 2 && mA.L1 == mB.L1) {
+      const bool q = mA.query_rows != 0;
+      if (mA.cpl == 1) {
+        if (mA.late) { if (q) dpc_fill_rows2<1, true, true>(mA, mB, score, es); else dpc_fill_rows2<1, true, false>(mA, mB, score, es); }
+        else { if (q) dpc_fill_rows2<1, false, true>(mA, mB, score, es); else dpc_fill_rows2<1, false, false>(mA, mB, score, es); }
+      } else {
+        if (mA.late) { if (q) dpc_fill_rows2<2, true, true>(mA, mB, score, es); else dpc_fill_rows2<2, true, false>(mA, mB, score, es); }
+        else { if (q) dpc_fill_rows2<2, false, true>(mA, mB, score, es); else dpc_fill_rows2<2, false, false>(mA, mB, score, es); }
+      }
+      return;
+    }
+    (*this)(mA, st, score, es, ln);
+    (*this)(mB, st, score, es, ln);
   }
   DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {
     if (!m.planes) return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);
