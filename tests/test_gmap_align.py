@@ -43,3 +43,81 @@ def test_offloaded_build_reproduces_align_test():
     r = run("gmap_cuda")
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == golden()
+
+
+def synthetic_case(tmp_path, seed, n_transcripts=24, genome_len=150_000):
+    """A random genomic segment and spliced, mutated transcripts of it (exons 80-400 bp, GT..AG introns 60-3000 bp,
+    substitutions, small indels, both strands): FASTA files for `gmap -g`."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    nt = np.array(list("ACGT"))
+    genome = nt[rng.integers(0, 4, genome_len)]
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    records = []
+    for t in range(n_transcripts):
+        pos = int(rng.integers(1000, genome_len - 40_000))
+        exons = []
+        for e in range(int(rng.integers(3, 9))):
+            elen = int(rng.integers(80, 400))
+            exons.append((pos, pos + elen))
+            ilen = int(rng.integers(60, 3000))
+            # canonical GT..AG (mostly), sometimes GC..AG or none
+            kind = rng.integers(0, 10)
+            if kind < 8:
+                genome[pos + elen:pos + elen + 2] = list("GT"); genome[pos + elen + ilen - 2:pos + elen + ilen] = list("AG")
+            elif kind == 8:
+                genome[pos + elen:pos + elen + 2] = list("GC"); genome[pos + elen + ilen - 2:pos + elen + ilen] = list("AG")
+            pos += elen + ilen
+        records.append(exons)
+    seqs = []
+    for t, exons in enumerate(records):
+        s = "".join("".join(genome[a:b]) for a, b in exons)
+        out = []
+        for ch in s:                                   # 1 % substitutions, 0.3 % deletions, 0.3 % insertions
+            u = rng.random()
+            if u < 0.003:
+                continue
+            if u < 0.006:
+                out.append("ACGT"[rng.integers(0, 4)])
+            if 0.006 <= u < 0.016:
+                ch = "ACGT"[("ACGT".index(ch) + 1 + rng.integers(0, 3)) % 4]
+            out.append(ch)
+        s = "".join(out)
+        if t % 2:
+            s = "".join(comp[c] for c in reversed(s))
+        if t % 5 == 0:
+            s = "ACGTTGCA" * 3 + s + "TTGACCAG" * 2           # unalignable ends
+        seqs.append(s)
+    gfile, qfile = tmp_path / "genome.fa", tmp_path / "transcripts.fa"
+    g = "".join(genome)
+    gfile.write_text(">seg\n" + "\n".join(g[i:i + 60] for i in range(0, len(g), 60)) + "\n")
+    qfile.write_text("".join(">t%d\n%s\n" % (i, "\n".join(s[j:j + 60] for j in range(0, len(s), 60))) for i, s in enumerate(seqs)))
+    return str(gfile), str(qfile)
+
+
+def run_files(binary, gfile, qfile):
+    exe = os.path.join(REFDIR, binary)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/%s not built (oracle/build_gmap.sh needs /root/reference)" % binary)
+    return subprocess.run([exe, "-A", "-g", gfile, qfile], capture_output=True, text=True, timeout=900)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2])
+def test_synthetic_transcripts_identical_to_reference_gmap(tmp_path, seed):
+    """Whole-program differential test: every Dynprog_* call stage 3 makes for spliced, mutated transcripts
+    (single gaps, genome gaps incl. finalp with the real MaxEnt hook, cDNA gaps, end gaps) goes to the GPU in
+    gmap_cuda; the alignments must be byte-identical to the unmodified reference binary's."""
+    gfile, qfile = synthetic_case(tmp_path, seed)
+    ref = run_files("gmap_ref", gfile, qfile)
+    got = run_files("gmap_cuda", gfile, qfile)
+    assert ref.returncode == 0 and got.returncode == 0, got.stderr[-2000:]
+    assert ref.stdout.count(">t") >= 20 and "Alignments:" in ref.stdout
+    assert got.stdout == ref.stdout
+
+
+def test_synthetic_case_runs_on_reference_gmap(tmp_path):
+    gfile, qfile = synthetic_case(tmp_path, 1, n_transcripts=4)
+    ref = run_files("gmap_ref", gfile, qfile)
+    assert ref.returncode == 0
+    assert ref.stdout.count("Alignments:") == 4
