@@ -95,11 +95,11 @@ def synthetic_case(tmp_path, seed, n_transcripts=24, genome_len=150_000):
     return str(gfile), str(qfile)
 
 
-def run_files(binary, gfile, qfile):
+def run_files(binary, gfile, qfile, extra=()):
     exe = os.path.join(REFDIR, binary)
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/%s not built (oracle/build_gmap.sh needs /root/reference)" % binary)
-    return subprocess.run([exe, "-A", "-g", gfile, qfile], capture_output=True, text=True, timeout=900)
+    return subprocess.run([exe, "-A", *extra, "-g", gfile, qfile], capture_output=True, text=True, timeout=900)
 
 
 @pytest.mark.gpu
@@ -121,3 +121,14 @@ def test_synthetic_case_runs_on_reference_gmap(tmp_path):
     ref = run_files("gmap_ref", gfile, qfile)
     assert ref.returncode == 0
     assert ref.stdout.count("Alignments:") == 4
+
+
+@pytest.mark.gpu
+def test_worker_threads_each_with_their_own_context(tmp_path):
+    """gmap -t 4: four worker threads, each with its own thread-local dpc_ctx_t (like the per-thread Dynprog_T of
+    gmap.c:2270), ordered output: identical to the single-threaded reference."""
+    gfile, qfile = synthetic_case(tmp_path, 3)
+    ref = run_files("gmap_ref", gfile, qfile)
+    got = run_files("gmap_cuda", gfile, qfile, extra=("-t", "4", "-O"))
+    assert ref.returncode == 0 and got.returncode == 0, got.stderr[-2000:]
+    assert got.stdout == ref.stdout
