@@ -88,18 +88,20 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
   for (int j = 0; j < CPL; j++) {
     x[j] = s.cm1[j] + r;
     inval[j] = vnot(vlt_u(x[j], L2));
-    /* nogap, 1545-1561 */
-    p1[j] = LATE ? (s.G1p[j] >= s.Np[j]) : (s.G1p[j] > s.Np[j]);
-    const VI mx = vmax(s.Np[j], s.G1p[j]);
-    p2[j] = LATE ? (s.G2p[j] >= mx) : (s.G2p[j] > mx);
-    if (QROWS) Nn[j] = vmax(mx, s.G2p[j]) + ((prof >> s.sh[j]) & 15) - 8;
-    else Nn[j] = vmax(mx, s.G2p[j]) + load_i8(score, s.sh[j] + rowg);
+    /* nogap, 1545-1561.  x > y is !(y >= x): each max also yields the tie-break predicate (vmax_ge) */
+    VM ge;
+    VI mx, best;
+    if (LATE) { mx = vmax_ge(s.G1p[j], s.Np[j], ge); p1[j] = ge; } else { mx = vmax_ge(s.Np[j], s.G1p[j], ge); p1[j] = vnot(ge); }
+    if (LATE) { best = vmax_ge(s.G2p[j], mx, ge); p2[j] = ge; } else { best = vmax_ge(mx, s.G2p[j], ge); p2[j] = vnot(ge); }
+    if (QROWS) Nn[j] = best + ((prof >> s.sh[j]) & 15) - 8;
+    else Nn[j] = best + load_i8(score, s.sh[j] + rowg);
     /* gap2, 1532-1542 */
     const VI Nu = j + 1 < CPL ? s.Np[j + 1 < CPL ? j + 1 : j] : upN;
     const VI G2u = j + 1 < CPL ? s.G2p[j + 1 < CPL ? j + 1 : j] : upG2;
     const VI a = Nu + open;
-    pv[j] = LATE ? (G2u >= a) : (G2u > a);
-    G2n[j] = vmax(a, G2u) + extend;
+    VI g2m;
+    if (LATE) { g2m = vmax_ge(G2u, a, ge); pv[j] = ge; } else { g2m = vmax_ge(a, G2u, ge); pv[j] = vnot(ge); }
+    G2n[j] = g2m + extend;
     /* gap1 feed: nogap + open - k*extend, running maximum inside the lane */
     a2[j] = Nn[j] + open;
     const VI sv = a2[j] - s.kE[j];
