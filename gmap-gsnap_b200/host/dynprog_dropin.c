@@ -16,13 +16,27 @@
  * dynprog.c) because Dynprog_init/_setup must still run for the solvers this library does not replace
  * (Dynprog_end5_known, Dynprog_microexon_*, ...).  The five solvers below never call their _cpu twins.
  *
- * Each call here is "add 1 + flush + wait + pairs": correct, and as slow as one kernel launch per gap.  The
- * batched use (a modified stage3.c that collects the gaps of many alignments) goes
- * through the same dpc_add / dpc_flush / dpc_result / dpc_pairs calls with more than one problem per flush.
+ * Batching.  The gaps of ONE alignment depend on each other (peel-back can eat the pairs of the previous fill,
+ * stage3.c:5546), so the unit of parallelism is the alignment.  Instead of rewriting stage3.c's path traversal
+ * as an explicit state machine, every worker thread runs DPC_FIBERS (default 64) copies of the reference's
+ * worker loop (gmap.c:2254 worker_thread) as cooperative fibers, each with its own stack, Pairpool and request
+ * in flight: a fiber that reaches one of the five solvers below ENQUEUES its gap (dpc_add) and yields; when
+ * every fiber of the thread is parked on a gap (or finished) the scheduler flushes the collected batch to the
+ * device, and the fibers resume with their results (dpc_result / dpc_pairs -> Pairpool_push).  stage3.c's
+ * traversal thus fills device batches instead of solving gaps one at a time, with its decision logic untouched.
+ * Two batch contexts alternate per thread (fibers read round k-1's results while they enqueue round k).
+ * gmap.c changes by one call: the pthread_create of its workers becomes Dynprog_cuda_worker_create
+ * (INTEGRATION.md section 3).  Called outside a fiber (single_thread(), DPC_FIBERS=1) a solver is
+ * "add 1 + flush + wait + pairs": correct, and as slow as one kernel launch per gap.
  */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <sys/mman.h>
+#if !defined(__x86_64__)
+#include <ucontext.h>
+#endif
 
 #include "bool.h"
 #include "types.h"
@@ -37,6 +51,7 @@
 #include "splicetrie_build.h"
 #include "dynprog.h"
 #include "maxent_hr.h"
+#include "except.h"
 
 #include "dynprog_cuda.h"
 
@@ -152,6 +167,184 @@ Dynprog_setup (bool novelsplicingp_in,
   }
 }
 
+
+/* ---- fibers: many copies of the reference's worker loop per OS thread ---------------------------------- */
+#define FIBER_STACK_BYTES (8UL << 20)	/* what a default pthread gets; reserved, touched lazily */
+enum { FIBER_RUNNABLE = 0, FIBER_PARKED = 1, FIBER_DONE = 2 };
+
+#if defined(__x86_64__)
+/* dropin_switch(&save_sp, load_sp): push the System V callee-saved registers, swap stacks, pop, return.  No
+   signal-mask system call (swapcontext makes one per switch). */
+__asm__ (".text\n"
+	 ".type dropin_switch,@function\n"
+	 "dropin_switch:\n"
+	 "	pushq %rbp\n	pushq %rbx\n	pushq %r12\n	pushq %r13\n	pushq %r14\n	pushq %r15\n"
+	 "	movq %rsp,(%rdi)\n"
+	 "	movq %rsi,%rsp\n"
+	 "	popq %r15\n	popq %r14\n	popq %r13\n	popq %r12\n	popq %rbx\n	popq %rbp\n"
+	 "	ret\n"
+	 ".size dropin_switch,.-dropin_switch\n");
+extern void dropin_switch (void **save_sp, void *load_sp);
+typedef void *fiber_regs_t;
+#else
+typedef ucontext_t fiber_regs_t;
+#endif
+
+typedef struct dropin_fiber {
+  fiber_regs_t regs;
+  char *stack;
+  int state;
+} dropin_fiber_t;
+
+typedef struct dropin_sched {
+  fiber_regs_t regs;		/* the scheduler's own context */
+  dropin_fiber_t *fibers;
+  int nfibers;
+  dropin_fiber_t *cur;		/* fiber running right now, NULL while the scheduler runs */
+  dpc_ctx_t *ctx[2];		/* ctx[fill] collects this round's gaps, ctx[fill^1] holds last round's results */
+  int fill;
+  int npending;
+  void *(*start_routine) (void *);
+  void *arg;
+  int nexcept;			/* Except_stack_create calls outstanding on this OS thread */
+  long nrounds, nproblems;
+} dropin_sched_t;
+
+static __thread dropin_sched_t *dropin_sched;
+
+static void
+dropin_to_scheduler (dropin_sched_t *s, dropin_fiber_t *f) {
+#if defined(__x86_64__)
+  dropin_switch(&f->regs,s->regs);
+#else
+  swapcontext(&f->regs,&s->regs);
+#endif
+}
+
+static void
+dropin_to_fiber (dropin_sched_t *s, dropin_fiber_t *f) {
+  s->cur = f;
+#if defined(__x86_64__)
+  dropin_switch(&s->regs,f->regs);
+#else
+  swapcontext(&s->regs,&f->regs);
+#endif
+  s->cur = NULL;
+}
+
+static void
+dropin_fiber_main (void) {
+  dropin_sched_t *s = dropin_sched;
+  dropin_fiber_t *f = s->cur;
+  s->start_routine(s->arg);	/* the reference's worker_thread: loops over Inbuffer_get_request until input ends */
+  f->state = FIBER_DONE;
+  dropin_to_scheduler(s,f);
+  abort();			/* a finished fiber is never resumed */
+}
+
+static void
+dropin_fiber_init (dropin_fiber_t *f) {
+  f->stack = (char *) mmap(NULL,FIBER_STACK_BYTES,PROT_READ|PROT_WRITE,MAP_PRIVATE|MAP_ANONYMOUS|MAP_NORESERVE|MAP_STACK,-1,0);
+  if (f->stack == (char *) MAP_FAILED) {
+    fprintf(stderr,"libdynprog_cuda drop-in: cannot reserve a fiber stack\n");
+    exit(9);
+  }
+  mprotect(f->stack,4096,PROT_NONE);	/* guard page */
+  f->state = FIBER_RUNNABLE;
+#if defined(__x86_64__)
+  {
+    void **sp = (void **) (f->stack + FIBER_STACK_BYTES);	/* 16-byte aligned */
+    *--sp = NULL;			/* return address slot of dropin_fiber_main (never used): entry rsp = 8 mod 16 */
+    *--sp = (void *) dropin_fiber_main;	/* popped by the ret of dropin_switch */
+    sp -= 6;				/* rbp rbx r12 r13 r14 r15 */
+    memset(sp,0,6*sizeof(void *));
+    f->regs = (void *) sp;
+  }
+#else
+  getcontext(&f->regs);
+  f->regs.uc_stack.ss_sp = f->stack;
+  f->regs.uc_stack.ss_size = FIBER_STACK_BYTES;
+  f->regs.uc_link = NULL;
+  makecontext(&f->regs,dropin_fiber_main,0);
+#endif
+}
+
+static int dropin_device (void);
+
+static void *
+dropin_scheduler (void *data) {
+  dropin_sched_t *s = (dropin_sched_t *) data;
+  int i, live, rc;
+
+  dropin_sched = s;
+  for (i = 0; i < 2; i++) {
+    if ((s->ctx[i] = dpc_ctx_new(dropin_device())) == NULL) dropin_fatal("dpc_ctx_new",DPC_ERR_CUDA);
+  }
+  for (i = 0; i < s->nfibers; i++) dropin_fiber_init(&s->fibers[i]);
+  do {
+    live = 0;
+    for (i = 0; i < s->nfibers; i++) {
+      dropin_fiber_t *f = &s->fibers[i];
+      if (f->state == FIBER_DONE) continue;
+      f->state = FIBER_RUNNABLE;
+      dropin_to_fiber(s,f);	/* picks up its result of the last round, runs on to its next gap (or to the end) */
+      if (f->state != FIBER_DONE) live++;
+    }
+    /* every live fiber is parked on a gap in ctx[fill]; all results of ctx[fill^1] have been consumed */
+    if (s->npending > 0) {
+      if ((rc = dpc_flush(s->ctx[s->fill])) < 0) dropin_fatal("dpc_flush",rc);
+      if ((rc = dpc_wait(s->ctx[s->fill])) < 0) dropin_fatal("dpc_wait",rc);
+      s->nrounds++; s->nproblems += s->npending;
+    }
+    s->fill ^= 1;
+    if ((rc = dpc_reset(s->ctx[s->fill])) < 0) dropin_fatal("dpc_reset",rc);
+    s->npending = 0;
+  } while (live > 0);
+
+  if (getenv("DPC_FIBER_STATS") != NULL) {
+    fprintf(stderr,"libdynprog_cuda drop-in: %d fibers, %ld device batches, %ld gaps (%.1f per batch)\n",
+	    s->nfibers,s->nrounds,s->nproblems,s->nrounds ? (double) s->nproblems/(double) s->nrounds : 0.0);
+  }
+  for (i = 0; i < s->nfibers; i++) munmap(s->fibers[i].stack,FIBER_STACK_BYTES);
+  dpc_ctx_free(s->ctx[0]); dpc_ctx_free(s->ctx[1]);
+  dropin_sched = NULL;
+  free(s->fibers);
+  free(s);
+  return NULL;
+}
+
+/* Replaces pthread_create for the workers of gmap.c:3920 / gsnap.c: the new OS thread runs `start_routine` (the
+   reference's worker_thread) DPC_FIBERS times as fibers.  DPC_FIBERS=1 gives the plain thread back. */
+int
+Dynprog_cuda_worker_create (pthread_t *thread, const pthread_attr_t *attr, void *(*start_routine) (void *), void *arg) {
+  const char *e = getenv("DPC_FIBERS");
+  int nfibers = e != NULL ? atoi(e) : 64;
+  dropin_sched_t *s;
+
+  if (nfibers <= 1) return pthread_create(thread,attr,start_routine,arg);
+  s = (dropin_sched_t *) calloc(1,sizeof(*s));
+  s->fibers = (dropin_fiber_t *) calloc(nfibers,sizeof(dropin_fiber_t));
+  s->nfibers = nfibers;
+  s->start_routine = start_routine;
+  s->arg = arg;
+  return pthread_create(thread,attr,dropin_scheduler,(void *) s);
+}
+
+/* worker_thread creates and destroys the exception-frame stack of its OS thread (gmap.c:2277, 2313; except.c:46);
+   with several worker loops per thread only the first creates and the last destroys it.  gmap.c is compiled
+   with -DExcept_stack_create=Dynprog_cuda_except_stack_create (and _destroy). */
+void
+Dynprog_cuda_except_stack_create (void) {
+  dropin_sched_t *s = dropin_sched;
+  if (s == NULL || s->nexcept++ == 0) Except_stack_create();
+}
+
+void
+Dynprog_cuda_except_stack_destroy (void) {
+  dropin_sched_t *s = dropin_sched;
+  if (s == NULL || --s->nexcept == 0) Except_stack_destroy();
+}
+
 /* ---- one problem through the library ------------------------------------------------------------ */
 static int
 dropin_device (void) {
@@ -162,21 +355,34 @@ dropin_device (void) {
 static List_T
 dropin_solve (dpc_result_t *r, const dpc_problem_t *p, Pairpool_T pairpool) {
   List_T pairs = NULL;
+  dropin_sched_t *s = dropin_sched;
+  dpc_ctx_t *ctx;
   int rc, ticket, n, i;
 
-  if (dropin_ctx == NULL && (dropin_ctx = dpc_ctx_new(dropin_device())) == NULL) {
-    dropin_fatal("dpc_ctx_new",DPC_ERR_CUDA);
+  if (s != NULL && s->cur != NULL) {
+    /* inside a fiber: enqueue into this round's batch and park until the scheduler has run it on the device */
+    dropin_fiber_t *f = s->cur;
+    ctx = s->ctx[s->fill];
+    if ((ticket = dpc_add(ctx,p)) < 0) dropin_fatal("dpc_add",ticket);
+    s->npending++;
+    f->state = FIBER_PARKED;
+    dropin_to_scheduler(s,f);
+  } else {
+    if (dropin_ctx == NULL && (dropin_ctx = dpc_ctx_new(dropin_device())) == NULL) {
+      dropin_fatal("dpc_ctx_new",DPC_ERR_CUDA);
+    }
+    ctx = dropin_ctx;
+    if ((rc = dpc_reset(ctx)) < 0) dropin_fatal("dpc_reset",rc);
+    if ((ticket = dpc_add(ctx,p)) < 0) dropin_fatal("dpc_add",ticket);
+    if ((rc = dpc_flush(ctx)) < 0) dropin_fatal("dpc_flush",rc);
+    if ((rc = dpc_wait(ctx)) < 0) dropin_fatal("dpc_wait",rc);
   }
-  if ((rc = dpc_reset(dropin_ctx)) < 0) dropin_fatal("dpc_reset",rc);
-  if ((ticket = dpc_add(dropin_ctx,p)) < 0) dropin_fatal("dpc_add",ticket);
-  if ((rc = dpc_flush(dropin_ctx)) < 0) dropin_fatal("dpc_flush",rc);
-  if ((rc = dpc_wait(dropin_ctx)) < 0) dropin_fatal("dpc_wait",rc);
-  if ((rc = dpc_result(dropin_ctx,ticket,r)) < 0) dropin_fatal("dpc_result",rc);
+  if ((rc = dpc_result(ctx,ticket,r)) < 0) dropin_fatal("dpc_result",rc);
   if (r->npairs > dropin_pairs_cap) {
     dropin_pairs_cap = 2*r->npairs + 256;
     dropin_pairs = (dpc_pair_t *) realloc(dropin_pairs,dropin_pairs_cap*sizeof(dpc_pair_t));
   }
-  if ((n = dpc_pairs(dropin_ctx,ticket,dropin_pairs,dropin_pairs_cap)) < 0) dropin_fatal("dpc_pairs",n);
+  if ((n = dpc_pairs(ctx,ticket,dropin_pairs,dropin_pairs_cap)) < 0) dropin_fatal("dpc_pairs",n);
 
   /* dpc_pairs lists the records head first; Pairpool_push prepends (pairpool.c:169-215) */
   for (i = n - 1; i >= 0; i--) {

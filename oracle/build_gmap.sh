@@ -7,7 +7,9 @@
 #   oracle/_ref/gmap_cuda   the same objects, except that the five gap-fill solvers of dynprog.c (and
 #                           Dynprog_init/_setup/_term) are renamed *_cpu with objcopy and replaced by
 #                           gmap-gsnap_b200/host/dynprog_dropin.c on top of libdynprog_cuda.so, and that gmap.c gets
-#                           the ONE added line INTEGRATION.md describes (registering a user segment's genome blocks).
+#                           the two edits INTEGRATION.md describes (registering a user segment's genome blocks;
+#                           worker threads created through Dynprog_cuda_worker_create, which runs DPC_FIBERS copies
+#                           of worker_thread per OS thread so that stage 3's gaps reach the device in batches).
 # It also stages the reference's own align.test inputs and golden output next to the binaries (git-ignored, but
 # they travel to the GPU box) so that tests/test_gpu_gmap.py can run BASELINE config 1 there.
 set -euo pipefail
@@ -35,10 +37,19 @@ $CC "${CFLAGS[@]}" -I"$REPO/include" -Wall -c "$REPO/gmap-gsnap_b200/host/dynpro
 # the one-line change to gmap.c: hand the user segment's blocks to the library
 sed 's|^    Genome_user_setup(genome_blocks);|    Genome_user_setup(genome_blocks);\n    { extern void Dynprog_cuda_register_blocks (UINT4 *blocks, unsigned int nwords); Dynprog_cuda_register_blocks(genome_blocks,((Sequence_fulllength(usersegment) + 31)/32U)*3 + 4); }|' gmap.c > cuda-gmap.c
 grep -q Dynprog_cuda_register_blocks cuda-gmap.c
-$CC "${CFLAGS[@]}" -c cuda-gmap.c -o cuda-gmap.o
+# the second change: workers are created through the drop-in's fiber scheduler
+sed -i 's|pthread_create(&(worker_thread_ids\[i\]),&thread_attr_join,worker_thread,(void \*) NULL);|{ extern int Dynprog_cuda_worker_create (pthread_t *, const pthread_attr_t *, void *(*) (void *), void *); Dynprog_cuda_worker_create(\&(worker_thread_ids[i]),\&thread_attr_join,worker_thread,(void *) NULL); }|' cuda-gmap.c
+grep -q Dynprog_cuda_worker_create cuda-gmap.c
+$CC "${CFLAGS[@]}" -DExcept_stack_create=Dynprog_cuda_except_stack_create -DExcept_stack_destroy=Dynprog_cuda_except_stack_destroy \
+    -c cuda-gmap.c -o cuda-gmap.o
 OBJS=$(ls gmap-*.o | grep -v -e '^gmap-dynprog.o$' -e '^gmap-gmap.o$')
 $CC -O3 -o "$OUT/gmap_cuda" $OBJS cuda-dynprog_cpu.o cuda-dynprog_dropin.o cuda-gmap.o \
     -L"$REPO/gmap-gsnap_b200/csrc" -ldynprog_cuda -Wl,-rpath,'$ORIGIN/../../gmap-gsnap_b200/csrc' -lz -lm -lpthread
+# index-building tools of the reference (for the whole-program bench on a synthetic genome database, BASELINE config 5)
+make -j"$(nproc)" gmapindex >> make.log 2>&1
+(cd ../util && make -s fa_coords gmap_process gmap_build >> ../src/make.log 2>&1)
+mkdir -p "$OUT/bin"
+cp gmapindex ../util/fa_coords ../util/gmap_process ../util/gmap_build "$OUT/bin/"
 mkdir -p "$OUT/align_test"
 cp "$REF/tests/ss.her2" "$REF/tests/ss.chr17test" "$REF/tests/align.test.ok" "$OUT/align_test/"
 # sanity: the unmodified build reproduces the reference's golden output

@@ -9,8 +9,9 @@
  *       donor / antiacceptor: largest p <= pos with seg[p+1..p+2] == "GT" / "CT"
  *       acceptor / antidonor: largest q <= pos with seg[q-2..q-1] == "AG" / "AC"
  *       -1 when there is none; seg = genome[genomicstart, genomicend) or its reverse complement when !plusp.
- *   - the gamma decoders are only reached with a gamma-compressed index; `gmap -g` (the align.test run) never
- *     calls them, so they abort.
+ *   - the gamma decoders (index databases, `gmap -d`) invert write_gamma / Indexdb_write_gammaptrs
+ *     (indexdb.c:1212-1252, 1978-2037); the whole-program bench builds its database with k-mer = base size 12
+ *     like tests/setup1.test.in:12, where every block is a single absolute offset.
  * It reads bases through the same 3-word blocks as genome.c:9325-9362.
  */
 #include <stdio.h>
@@ -37,27 +38,53 @@ Genome_hr_user_setup (UINT4 *ref_blocks_in,
   ref_blocks = ref_blocks_in;
 }
 
-static void
-unavailable (const char *name) {
-  fprintf(stderr,"genome_hr stand-in: %s is not available (oracle build only)\n",name);
-  abort();
+/* Elias-gamma offsets: the inverse of write_gamma / Indexdb_write_gammaptrs (indexdb.c:1212-1252, 1978-2037), used
+   the way Indexdb_offsets_from_gammas uses it (indexdb.c:1395-1416): a block starts with an absolute offset word,
+   followed by blocksize-1 gamma codes of (difference + 1), most significant bit first in 32-bit words; ctr is the
+   number of unread bits left in *ptr (0 = *ptr is the next unread word). */
+static unsigned int
+gamma_bit (unsigned int **ptr, int *ctr) {
+  unsigned int bit;
+  if (*ctr == 0) *ctr = 32;
+  bit = (**ptr >> (*ctr - 1)) & 1U;
+  if (--*ctr == 0) (*ptr)++;
+  return bit;
 }
 
 int
 Genome_read_gamma (unsigned int **ptr, int ctr, unsigned int *cum) {
-  (void) ptr; (void) ctr; (void) cum; unavailable("Genome_read_gamma"); return 0;
+  unsigned int value = 1U;
+  int nzeros = 0;
+  while (gamma_bit(ptr,&ctr) == 0U) nzeros++;
+  while (nzeros-- > 0) value = (value << 1) | gamma_bit(ptr,&ctr);
+  *cum += value - 1U;
+  return ctr;
 }
+
 Positionsptr_T
 Genome_offsetptr_from_gammas (Positionsptr_T *end0, UINT4 *gammaptrs, Positionsptr_T *offsetscomp,
 			      unsigned int offsets_blocksize, Storedoligomer_T oligo) {
-  (void) end0; (void) gammaptrs; (void) offsetscomp; (void) offsets_blocksize; (void) oligo;
-  unavailable("Genome_offsetptr_from_gammas"); return 0;
+  unsigned int block = oligo/offsets_blocksize, rem = oligo % offsets_blocksize, j;
+  unsigned int *ptr = &offsetscomp[gammaptrs[block]];
+  unsigned int cum = *ptr++;
+  Positionsptr_T ptr0;
+  int ctr = 0;
+  for (j = 0; j < rem; j++) ctr = Genome_read_gamma(&ptr,ctr,&cum);
+  ptr0 = cum;
+  if (rem + 1U == offsets_blocksize) {
+    *end0 = offsetscomp[gammaptrs[block+1]];
+  } else {
+    ctr = Genome_read_gamma(&ptr,ctr,&cum);
+    *end0 = cum;
+  }
+  return ptr0;
 }
+
 Positionsptr_T
 Genome_offsetptr_only_from_gammas (UINT4 *gammaptrs, Positionsptr_T *offsetscomp,
 				   unsigned int offsets_blocksize, Storedoligomer_T oligo) {
-  (void) gammaptrs; (void) offsetscomp; (void) offsets_blocksize; (void) oligo;
-  unavailable("Genome_offsetptr_only_from_gammas"); return 0;
+  Positionsptr_T end0;
+  return Genome_offsetptr_from_gammas(&end0,gammaptrs,offsetscomp,offsets_blocksize,oligo);
 }
 
 static char
