@@ -94,6 +94,8 @@ WORKLOADS = {
     "single": "Dynprog_single_gap, 1M synthetic 10-100 bp gap fills, band 30, on 1 B200 per rank (BASELINE configs[1])",
     "genome": "Dynprog_genome_gap, synthetic cDNA/genomic gaps across GT-AG/GC-AG/AT-AC introns 50 bp-20 kb, band 7, 10% long (BASELINE configs[2], finalp off)",
     "end": "Dynprog_end5_gap/end3_gap, synthetic 250-bp read ends, tails 1-40 + 11 peeled, band 3 (BASELINE configs[3])",
+    "gmap": "whole-program GMAP (stage 1-3) on synthetic 2-kb spliced transcripts vs a synthetic genome database, "
+            "gap fills collected from stage 3 into device batches (BASELINE configs[4], bounded sample)",
 }
 
 
@@ -140,6 +142,73 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_gmap_workload(args, rank, world, local_rank):
+    """BASELINE configs[4] on a bounded sample: gmap_ref -t <cores> against gmap_cuda (drop-in solvers, fibers).
+    One step = the whole transcript file through one binary; every rank aligns its own file against its own
+    GPU with cores/world worker threads.  Queries/s; the outputs of the two binaries must be identical."""
+    import filecmp
+    from gmap_gsnap_b200 import gmap_e2e as g
+    if not g.have_binaries():
+        if rank == 0:
+            print(json.dumps({"metric": "gmap_queries_per_s", "unavailable": "oracle/_ref binaries not built (oracle/build_gmap.sh)"}))
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, cores // max(1, world))
+    n = args.problems if args.problems != N_PROBLEMS else 8000
+    case = g.prepare("/tmp/dpc_gmap_case_%d" % rank, args.genome_bases, 4, n, seed=5 + rank)
+    line = {"metric": "gmap_queries_per_s", "unit": "queries/s", "n_gpus": world, "steps": 1, "warmup": 0,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOADS["gmap"], "transcripts_per_rank": n, "transcript_bp": 2000,
+                       "genome_bases": args.genome_bases, "worker_threads_per_rank": threads, "fibers_per_thread": args.fibers}}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dt, out, err = g.run_gmap("gmap_ref", case, cores)
+        line.update({"impl": "reference", "value": n / dt, "ms_per_step": 1e3 * dt,
+                     "cpu_baseline": {"value": n / dt, "unit": "queries/s", "cores": cores, "kind": "reference",
+                                      "sample": "%d transcripts, unmodified gmap -t %d" % (n, cores)},
+                     "e2e": {"value": n / dt, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line), flush=True)
+        return
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    dt, out, err = g.run_gmap("gmap_cuda", case, threads, fibers=args.fibers, device=local_rank)
+    stats = [l for l in err.splitlines() if "device batches" in l]
+    gaps = sum(int(l.split(" device batches, ")[1].split(" gaps")[0]) for l in stats)
+    batches = sum(int(l.split(" fibers, ")[1].split(" device batches")[0]) for l in stats)
+    total_dt, total_n, total_gaps = dt, float(n), float(gaps)
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt, 0, 0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u = torch.tensor([n, gaps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        total_dt, total_n, total_gaps = float(t[0]), float(u[0]), float(u[1])
+    if rank == 0:
+        line.update({"value": total_n / total_dt, "ms_per_step": 1e3 * total_dt, "gap_fills_per_s": total_gaps / total_dt,
+                     "gap_fills": int(total_gaps), "device_batches_rank0": batches, "gpu_launches": batches,
+                     "e2e": {"value": total_n / total_dt, "unit": "queries/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                             "includes": "process start, index load, stage 1-3 on the host, gap fills on the device, output"}})
+        if not args.no_cpu_baseline:
+            rdt, rout, rerr = g.run_gmap("gmap_ref", case, cores)
+            line["cpu_baseline"] = {"value": n / rdt, "unit": "queries/s", "cores": cores, "kind": "reference",
+                                    "sample": "the same %d transcripts of rank 0, unmodified gmap -t %d" % (n, cores)}
+            line["outputs_identical_to_reference"] = bool(filecmp.cmp(rout, out, shallow=False))
+            tdt, tout, terr = g.run_gmap("gmap_ref_timed", case, cores) if os.path.exists(os.path.join(g.REFDIR, "gmap_ref_timed")) else (0, None, "")
+            for l in terr.splitlines():
+                if l.startswith("dynprog_timed:"):
+                    secs = float(l.split(" solver calls, ")[1].split(" thread-seconds")[0])
+                    line["reference_share_of_time_in_the_five_solvers"] = secs / (tdt * cores)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +219,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="single", choices=sorted(WORKLOADS), help="single = the headline config; genome / end = the other hot-path configs")
+    ap.add_argument("--genome-bases", type=int, default=100_000_000, help="gmap workload: size of the synthetic genome database")
+    ap.add_argument("--fibers", type=int, default=16, help="gmap workload: worker loops per worker thread (DPC_FIBERS)")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: load the batch, run the timed kernel steps, print their times, exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
@@ -158,6 +229,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.workload == "gmap":
+        run_gmap_workload(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

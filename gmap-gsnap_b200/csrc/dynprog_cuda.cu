@@ -132,6 +132,15 @@ static int ensure_device(int dev) {
   DeviceState &d = g_dev[dev];
   CK(cudaSetDevice(dev));
   if (d.ready && d.version == g_version) return DPC_OK;
+  if (!d.ready) {
+    /* how a host thread waits in dpc_wait: spin (CUDA's default with few threads), yield, or sleep on an interrupt.
+       Many worker threads that share cores with other work (gmap -t N) are better off sleeping: DPC_SYNC=block. */
+    const char *e = getenv("DPC_SYNC");
+    if (e && !strcmp(e, "block")) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+    else if (e && !strcmp(e, "yield")) cudaSetDeviceFlags(cudaDeviceScheduleYield);
+    else if (e && !strcmp(e, "spin")) cudaSetDeviceFlags(cudaDeviceScheduleSpin);
+    cudaGetLastError();
+  }
   if (d.ready) { cudaFree(d.d_blocks); cudaFree(d.d_tables); d.ready = false; }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));

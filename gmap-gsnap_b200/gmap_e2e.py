@@ -139,10 +139,14 @@ def run_gmap(binary, case, threads, fibers=None, device=None, extra=(), out=None
     env["DPC_FIBER_STATS"] = "1"
     out = out or os.path.join(case["dbdir"], os.path.basename(binary) + ".out")
     cmd = [os.path.join(REFDIR, binary), "-D", case["dbdir"], "-d", case["dbname"], "-t", str(threads), "-O", "-A", *extra, case["queries"]]
+    import resource
+    ru0 = resource.getrusage(resource.RUSAGE_CHILDREN)
     t0 = time.time()
     with open(out, "wb") as f:
         r = subprocess.run(cmd, stdout=f, stderr=subprocess.PIPE, env=env, timeout=timeout)
     dt = time.time() - t0
+    ru1 = resource.getrusage(resource.RUSAGE_CHILDREN)
+    run_gmap.last_cpu = (ru1.ru_utime - ru0.ru_utime, ru1.ru_stime - ru0.ru_stime, ru1.ru_minflt - ru0.ru_minflt)
     if r.returncode != 0:
         raise RuntimeError("%s exited %d\n%s" % (binary, r.returncode, r.stderr.decode()[-3000:]))
     return dt, out, r.stderr.decode()

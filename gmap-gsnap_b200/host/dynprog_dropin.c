@@ -32,6 +32,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <pthread.h>
 #include <sys/mman.h>
 #if !defined(__x86_64__)
@@ -208,9 +209,19 @@ typedef struct dropin_sched {
   void *arg;
   int nexcept;			/* Except_stack_create calls outstanding on this OS thread */
   long nrounds, nproblems;
+  double t_device, t_start;	/* seconds blocked in flush + wait; start of the scheduler (DPC_FIBER_STATS) */
+  double t_add, t_post;		/* seconds in dpc_add; in dpc_result + dpc_pairs + Pairpool_push (DPC_FIBER_STATS) */
+  int stats;
 } dropin_sched_t;
 
 static __thread dropin_sched_t *dropin_sched;
+
+static double
+dropin_now (void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC,&t);
+  return (double) t.tv_sec + 1e-9*(double) t.tv_nsec;
+}
 
 static void
 dropin_to_scheduler (dropin_sched_t *s, dropin_fiber_t *f) {
@@ -275,8 +286,11 @@ static void *
 dropin_scheduler (void *data) {
   dropin_sched_t *s = (dropin_sched_t *) data;
   int i, live, rc;
+  const int stats = getenv("DPC_FIBER_STATS") != NULL;
 
   dropin_sched = s;
+  s->stats = stats;
+  s->t_start = dropin_now();
   for (i = 0; i < 2; i++) {
     if ((s->ctx[i] = dpc_ctx_new(dropin_device())) == NULL) dropin_fatal("dpc_ctx_new",DPC_ERR_CUDA);
   }
@@ -292,18 +306,21 @@ dropin_scheduler (void *data) {
     }
     /* every live fiber is parked on a gap in ctx[fill]; all results of ctx[fill^1] have been consumed */
     if (s->npending > 0) {
+      double t0 = stats ? dropin_now() : 0.0;
       if ((rc = dpc_flush(s->ctx[s->fill])) < 0) dropin_fatal("dpc_flush",rc);
       if ((rc = dpc_wait(s->ctx[s->fill])) < 0) dropin_fatal("dpc_wait",rc);
       s->nrounds++; s->nproblems += s->npending;
+      if (stats) s->t_device += dropin_now() - t0;
     }
     s->fill ^= 1;
     if ((rc = dpc_reset(s->ctx[s->fill])) < 0) dropin_fatal("dpc_reset",rc);
     s->npending = 0;
   } while (live > 0);
 
-  if (getenv("DPC_FIBER_STATS") != NULL) {
-    fprintf(stderr,"libdynprog_cuda drop-in: %d fibers, %ld device batches, %ld gaps (%.1f per batch)\n",
-	    s->nfibers,s->nrounds,s->nproblems,s->nrounds ? (double) s->nproblems/(double) s->nrounds : 0.0);
+  if (stats) {
+    fprintf(stderr,"libdynprog_cuda drop-in: %d fibers, %ld device batches, %ld gaps (%.1f per batch), %.2f s in flush+wait, %.2f s in add, %.2f s in result+pairs+push, of %.2f s\n",
+	    s->nfibers,s->nrounds,s->nproblems,s->nrounds ? (double) s->nproblems/(double) s->nrounds : 0.0,
+	    s->t_device,s->t_add,s->t_post,dropin_now() - s->t_start);
   }
   for (i = 0; i < s->nfibers; i++) munmap(s->fibers[i].stack,FIBER_STACK_BYTES);
   dpc_ctx_free(s->ctx[0]); dpc_ctx_free(s->ctx[1]);
@@ -357,16 +374,20 @@ dropin_solve (dpc_result_t *r, const dpc_problem_t *p, Pairpool_T pairpool) {
   List_T pairs = NULL;
   dropin_sched_t *s = dropin_sched;
   dpc_ctx_t *ctx;
+  double tpost = 0.0;
   int rc, ticket, n, i;
 
   if (s != NULL && s->cur != NULL) {
     /* inside a fiber: enqueue into this round's batch and park until the scheduler has run it on the device */
     dropin_fiber_t *f = s->cur;
+    double t0 = s->stats ? dropin_now() : 0.0;
     ctx = s->ctx[s->fill];
     if ((ticket = dpc_add(ctx,p)) < 0) dropin_fatal("dpc_add",ticket);
     s->npending++;
     f->state = FIBER_PARKED;
+    if (s->stats) s->t_add += dropin_now() - t0;
     dropin_to_scheduler(s,f);
+    if (s->stats) tpost = dropin_now();
   } else {
     if (dropin_ctx == NULL && (dropin_ctx = dpc_ctx_new(dropin_device())) == NULL) {
       dropin_fatal("dpc_ctx_new",DPC_ERR_CUDA);
@@ -393,6 +414,7 @@ dropin_solve (dpc_result_t *r, const dpc_problem_t *p, Pairpool_T pairpool) {
       pairs = Pairpool_push(pairs,pairpool,q->querypos,q->genomepos,q->cdna,q->comp,q->genome,q->dynprogindex);
     }
   }
+  if (tpost != 0.0) s->t_post += dropin_now() - tpost;
   return pairs;
 }
 

@@ -50,6 +50,11 @@ make -j"$(nproc)" gmapindex >> make.log 2>&1
 (cd ../util && make -s fa_coords gmap_process gmap_build >> ../src/make.log 2>&1)
 mkdir -p "$OUT/bin"
 cp gmapindex ../util/fa_coords ../util/gmap_process ../util/gmap_build "$OUT/bin/"
+# measurement scaffolding: the unmodified reference with a timer around its five gap-fill solvers
+ARGS5=""; for s in Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap; do ARGS5="$ARGS5 --redefine-sym $s=${s}_cpu"; done
+objcopy $ARGS5 gmap-dynprog.o timed-dynprog_cpu.o
+$CC "${CFLAGS[@]}" -c "$REPO/oracle/dynprog_timed.c" -o timed-wrap.o
+$CC -O3 -o "$OUT/gmap_ref_timed" $(ls gmap-*.o | grep -v -e '^gmap-dynprog.o$') timed-dynprog_cpu.o timed-wrap.o -lz -lm -lpthread
 mkdir -p "$OUT/align_test"
 cp "$REF/tests/ss.her2" "$REF/tests/ss.chr17test" "$REF/tests/align.test.ok" "$OUT/align_test/"
 # sanity: the unmodified build reproduces the reference's golden output
