@@ -18,7 +18,11 @@ oracle:
 	$(MAKE) -C oracle
 
 # single-lane CPU build of the device routines: test scaffolding only (tests/emul/dpc_emul.cpp)
-emul: tests/emul/libdpc_emul.so
+emul: tests/emul/libdpc_emul.so tests/emul/_mock/libdynprog_cuda.so
+# test double of the ticket API over the compiled reference (host-side scheduling tests without a GPU)
+tests/emul/_mock/libdynprog_cuda.so: tests/emul/dpc_mock_ref.c include/dynprog_cuda.h
+	mkdir -p tests/emul/_mock
+	gcc -O2 -fPIC -Wall -shared -o $@ tests/emul/dpc_mock_ref.c -ldl
 tests/emul/libdpc_emul.so: tests/emul/dpc_emul.cpp $(PKG)/csrc/dpc_core.h $(PKG)/csrc/dpc_host.h include/dynprog_cuda.h
 	g++ -O2 -fPIC -Wall -Wextra -Wno-unknown-pragmas -shared -o $@ tests/emul/dpc_emul.cpp
 

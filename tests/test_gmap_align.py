@@ -132,3 +132,54 @@ def test_worker_threads_each_with_their_own_context(tmp_path):
     got = run_files("gmap_cuda", gfile, qfile, extra=("-t", "4", "-O"))
     assert ref.returncode == 0 and got.returncode == 0, got.stderr[-2000:]
     assert got.stdout == ref.stdout
+
+
+# ---- the drop-in's fiber scheduler (host side of stage 3 batching) -------------------------------------------
+MOCK = os.path.join(ROOT, "tests", "emul", "_mock")
+
+
+def run_files_env(binary, gfile, qfile, extra=(), env_extra=None):
+    exe = os.path.join(REFDIR, binary)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/%s not built (oracle/build_gmap.sh needs /root/reference)" % binary)
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([exe, "-A", *extra, "-g", gfile, qfile], capture_output=True, text=True, timeout=900, env=env)
+
+
+def test_fiber_scheduler_on_cpu_test_double(tmp_path):
+    """Host logic of the batched drop-in without a GPU: gmap_cuda is run against tests/emul/_mock (the ticket API
+    answered by the compiled reference).  Two worker threads x 8 fibers collect stage 3's gaps into batches
+    (double-buffered contexts, ticket bookkeeping, per-fiber stacks and Pairpools); the alignments must be
+    byte-identical to the unmodified reference binary's, and batches must hold more than one gap."""
+    if not os.path.exists(os.path.join(MOCK, "libdynprog_cuda.so")) or not os.path.exists(os.path.join(REFDIR, "libdynprog_ref.so")):
+        pytest.skip("test double not built")
+    gfile, qfile = synthetic_case(tmp_path, 4, n_transcripts=16, genome_len=120_000)
+    ref = run_files("gmap_ref", gfile, qfile)
+    env = {"LD_LIBRARY_PATH": MOCK, "DPC_FIBERS": "8", "DPC_FIBER_STATS": "1"}
+    got = run_files_env("gmap_cuda", gfile, qfile, extra=("-t", "2", "-O"), env_extra=env)
+    assert ref.returncode == 0 and got.returncode == 0, got.stderr[-2000:]
+    assert got.stdout == ref.stdout
+    stats = [l for l in got.stderr.splitlines() if "device batches" in l]
+    assert len(stats) == 2
+    per_batch = [float(l.split("(")[1].split(" per batch")[0]) for l in stats]
+    assert max(per_batch) > 1.5
+    # DPC_FIBERS=1: the plain worker thread, one gap per flush
+    env["DPC_FIBERS"] = "1"
+    one = run_files_env("gmap_cuda", gfile, qfile, extra=("-t", "2", "-O"), env_extra=env)
+    assert one.returncode == 0 and one.stdout == ref.stdout
+
+
+@pytest.mark.gpu
+def test_database_run_with_fibers_identical_to_reference(tmp_path):
+    """BASELINE configs[4] in small: a synthetic genome database (built with the reference's gmapindex), 2-kb
+    spliced transcripts, gmap -t 4 with 16 fibers per thread on the GPU vs the unmodified reference."""
+    import filecmp
+    from gmap_gsnap_b200 import gmap_e2e as g
+    if not g.have_binaries():
+        pytest.skip("oracle/_ref binaries not built")
+    case = g.prepare(str(tmp_path), 4_000_000, 4, 300, seed=9)
+    _, ref_out, _ = g.run_gmap("gmap_ref", case, 4)
+    _, got_out, err = g.run_gmap("gmap_cuda", case, 4, fibers=16)
+    assert filecmp.cmp(ref_out, got_out, shallow=False)
+    assert "device batches" in err
