@@ -35,12 +35,20 @@
 /* CPL diagonals per lane (k = CPL*lane + j), LATE = jump_late_p of this matrix, EP = end-point search over all
  * rows (find_best_endpoint), NBAND = keep the nogap band for a bridge, QROWS = rows are the query.
  *
- * Values outside the band only have to stay far below every real score (they can never win a max, and the
- * direction bits they produce are never read: the traceback only follows real-valued chains and the bridges only
- * read in-band cells), so they are not kept bit-identical to the reference's NEG arithmetic; what IS kept exact is
- * everything a valid cell can read: row 0, column 0 (set when a diagonal passes c == 0) and NEG above the band. */
+ * No per-cell boundary handling.  A valid cell only reads cells to its left and above, so:
+ *  - cells right of column L2 are simply computed (garbage that can only flow right and down, never back into
+ *    the matrix; their direction bits and band entries are never read);
+ *  - cells left of column 1 come out of the recurrence itself: row 0 starts with N(0,0) = 0 and NEG everywhere
+ *    left of it, so N and gap1 stay "NEG-ish" (NEG plus a bounded number of score/penalty terms, always far
+ *    below any real score) for every c <= 0, and gap2 of column 0 is max(N(r-1,0) + open, gap2(r-1,0)) + extend
+ *    = open + r*extend exactly as 1477-1488 set it (N(0,0) + open for r = 1, the gap2 chain afterwards);
+ *  - diagonals beyond the band (k >= W, they exist because a lane owns CPL of them) get a constant NEG added to
+ *    their nogap value every row, which keeps "NEG above the band" (1501-1507) for the cells that read them.
+ * NEG-ish values never win a max against a real one and never tie with one; the direction bits produced from
+ * NEG-ish operands belong to cells the traceback cannot reach (it follows real-valued chains) and the bridges
+ * only read in-band cells.  Everything a reachable cell can observe is exact. */
 template <int CPL> struct RowState {
-  vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL];
+  vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL], bias[CPL];
   vec::VM kok[CPL], ebok[CPL];
   vec::VI bs, bk;
 };
@@ -59,6 +67,7 @@ DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) 
     s.ebok[j] = vand(k >= lband - es.eb, k <= lband + es.eb);
     const VI c0 = k - lband;                              /* column of this diagonal in row 0 */
     s.cm1[j] = vsel(s.kok[j], c0 - 1, 1 << 24);           /* c - 1 = r + cm1; diagonals past the band never become valid */
+    s.bias[j] = vsel(s.kok[j], QROWS ? -8 : 0, DPC_NEG);  /* score bias of the 4-bit profile; NEG on the diagonals past the band */
     /* row 0 (1460-1475): (0,0) nogap 0; (0,c) gap1 = open + c*extend for 1 <= c <= min(rband, L2) */
     s.Np[j] = vsel(c0 == 0, 0, DPC_NEG);
     s.G1p[j] = vsel(vand(vand(c0 >= 1, c0 <= L2), s.kok[j]), open + c0 * extend, DPC_NEG);
@@ -78,23 +87,20 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
   const VI lane = lane_index();
   const int prof = QROWS ? (int)m.prof[m.prof_base + r * m.prof_step] : 0;
   const int rowg = QROWS ? 0 : (int)m.rowch[r - 1];
-  const int col0 = open + r * extend;                   /* gap2 of (r,0), 1477-1488 */
   (void)L1;
   /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */
   const VI upN = shfl_down1(s.Np[0], DPC_NEG), upG2 = shfl_down1(s.G2p[0], DPC_NEG);
-  VI Nn[CPL], G2n[CPL], a2[CPL], li[CPL], x[CPL];
-  VM p1[CPL], p2[CPL], pv[CPL], inval[CPL];
+  VI Nn[CPL], G2n[CPL], a2[CPL], li[CPL];
+  VM p1[CPL], p2[CPL], pv[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
-    x[j] = s.cm1[j] + r;
-    inval[j] = vnot(vlt_u(x[j], L2));
     /* nogap, 1545-1561.  x > y is !(y >= x): each max also yields the tie-break predicate (vmax_ge) */
     VM ge;
     VI mx, best;
     if (LATE) { mx = vmax_ge(s.G1p[j], s.Np[j], ge); p1[j] = ge; } else { mx = vmax_ge(s.Np[j], s.G1p[j], ge); p1[j] = vnot(ge); }
     if (LATE) { best = vmax_ge(s.G2p[j], mx, ge); p2[j] = ge; } else { best = vmax_ge(mx, s.G2p[j], ge); p2[j] = vnot(ge); }
-    if (QROWS) Nn[j] = best + ((prof >> s.sh[j]) & 15) - 8;
-    else Nn[j] = best + load_i8(score, s.sh[j] + rowg);
+    if (QROWS) Nn[j] = best + ((prof >> s.sh[j]) & 15) + s.bias[j];
+    else Nn[j] = best + load_i8(score, s.sh[j] + rowg) + s.bias[j];
     /* gap2, 1532-1542 */
     const VI Nu = j + 1 < CPL ? s.Np[j + 1 < CPL ? j + 1 : j] : upN;
     const VI G2u = j + 1 < CPL ? s.G2p[j + 1 < CPL ? j + 1 : j] : upG2;
@@ -133,11 +139,13 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
     const uint32_t b1 = vballot(p2[j]), b0 = vballot(p1[j]) & ~b1, b2 = vballot(h), b3 = vballot(pv[j]);
     store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
     if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), s.kok[j]);
-    if (EP) keep_better(s.bs, s.bk, Nn[j], x[j] + (r * (L2 + 1) + 1), vand(vnot(inval[j]), s.ebok[j]), LATE);
-    /* what the next row sees on this diagonal: the cell, column 0, or NEG */
-    s.Np[j] = vsel(inval[j], DPC_NEG, Nn[j]);
+    if (EP) {
+      const VI x = s.cm1[j] + r;
+      keep_better(s.bs, s.bk, Nn[j], x + (r * (L2 + 1) + 1), vand(vlt_u(x, L2), s.ebok[j]), LATE);
+    }
+    s.Np[j] = Nn[j];
     s.G1p[j] = G1n;
-    s.G2p[j] = vsel(x[j] == -1, col0, vsel(inval[j], DPC_NEG, G2n[j]));
+    s.G2p[j] = G2n[j];
   }
 }
 
@@ -162,7 +170,13 @@ template <int CPL, bool LATE, bool EP, bool NBAND, bool QROWS>
 DPC_VFN void dpc_fill_rows(const Mat &m, const int8_t *score, EndSearch &es) {
   RowState<CPL> s;
   dpc_rows_init<CPL, QROWS>(s, m, es);
-  for (int r = 1; r <= m.L1; r++) dpc_rows_step<CPL, LATE, EP, NBAND, QROWS>(s, m, score, r);
+  int r = 1;
+  /* two rows per trip: the loop-carried state then stays in place instead of being copied at the end of every row */
+  for (; r < m.L1; r += 2) {
+    dpc_rows_step<CPL, LATE, EP, NBAND, QROWS>(s, m, score, r);
+    dpc_rows_step<CPL, LATE, EP, NBAND, QROWS>(s, m, score, r + 1);
+  }
+  if (r == m.L1) dpc_rows_step<CPL, LATE, EP, NBAND, QROWS>(s, m, score, r);
   dpc_rows_finish<CPL, LATE>(s, m, es);
   vec::sync();
 }
