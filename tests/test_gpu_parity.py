@@ -2,6 +2,7 @@
 Bit-exact for scores, end points, intron boundaries, counts and Pair records; 1e-6 relative for the
 splice-site probabilities (the tolerance BASELINE.json's north_star states)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -159,3 +160,31 @@ def test_full_size_properties(workload, port, cuda):
     assert (res == res2).all()
     sample = probs[:: n // 5000]
     assert not api.compare(*port.solve(sample), *cuda.solve(sample))
+
+
+@pytest.mark.parametrize("kind,n", [("single", 1_000_000), ("genome", 500_000), ("end", 1_000_000)])
+def test_full_size_exact_against_compiled_reference(kind, n):
+    """BASELINE configs[1..3] at their full sizes, EXACT: the unmodified reference (oracle/_ref/libdynprog_ref.so,
+    all host threads) solves the same problems as the GPU and every output field must be equal -- scores, counts,
+    intron boundaries, introntype, npairs, dynprogindex; the Pair records are compared on the first 100 000."""
+    import bench
+    if not os.path.exists(os.path.join(bench.ROOT, "oracle", "_ref", "libdynprog_ref.so")):
+        pytest.skip("compiled reference not built")
+    w, probs = bench.make_workload(0, n, kind)
+    ref = api.RefOracle()
+    ref.init()
+    ref.setup(w.make_setup())
+    lib = api.CudaLib()
+    lib.init()
+    lib.setup(w.make_setup())
+    lib.open(0)
+    try:
+        got, _, _ = lib.solve(probs, want_pairs=False)
+        want, _ = ref.solve_mt(probs, os.cpu_count() or 1)
+        empty = np.zeros(0, dtype=api.PAIR_DT)
+        z = np.zeros(1, dtype=np.int64)
+        assert not api.compare(want, empty, z, got, empty, z, rtol=RTOL)
+        head = probs[:100_000]
+        assert not api.compare(*ref.solve(head), *lib.solve(head), rtol=RTOL)
+    finally:
+        lib.close()
