@@ -32,9 +32,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <limits.h>
 #include <time.h>
 #include <pthread.h>
 #include <sys/mman.h>
+#include <malloc.h>
 #if !defined(__x86_64__)
 #include <ucontext.h>
 #endif
@@ -215,6 +217,7 @@ typedef struct dropin_sched {
 } dropin_sched_t;
 
 static __thread dropin_sched_t *dropin_sched;
+static __thread long dropin_memo_hits, dropin_memo_misses;	/* memo of device results, below */
 
 static double
 dropin_now (void) {
@@ -318,9 +321,9 @@ dropin_scheduler (void *data) {
   } while (live > 0);
 
   if (stats) {
-    fprintf(stderr,"libdynprog_cuda drop-in: %d fibers, %ld device batches, %ld gaps (%.1f per batch), %.2f s in flush+wait, %.2f s in add, %.2f s in result+pairs+push, of %.2f s\n",
+    fprintf(stderr,"libdynprog_cuda drop-in: %d fibers, %ld device batches, %ld gaps (%.1f per batch), %.2f s in flush+wait, %.2f s in add, %.2f s in result+pairs+push, of %.2f s; memo %ld hits, %ld misses\n",
 	    s->nfibers,s->nrounds,s->nproblems,s->nrounds ? (double) s->nproblems/(double) s->nrounds : 0.0,
-	    s->t_device,s->t_add,s->t_post,dropin_now() - s->t_start);
+	    s->t_device,s->t_add,s->t_post,dropin_now() - s->t_start,dropin_memo_hits,dropin_memo_misses);
   }
   for (i = 0; i < s->nfibers; i++) munmap(s->fibers[i].stack,FIBER_STACK_BYTES);
   dpc_ctx_free(s->ctx[0]); dpc_ctx_free(s->ctx[1]);
@@ -339,6 +342,20 @@ Dynprog_cuda_worker_create (pthread_t *thread, const pthread_attr_t *attr, void 
   dropin_sched_t *s;
 
   if (nfibers <= 1) return pthread_create(thread,attr,start_routine,arg);
+  {
+    /* Many requests in flight per thread interleave their large, short-lived allocations (stage 2's position
+       tables, diagonals, pair pools); with glibc's defaults every one of them is mapped, faulted in and unmapped
+       again under the process-wide mmap lock.  Keep freed memory in the arenas instead (measured on the
+       whole-program bench: 9.2 M -> 4.5 M page faults, 29 s -> 8 s of system time).  DPC_MALLOC_TUNING=0 skips it. */
+    static int tuned = 0;
+    const char *m = getenv("DPC_MALLOC_TUNING");
+    if (!tuned && (m == NULL || atoi(m) != 0)) {
+      mallopt(M_MMAP_MAX,0);
+      mallopt(M_TRIM_THRESHOLD,INT_MAX);
+      mallopt(M_TOP_PAD,256 << 20);
+    }
+    tuned = 1;
+  }
   s = (dropin_sched_t *) calloc(1,sizeof(*s));
   s->fibers = (dropin_fiber_t *) calloc(nfibers,sizeof(dropin_fiber_t));
   s->nfibers = nfibers;
@@ -369,13 +386,158 @@ dropin_device (void) {
   return e != NULL ? atoi(e) : 0;
 }
 
+/* ---- memo of device results --------------------------------------------------------------------------- */
+/* Stage 3 solves the same gap again and again: every pass over a path (stage3.c build_pairs_singles /
+   _introns / _end5 / _end3, repeated by path_compute until nothing changes) peels the same pairs back and calls
+   the solver with the same arguments.  A solver's outputs are a pure function of its arguments, the query bytes
+   and the (constant) genome, so each worker thread keeps the device results of its recent problems in a
+   direct-mapped table and replays them -- result fields and Pair records, re-stamped with the caller's current
+   dynprogindex -- instead of sending the gap to the device again.  Exact by construction: a hit requires every
+   scalar argument and every query byte to be equal.  DPC_MEMO=0 turns it off; DPC_MEMO=<n> sets the table size. */
+typedef struct dropin_memo {
+  uint64_t hash;
+  dpc_problem_t key;		/* pointers cleared, dynprogindex reduced to its sign */
+  dpc_result_t res;
+  char *q; int qlen, qcap;
+  dpc_pair_t *pairs; int npairs, pcap;
+  int in_index;
+  int cdna_direction;		/* of the stored problem (single / end gaps keep it out of the key) */
+  int any_direction;		/* single / end gaps: the result does not depend on cdna_direction */
+  int valid;
+} dropin_memo_t;
+
+static __thread dropin_memo_t *dropin_memo_tab;
+static __thread int dropin_memo_n = -1;		/* -1: not configured yet; 0: off */
+
+static int
+dropin_memo_spans (const dpc_problem_t *p, const char **a, int *na, const char **b, int *nb) {
+  *a = *b = NULL; *na = *nb = 0;
+  if (p->seq1 == NULL || p->length1 <= 0 || p->length1 > 4096) return 0;
+  if (p->kind == DPC_END5_GAP) { *a = p->seq1 - (p->length1 - 1); *na = p->length1; }
+  else { *a = p->seq1; *na = p->length1; }
+  if (p->kind == DPC_CDNA_GAP) {
+    if (p->seq1R == NULL || p->length1R <= 0 || p->length1R > 4096) return 0;
+    *b = p->seq1R - (p->length1R - 1); *nb = p->length1R;
+  }
+  return 1;
+}
+
+static uint64_t
+dropin_fnv (uint64_t h, const void *data, size_t n) {
+  const unsigned char *c = (const unsigned char *) data;
+  size_t i;
+  for (i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ULL; }
+  return h;
+}
+
+/* Returns the table slot for p (filling *key, *hash); *hit tells whether it already holds p's result. */
+static dropin_memo_t *
+dropin_memo_find (const dpc_problem_t *p, dpc_problem_t *key, uint64_t *hash, int *hit) {
+  const char *a, *b;
+  int na, nb, k;
+  dropin_memo_t *e;
+
+  *hit = 0;
+  if (dropin_memo_n < 0) {
+    const char *env = getenv("DPC_MEMO");
+    dropin_memo_n = env != NULL ? atoi(env) : 8192;
+    if (dropin_memo_n > 0) dropin_memo_tab = (dropin_memo_t *) calloc((size_t) dropin_memo_n,sizeof(dropin_memo_t));
+    if (dropin_memo_tab == NULL) dropin_memo_n = 0;
+  }
+  if (dropin_memo_n == 0 || !dropin_memo_spans(p,&a,&na,&b,&nb)) return NULL;
+  *key = *p;
+  key->seq1 = key->seq1R = NULL;
+  key->dynprogindex = p->dynprogindex > 0 ? 1 : -1;
+  /* the solvers only look at the quality class of defect_rate (dynprog.h:27-28, dynprog.c:4480-4500) */
+  key->defect_rate = p->defect_rate < DEFECT_HIGHQ ? 0.0 : p->defect_rate < DEFECT_MEDQ ? 1.0 : 2.0;
+  /* score_threshold is only read in probability mode (dynprog.c:3829-4081) */
+  if (!p->use_probabilities_p) key->score_threshold = 0;
+  /* single and end gaps see cdna_direction only in add_genomeskip's intron test of genome runs of 9 or more
+     (dynprog.c:2416-2512): GMAP solves every gap once per direction, and a result without such a run serves both */
+  if (p->kind != DPC_GENOME_GAP && p->kind != DPC_CDNA_GAP) key->cdna_direction = 0;
+  *hash = dropin_fnv(dropin_fnv(dropin_fnv(1469598103934665603ULL,key,sizeof(*key)),a,(size_t) na),b,(size_t) nb);
+  /* direction-independent results live in the slot of the hash; a single / end gap whose result does depend on
+     cdna_direction (rare) lives one or two slots further, by direction, so the two directions do not evict each other */
+  for (k = 0; k < 2; k++) {
+    e = &dropin_memo_tab[(*hash + (uint64_t) (k == 0 ? 0 : p->cdna_direction > 0 ? 2 : 1)) % (uint64_t) dropin_memo_n];
+    if (e->valid && e->hash == *hash && e->qlen == na + nb && memcmp(&e->key,key,sizeof(*key)) == 0 &&
+	memcmp(e->q,a,(size_t) na) == 0 && memcmp(e->q + na,b,(size_t) nb) == 0 &&
+	(e->any_direction || e->cdna_direction == p->cdna_direction)) {
+      *hit = 1;
+      return e;
+    }
+  }
+  e = &dropin_memo_tab[*hash % (uint64_t) dropin_memo_n];
+  return e;
+}
+
+static void
+dropin_memo_store (dropin_memo_t *e, const dpc_problem_t *p, const dpc_problem_t *key, uint64_t hash,
+		   const dpc_result_t *r, const dpc_pair_t *pairs, int npairs) {
+  const char *a, *b;
+  int na, nb, i, any_direction;
+  if (!dropin_memo_spans(p,&a,&na,&b,&nb)) return;
+  /* a genome run of MICROINTRON_LENGTH (9, dynprog.c:139) or more shows up as a gapholder record or, as dashes,
+     in nindels (counted before end gaps strip leading indel pairs, dynprog.c:5265) */
+  any_direction = r->nindels != DPC_UNSET && r->nindels < 9;
+  for (i = 0; i < npairs; i++) if (pairs[i].gapp) any_direction = 0;
+  if (!any_direction && key->cdna_direction == 0 && p->cdna_direction != 0) {
+    e = &dropin_memo_tab[(hash + (uint64_t) (p->cdna_direction > 0 ? 2 : 1)) % (uint64_t) dropin_memo_n];
+  }
+  if (na + nb > e->qcap) { e->qcap = 2*(na + nb) + 64; e->q = (char *) realloc(e->q,(size_t) e->qcap); }
+  if (npairs > e->pcap) { e->pcap = 2*npairs + 64; e->pairs = (dpc_pair_t *) realloc(e->pairs,(size_t) e->pcap*sizeof(dpc_pair_t)); }
+  if (e->q == NULL || (npairs > 0 && e->pairs == NULL)) { e->valid = 0; e->qcap = e->pcap = 0; return; }
+  memcpy(e->q,a,(size_t) na);
+  if (nb > 0) memcpy(e->q + na,b,(size_t) nb);
+  e->qlen = na + nb;
+  if (npairs > 0) memcpy(e->pairs,pairs,(size_t) npairs*sizeof(dpc_pair_t));
+  e->npairs = npairs;
+  e->key = *key; e->hash = hash; e->res = *r; e->in_index = p->dynprogindex;
+  e->cdna_direction = p->cdna_direction;
+  e->any_direction = any_direction;
+  e->valid = 1;
+}
+
+/* dpc_pairs lists the records head first; Pairpool_push prepends (pairpool.c:169-215) */
+static List_T
+dropin_push_pairs (const dpc_pair_t *rec, int n, int dynprogindex, Pairpool_T pairpool) {
+  List_T pairs = NULL;
+  int i;
+  for (i = n - 1; i >= 0; i--) {
+    const dpc_pair_t *q = &rec[i];
+    if (q->gapp) {
+      pairs = Pairpool_push_gapholder(pairs,pairpool,/*queryjump*/UNKNOWNJUMP,/*genomejump*/UNKNOWNJUMP,/*knownp*/false);
+    } else {
+      pairs = Pairpool_push(pairs,pairpool,q->querypos,q->genomepos,q->cdna,q->comp,q->genome,dynprogindex);
+    }
+  }
+  return pairs;
+}
+
 static List_T
 dropin_solve (dpc_result_t *r, const dpc_problem_t *p, Pairpool_T pairpool) {
   List_T pairs = NULL;
   dropin_sched_t *s = dropin_sched;
   dpc_ctx_t *ctx;
+  dpc_problem_t key;
+  dropin_memo_t *memo;
+  uint64_t hash = 0;
   double tpost = 0.0;
-  int rc, ticket, n, i;
+  int rc, ticket, n, hit;
+
+  memo = dropin_memo_find(p,&key,&hash,&hit);
+  if (hit) {
+    *r = memo->res;
+    r->dynprogindex_out = p->dynprogindex + (memo->res.dynprogindex_out - memo->in_index);
+    dropin_memo_hits++;
+    return dropin_push_pairs(memo->pairs,memo->npairs,p->dynprogindex,pairpool);
+  }
+  dropin_memo_misses++;
+#ifdef DPC_MEMO_DEBUG
+  fprintf(stderr,"MISS %d %d | %d %d %d %d | %d %d %d %d | %u %u | %d %d %d %d %d | %d%d%d%d%d%d%d | %g | %llx\n",p->kind,p->endalign,p->length1,p->length1R,p->length2,p->length2R,
+	  p->offset1,p->offset1R,p->offset2,p->offset2R,p->chrpos,p->genomiclength,p->chrnum,p->cdna_direction,p->extraband,p->maxpeelback,p->score_threshold,
+	  p->watsonp,p->jump_late_p,p->widebandp,p->halfp,p->finalp,p->use_probabilities_p,p->splicingp,key.defect_rate,(unsigned long long) dropin_fnv(1469598103934665603ULL,p->seq1 ? (p->kind == DPC_END5_GAP ? p->seq1 - (p->length1-1) : p->seq1) : "",p->length1 > 0 ? p->length1 : 0));
+#endif
 
   if (s != NULL && s->cur != NULL) {
     /* inside a fiber: enqueue into this round's batch and park until the scheduler has run it on the device */
@@ -404,16 +566,8 @@ dropin_solve (dpc_result_t *r, const dpc_problem_t *p, Pairpool_T pairpool) {
     dropin_pairs = (dpc_pair_t *) realloc(dropin_pairs,dropin_pairs_cap*sizeof(dpc_pair_t));
   }
   if ((n = dpc_pairs(ctx,ticket,dropin_pairs,dropin_pairs_cap)) < 0) dropin_fatal("dpc_pairs",n);
-
-  /* dpc_pairs lists the records head first; Pairpool_push prepends (pairpool.c:169-215) */
-  for (i = n - 1; i >= 0; i--) {
-    const dpc_pair_t *q = &dropin_pairs[i];
-    if (q->gapp) {
-      pairs = Pairpool_push_gapholder(pairs,pairpool,/*queryjump*/UNKNOWNJUMP,/*genomejump*/UNKNOWNJUMP,/*knownp*/false);
-    } else {
-      pairs = Pairpool_push(pairs,pairpool,q->querypos,q->genomepos,q->cdna,q->comp,q->genome,q->dynprogindex);
-    }
-  }
+  if (memo != NULL) dropin_memo_store(memo,p,&key,hash,r,dropin_pairs,n);
+  pairs = dropin_push_pairs(dropin_pairs,n,p->dynprogindex,pairpool);
   if (tpost != 0.0) s->t_post += dropin_now() - tpost;
   return pairs;
 }
