@@ -154,7 +154,7 @@ def run_gmap_workload(args, rank, world, local_rank):
         return
     cores = os.cpu_count() or 1
     threads = max(1, cores // max(1, world))
-    n = args.problems if args.problems != N_PROBLEMS else 8000
+    n = args.problems if args.problems != N_PROBLEMS else 16000
     case = g.prepare("/tmp/dpc_gmap_case_%d" % rank, args.genome_bases, 4, n, seed=5 + rank)
     line = {"metric": "gmap_queries_per_s", "unit": "queries/s", "n_gpus": world, "steps": 1, "warmup": 0,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -344,7 +344,10 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms[len(ms) // 2] * 1e-3) / 1e9 if rank == 0 else None,
                      "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9 / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": 474.4e6 if (args.workload == "single" and n == 1_000_000) else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the step's two launches, "
+                                       "profiles/r1_final_single_gap_ncu_full.csv (bytes per step)",
+                     "peak_source": peak_src,
                      "note": "fused fill+traceback keeps matrices and direction nibbles in shared memory; algorithmic HBM bytes are "
                              "descriptors, sequences and result records only, so the kernel is integer-ALU/latency bound (see alu_roofline)"},
         "alu_roofline": {"achieved_gcups_per_gpu": cells / (float(np.mean(ms)) * 1e-3) / 1e9,
