@@ -425,28 +425,44 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
   for (int t = ln.lane; t < 64; t += ln.n) itab[t] = (int8_t)dpc_intron_score(&it, t, t, p.cdna_direction, p.reward, finalp);
   DPC_SYNC();
   const bool fast = mL.planes && mR.planes && mL.cpl == 1 && mR.cpl == 1 && !lknown && !rknown && !probmode;
-  for (int rL = 1; rL < L1 && fast; rL++) {
-    /* common case (bands of at most 32 diagonals, no known sites, integer mode): lane = diagonal, exactly like the
-       fill -- one candidate per lane and side, rows of the nogap band and of the direction planes read directly */
-    const int rR = L1 - rL;
-    const int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
-    const int cloR = rR - lbandR < 1 ? 1 : rR - lbandR, chighR = rR + rbandR > L2R - 1 ? L2R - 1 : rR + rbandR;
-    const int nL = chighL >= cloL ? chighL - cloL + 1 : 0;
-    const int16_t *rowL = mL.nband + (rL - 1) * mL.W, *rowR = mR.nband + (rR - 1) * mR.W;
-    const uint32_t *wL = mL.dir + (rL - 1) * 4, *wR = mR.dir + (rR - 1) * 4;
-    const int dR = rowR[mR.lband], dL = rowL[mL.lband];           /* the main-diagonal cells (rR,rR) and (rL,rL) */
-    const int diR = rdi[rR], diL = ldi[rL];
+  /* common case (bands of at most 32 diagonals, no known sites, integer mode): lane = diagonal, exactly like the
+     fill -- one candidate per lane and side, rows of the nogap band and of the direction planes read directly.
+     Four row pairs at a time, loads first: for long gaps the bands and planes sit in HBM scratch (L2), and one
+     row pair at a time is a chain of dependent load latencies (ncu: half of the long-gap launch was spent here). */
+  enum { BR = 4 };
+  for (int rL0 = 1; rL0 < L1 && fast; rL0 += BR) {
     for (int k = ln.lane; k < 32; k += ln.n) {                   /* one trip per lane on the GPU */
-      const int cL = rL - mL.lband + k, cR = rR - mR.lband + k;
-      if (cL >= cloL && cL <= chighL && rR < p.gap - cL) {
-        const int s = rowL[k] - (int)(((wL[0] | wL[1]) >> k) & 1U) + itab[ldi[cL] & diR] + dR;
-        const int key = rL * 8192 + (cL - cloL);
-        if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+      const int kL = k < mL.W ? k : mL.W - 1, kR = k < mR.W ? k : mR.W - 1;
+      int vL[BR], vR[BR], dL[BR], dR[BR];
+      uint32_t hL[BR], hR[BR];
+#pragma unroll
+      for (int u = 0; u < BR; u++) {
+        const int rL = rL0 + u < L1 ? rL0 + u : L1 - 1, rR = L1 - rL;
+        const int16_t *rowL = mL.nband + (rL - 1) * mL.W, *rowR = mR.nband + (rR - 1) * mR.W;
+        const uint32_t *wL = mL.dir + (rL - 1) * 4, *wR = mR.dir + (rR - 1) * 4;
+        vL[u] = rowL[kL]; vR[u] = rowR[kR];
+        dL[u] = rowL[mL.lband]; dR[u] = rowR[mR.lband];          /* the main-diagonal cells (rL,rL) and (rR,rR) */
+        hL[u] = wL[0] | wL[1]; hR[u] = wR[0] | wR[1];
       }
-      if (cR >= cloR && cR <= chighR && rL < p.gap - cR) {
-        const int s = rowR[k] - (int)(((wR[0] | wR[1]) >> k) & 1U) + itab[diL & rdi[cR]] + dL;
-        const int key = rL * 8192 + nL + (cR - cloR);
-        if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+#pragma unroll
+      for (int u = 0; u < BR; u++) {
+        const int rL = rL0 + u, rR = L1 - rL;
+        if (rL >= L1) break;
+        const int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
+        const int cloR = rR - lbandR < 1 ? 1 : rR - lbandR, chighR = rR + rbandR > L2R - 1 ? L2R - 1 : rR + rbandR;
+        const int nL = chighL >= cloL ? chighL - cloL + 1 : 0;
+        const int diR = rdi[rR], diL = ldi[rL];
+        const int cL = rL - mL.lband + k, cR = rR - mR.lband + k;
+        if (cL >= cloL && cL <= chighL && rR < p.gap - cL) {
+          const int s = vL[u] - (int)((hL[u] >> k) & 1U) + itab[ldi[cL] & diR] + dR[u];
+          const int key = rL * 8192 + (cL - cloL);
+          if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+        }
+        if (cR >= cloR && cR <= chighR && rL < p.gap - cR) {
+          const int s = vR[u] - (int)((hR[u] >> k) & 1U) + itab[diL & rdi[cR]] + dL[u];
+          const int key = rL * 8192 + nL + (cR - cloR);
+          if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+        }
       }
     }
   }
