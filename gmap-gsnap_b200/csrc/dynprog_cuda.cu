@@ -532,6 +532,13 @@ int dpc_device_count(void) {
   return n;
 }
 
+int dpc_warmup(int device) {
+  if (device < 0 || device >= dpc_device_count()) return DPC_ERR_CUDA;
+  CK(cudaSetDevice(device));
+  CK(cudaFree(0));
+  return DPC_OK;
+}
+
 dpc_ctx_t *dpc_ctx_new(int device) {
   if (device < 0 || device >= dpc_device_count()) return NULL;
   if (ensure_device(device) != DPC_OK) return NULL;

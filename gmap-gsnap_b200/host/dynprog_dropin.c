@@ -113,10 +113,22 @@ dropin_splice_known (int which, int chrnum, uint32_t splicesitepos, int sign, vo
 					    splicesitepos,splicesitepos+1U,type,sign) == true;
 }
 
+static int dropin_device (void);
+
+static void *
+dropin_warmup_thread (void *data) {
+  (void) data;
+  dpc_warmup(dropin_device());	/* errors surface later, in dpc_ctx_new */
+  return NULL;
+}
+
 void
 Dynprog_init (int maxlookback, int extraquerygap, int maxpeelback,
 	      int extramaterial_end, int extramaterial_paired, Mode_T mode) {
+  pthread_t warm;
   int rc;
+  /* gmap.c:3456 calls this before it loads the genome and its index (3510-3620): start the CUDA context now */
+  if (pthread_create(&warm,NULL,dropin_warmup_thread,NULL) == 0) pthread_detach(warm);
   Dynprog_init_cpu(maxlookback,extraquerygap,maxpeelback,extramaterial_end,extramaterial_paired,mode);
   if ((rc = dpc_init(maxlookback,extraquerygap,maxpeelback,extramaterial_end,extramaterial_paired,(int) mode)) != DPC_OK) {
     dropin_fatal("dpc_init",rc);

@@ -181,6 +181,10 @@ void dpc_maxlengths(int *maxlength1, int *maxlength2);
 const char *dpc_strerror(int code);
 /* Number of usable CUDA devices (0 when there is no driver/GPU). */
 int dpc_device_count(void);
+/* Optional: creates the CUDA context of `device` ahead of time (callable from any thread, before dpc_setup), so
+ * that a host program can overlap the ~0.5 s of driver/context start-up with its own initialisation (the
+ * drop-in does it from Dynprog_init, which gmap.c:3456 calls before it loads the genome index). */
+int dpc_warmup(int device);
 
 /* ---- per-thread batch context (one Dynprog_T triple + stream) ---------- */
 dpc_ctx_t *dpc_ctx_new(int device);

@@ -54,6 +54,7 @@ int dpc_setup(const dpc_setup_t *s) { return load_ref() ? DPC_ERR_CUDA : ref_set
 void dpc_term(void) {}
 const char *dpc_strerror(int code) { (void)code; return "mock backend error"; }
 int dpc_device_count(void) { return 1; }
+int dpc_warmup(int device) { (void)device; return DPC_OK; }
 
 dpc_ctx_t *dpc_ctx_new(int device) { (void)device; return (dpc_ctx_t *)calloc(1, sizeof(dpc_ctx_t)); }
 void dpc_ctx_free(dpc_ctx_t *c) { if (c) { dpc_reset(c); free(c->p); free(c->own); free(c->r); free(c->pairs); free(c->off); free(c); } }
