@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 DPC_UNSET = -2000000001
-SINGLE_GAP, GENOME_GAP, CDNA_GAP, END5_GAP, END3_GAP = range(5)
+SINGLE_GAP, GENOME_GAP, CDNA_GAP, END5_GAP, END3_GAP, END5_SPLICEJUNCTION, END3_SPLICEJUNCTION = range(7)
 QUERYEND_GAP, QUERYEND_INDELS, QUERYEND_NOGAPS, BEST_LOCAL = range(4)
 KIND_NAMES = ["single_gap", "genome_gap", "cdna_gap", "end5_gap", "end3_gap"]
 
@@ -194,6 +194,77 @@ class Workload:
         d.update(kw)
         sp = self.params(**d)
         return self._gen("synth_cdna_gaps", n, 2 * sp.len_hi + sp.intron_hi + 64, sp)
+
+    def splicejunction_gaps(self, n, extraband=3, seed=77, len_lo=8, len_hi=60, p_sub=0.04, p_indel=0.01, long_run_pm=30):
+        """Problems for Dynprog_end5/3_splicejunction (dynprog.c:5411-5552, 5869-6012): the genomic side is a
+        splice-junction STRING (anchor exon piece of `contlength` bases + the far exon piece), not a genome window;
+        the query is a mutated copy of it.  A few problems get a genome-only run of 9+ flanked by GT..AG / CT..AC
+        so that the gapholder path of add_genomeskip (2448-2451) is exercised.  Pure numpy; test workloads only."""
+        rng = np.random.default_rng(seed)
+        probs = np.zeros(n, dtype=PROBLEM_DT)
+        qbuf = np.zeros(n * (2 * len_hi + 64) * 2 + 4096, dtype=np.uint8)
+        base = qbuf.ctypes.data
+        at = 0
+        acgt = np.frombuffer(b"ACGT", np.uint8)
+        for i in range(n):
+            five = bool(rng.integers(0, 2))
+            L2 = int(rng.integers(len_lo, len_hi + 1)) + 10
+            cont = int(rng.integers(0, L2 + 1)) if rng.random() < 0.1 else int(rng.integers(1, max(2, L2 // 2)))
+            g = acgt[rng.integers(0, 4, L2)]
+            if rng.random() < 0.02:
+                g[rng.integers(0, L2)] = ord("N")
+            q = []
+            j = 0
+            skip_at = int(rng.integers(2, max(3, L2 - 14))) if rng.integers(0, 1000) < long_run_pm and L2 > 30 else -1
+            while j < L2 - 10:
+                if j == skip_at:
+                    run = int(rng.integers(9, 13))
+                    if rng.random() < 0.7:
+                        g[j:j + 2] = (71, 84) if rng.random() < 0.5 else (67, 84)
+                        g[j + run - 2:j + run] = (65, 71) if g[j] == 71 else (65, 67)
+                    j += run
+                    continue
+                u = rng.random()
+                if u < p_indel:
+                    j += 1
+                    continue
+                if u < 2 * p_indel:
+                    q.append(int(acgt[rng.integers(0, 4)]))
+                ch = int(g[j])
+                if u > 1 - p_sub:
+                    ch = int(acgt[rng.integers(0, 4)])
+                if rng.random() < 0.01:
+                    ch |= 0x20
+                q.append(ch)
+                j += 1
+            if not q:
+                q = [65]
+            q = np.array(q, np.uint8)
+            L1 = len(q)
+            # both strings are laid out in reading order; the END5 variant hands over pointers to their LAST characters
+            qs, gs = (q[::-1], g[::-1]) if five else (q, g)
+            qbuf[at:at + L1] = qs
+            qa = at; at += L1 + 1
+            qbuf[at:at + L2] = gs
+            ga = at; at += L2 + 1
+            pr = probs[i]
+            pr["kind"] = END5_SPLICEJUNCTION if five else END3_SPLICEJUNCTION
+            pr["seq1"] = base + qa + (L1 - 1 if five else 0)
+            pr["seq1R"] = base + ga + (L2 - 1 if five else 0)
+            pr["length1"], pr["length2"], pr["length2R"] = L1, L2, cont
+            o1, oa, far = int(rng.integers(20, 2000)), int(rng.integers(1000, 100000)), int(rng.integers(200, 50000))
+            pr["offset1"] = o1
+            pr["offset2"] = oa
+            pr["offset2R"] = oa - far if five else oa + far
+            pr["chroffset"], pr["chrhigh"], pr["chrpos"], pr["genomiclength"] = 0, self.nbases, 1000, 200000
+            pr["cdna_direction"] = int(rng.integers(-1, 2))
+            pr["extraband"] = extraband
+            pr["maxpeelback"] = 11
+            pr["dynprogindex"] = int(rng.integers(1, 50)) * (1 if rng.random() < 0.5 else -1)
+            pr["watsonp"], pr["jump_late_p"], pr["widebandp"], pr["splicingp"] = int(rng.integers(0, 2)), int(rng.integers(0, 2)), 1, 1
+            pr["defect_rate"] = float(rng.choice([0.0, 0.01, 0.05]))
+        self._keep.append(qbuf)
+        return probs
 
     def make_setup(self, splice_prob=None, splice_known=None, novelsplicingp=1):
         s = Setup()

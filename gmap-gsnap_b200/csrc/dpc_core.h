@@ -51,7 +51,8 @@ enum { DPC_GN = 4, DPC_GSTAR = 5 };
 /* problem flags */
 enum {
   DPC_F_WATSON = 1, DPC_F_LATE = 2, DPC_F_WIDEBAND = 4, DPC_F_HALFP = 8, DPC_F_FINALP = 16,
-  DPC_F_PROBMODE = 32, DPC_F_ALLSTAR = 64, DPC_F_KNOWN = 128, DPC_F_NOVEL = 256
+  DPC_F_PROBMODE = 32, DPC_F_ALLSTAR = 64, DPC_F_KNOWN = 128, DPC_F_NOVEL = 256,
+  DPC_F_SEQ2 = 512          /* the columns' genome codes are in the byte pool at q1, in matrix order (splice-junction solvers) */
 };
 
 /* device-side problem descriptor (host packs it from dpc_problem_t) */
@@ -728,7 +729,12 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         m0.rowch[i] = (uint8_t)q;
         if (m0.planes) m0.prof[i] = dpc_pack_prof(score, q);
       }
-      for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+      if (p.flags & DPC_F_SEQ2) {
+        /* Dynprog_end5/3_splicejunction 5411-5552, 5869-6012: use_genomicseg_p, sequence2 = the splice-junction string */
+        for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = pool[p.q1 + (uint32_t)i];
+      } else {
+        for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+      }
       if (ln.lane == 0) m0.colch[p.L2] = 7;                               /* sentinel one past the last column */
       DPC_SYNC();
       EndSearch es; es.eb = p.extraband;

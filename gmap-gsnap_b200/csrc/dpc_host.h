@@ -463,6 +463,36 @@ struct Batch {
       todev = true;
       break;
     }
+    case DPC_END5_SPLICEJUNCTION: case DPC_END3_SPLICEJUNCTION: {      /* 5411-5552, 5869-6012 */
+      const bool five = p.kind == DPC_END5_SPLICEJUNCTION;
+      const int L1 = p.length1, L2 = p.length2;
+      if (L1 <= 0 || L1 > g.maxlength1 || L2 <= 0 || L2 > g.maxlength2) {      /* 5452-5465: no chopping here */
+        r.nmatches = r.nmismatches = r.nopens = r.nindels = 0; r.finalscore = 0;
+        break;
+      }
+      if (p.seq1R == NULL || p.length2R < 0) return DPC_ERR_ARG;
+      if (!alphabet_ok(five ? p.seq1 - (L1 - 1) : p.seq1, L1)) return DPC_ERR_ALPHABET;
+      d.kind = (uint8_t)(five ? DPC_END5_GAP : DPC_END3_GAP);           /* same device work as an end gap ... */
+      d.endalign = DPC_QUERYEND_INDELS;                                /* ... with the end point on the last row, 5506 */
+      d.type = ENDQ; d.open = -12; d.extend = -1;                      /* END, 240-247; ENDQ 179 */
+      d.flags |= DPC_F_WIDEBAND | DPC_F_SEQ2;
+      d.L1 = L1; d.L2 = L2; d.off2 = p.offset2;
+      d.q0 = h.q0 = five ? pool_put(p.seq1 - (L1 - 1), L1) : pool_put(p.seq1, L1);
+      {
+        /* the junction string as genome codes in matrix order (column i = sequence2[+-i]) */
+        uint8_t *codes = pool.grow((size_t)L2);
+        d.q1 = h.q1 = (uint32_t)(codes - pool.data());
+        for (int i = 0; i < L2; i++) {
+          const int ch = (unsigned char)(five ? p.seq1R[-i] : p.seq1R[i]);
+          const int code = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : ch == 'N' ? 4 : -1;
+          if (code < 0) return DPC_ERR_ALPHABET;
+          codes[i] = (uint8_t)code;
+        }
+      }
+      d.flags |= DPC_F_ALLSTAR;          /* no genome access: the segment checks below do not apply */
+      todev = true;
+      break;
+    }
     case DPC_GENOME_GAP: {                                             /* Dynprog_genome_gap, 4798-5061 */
       int L1 = p.length1, L2L = p.length2, L2R = p.length2R;
       r.nmatches = r.nmismatches = r.nopens = r.nindels = 0;
@@ -527,7 +557,7 @@ struct Batch {
       return DPC_ERR_ARG;
     }
     if (todev) {
-      if (!segment_ok(p)) return DPC_ERR_ARG;
+      if (!(d.flags & DPC_F_SEQ2) && !segment_ok(p)) return DPC_ERR_ARG;
       h.dev = (int32_t)dprobs.size();
       dprobs.grow(1);
       dev2host.push_back((uint32_t)probs.size());
@@ -689,6 +719,49 @@ struct Batch {
       emit(out, sL.p + first, sL.n - first, five);                     /* end5: List_reverse again 5283; end3: as is 5740 */
       break;
     }
+    case DPC_END5_SPLICEJUNCTION: case DPC_END3_SPLICEJUNCTION: {
+      /* traceback_local twice (2875-2969): columns above contlength carry the far offset, then the known
+         gapholder, then the rest with the anchor offset.  An iteration of the reference emits one aligned column
+         and the gap run that follows it, so the split can only fall before an aligned column. */
+      const bool five = p.kind == DPC_END5_SPLICEJUNCTION;
+      const int endc = p.length2R;
+      char *qa = fit(s.qa, h.L1), *ga = fit(s.ga, h.L2);
+      for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
+      for (int k = 0; k < h.L2; k++) ga[k] = (char)dpc_code_char(pool[h.q1 + (uint32_t)k]);
+      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 4); sL.n = 0;
+      std::vector<uint16_t> part;
+      const int nops = dr.nopsL;
+      int r = dr.bestrL, c = dr.bestcL, k = 0, used = 0;                /* used: columns of run k taken by the first call */
+      while (k < nops && c > endc) {
+        const int op = ops[k] & 3, len = ops[k] >> 2;
+        if (op == DPC_OP_M) {
+          const int take = len < c - endc ? len : c - endc;
+          part.push_back((uint16_t)((take << 2) | DPC_OP_M));
+          r -= take; c -= take;
+          if (take < len) { used = take; break; }                      /* the rest of this run belongs to the second call */
+          k++;
+          if (k < nops && (ops[k] & 3) != DPC_OP_M) {                   /* the gap run after the run's last column */
+            part.push_back(ops[k]);
+            if ((ops[k] & 3) == DPC_OP_QSKIP) r -= ops[k] >> 2; else c -= ops[k] >> 2;
+            k++;
+          }
+        } else {
+          part.push_back(ops[k]);
+          if (op == DPC_OP_QSKIP) r -= len; else c -= len;
+          k++;
+        }
+      }
+      replay(sL, part.data(), (int)part.size(), dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2R, five, false, p.dynprogindex, true);
+      sL.push(0, five ? p.offset2 - p.offset2R : p.offset2R - p.offset2, ' ', ' ', ' ', 0, 2);   /* 5518, 5977 */
+      part.clear();
+      if (used > 0) { part.push_back((uint16_t)((((ops[k] >> 2) - used) << 2) | DPC_OP_M)); k++; }
+      for (; k < nops; k++) part.push_back(ops[k]);
+      replay(sL, part.data(), (int)part.size(), r, c, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex, true);
+      int first = 0;                                                   /* 5541-5544, 6000-6003 */
+      while (first < sL.n && sL.p[first].comp == '-') first++;
+      emit(out, sL.p + first, sL.n - first, five);                     /* end5: List_reverse again 5551; end3: as is 6011 */
+      break;
+    }
     case DPC_GENOME_GAP: {
       if (!(dr.status & DPC_ST_OK)) break;
       const int L1 = p.length1, L2L = p.length2, L2R = p.length2R, revoffset1 = p.offset1 + L1 - 1;
@@ -769,6 +842,11 @@ struct Batch {
         r.finalscore = 0; npairs = 0;                                  /* 5259-5262 */
       } else if (!star) npairs = pushed;                               /* a leading '-' needs a skipped '*' column before it */
       break;
+    case DPC_END5_SPLICEJUNCTION: case DPC_END3_SPLICEJUNCTION:
+      r.nmatches = dr.nmatches; r.nmismatches = dr.nmismatches; r.nopens = dr.nopens; r.nindels = dr.nindels;
+      r.finalscore = 3 * dr.nmatches - 5 * dr.nmismatches - 12 * dr.nopens - dr.nindels;      /* 5537, 5996 */
+      r.dynprogindex_out = bump(p.dynprogindex);
+      break;                                                           /* npairs: counted by rebuilding */
     case DPC_GENOME_GAP: {
       r.finalscore = dr.finalscore;
       r.introntype = ((dr.status & DPC_ST_HAVE) && !p.use_probabilities_p) ? dr.introntype : DPC_UNSET;

@@ -11,6 +11,8 @@
  *   Dynprog_genome_gap   dynprog.c:4798
  *   Dynprog_end5_gap     dynprog.c:5094
  *   Dynprog_end3_gap     dynprog.c:5556
+ *   Dynprog_end5_splicejunction  dynprog.c:5411   (called by Splicetrie_solve_end5, splicetrie.c:352, 447, once per
+ *   Dynprog_end3_splicejunction  dynprog.c:5869    known far splice site: runs with a known-splicing file, gmap -s)
  *
  * The originals stay linked under the names <name>_cpu (objcopy --redefine-sym, or eight #defines on top of
  * dynprog.c) because Dynprog_init/_setup must still run for the solvers this library does not replace
@@ -425,6 +427,7 @@ static int
 dropin_memo_spans (const dpc_problem_t *p, const char **a, int *na, const char **b, int *nb) {
   *a = *b = NULL; *na = *nb = 0;
   if (p->seq1 == NULL || p->length1 <= 0 || p->length1 > 4096) return 0;
+  if (p->kind == DPC_END5_SPLICEJUNCTION || p->kind == DPC_END3_SPLICEJUNCTION) return 0;   /* every call has its own junction string */
   if (p->kind == DPC_END5_GAP) { *a = p->seq1 - (p->length1 - 1); *na = p->length1; }
   else { *a = p->seq1; *na = p->length1; }
   if (p->kind == DPC_CDNA_GAP) {
@@ -517,7 +520,9 @@ dropin_push_pairs (const dpc_pair_t *rec, int n, int dynprogindex, Pairpool_T pa
   int i;
   for (i = n - 1; i >= 0; i--) {
     const dpc_pair_t *q = &rec[i];
-    if (q->gapp) {
+    if (q->gapp == 2) {		/* the known gapholder of the splice-junction solvers, dynprog.c:5518, 5977 */
+      pairs = Pairpool_push_gapholder(pairs,pairpool,/*queryjump*/q->querypos,/*genomejump*/q->genomepos,/*knownp*/true);
+    } else if (q->gapp) {
       pairs = Pairpool_push_gapholder(pairs,pairpool,/*queryjump*/UNKNOWNJUMP,/*genomejump*/UNKNOWNJUMP,/*knownp*/false);
     } else {
       pairs = Pairpool_push(pairs,pairpool,q->querypos,q->genomepos,q->cdna,q->comp,q->genome,dynprogindex);
@@ -751,4 +756,63 @@ Dynprog_end3_gap (int *dynprogindex, int *finalscore, int *nmatches, int *nmisma
   return dropin_end_gap(DPC_END3_GAP,dynprogindex,finalscore,nmatches,nmismatches,nopens,nindels,sequence1,
 			length1,length2,offset1,offset2,chroffset,chrhigh,chrpos,genomiclength,
 			cdna_direction,watsonp,jump_late_p,pairpool,extraband_end,defect_rate,endalign);
+}
+
+
+static List_T
+dropin_splicejunction (int kind, int *dynprogindex, int *finalscore, int *nmatches, int *nmismatches,
+		       int *nopens, int *nindels, char *sequence1, char *sequence2,
+		       int length1, int length2, int offset1, int offset2_anchor, int offset2_far,
+		       Genomicpos_T chroffset, Genomicpos_T chrhigh,
+		       Genomicpos_T chrpos, Genomicpos_T genomiclength,
+		       int cdna_direction, bool watsonp, bool jump_late_p, Pairpool_T pairpool,
+		       int extraband_end, double defect_rate, int contlength) {
+  dpc_problem_t p;
+  dpc_result_t r;
+  List_T pairs;
+
+  dropin_common(&p,kind,*dynprogindex,chroffset,chrhigh,chrpos,genomiclength,
+		cdna_direction,watsonp,jump_late_p,extraband_end,defect_rate);
+  p.seq1 = sequence1; p.seq1R = sequence2;	/* the splice-junction string travels as characters */
+  p.length1 = length1; p.length2 = length2; p.length2R = contlength;
+  p.offset1 = offset1; p.offset2 = offset2_anchor; p.offset2R = offset2_far;
+  pairs = dropin_solve(&r,&p,pairpool);
+  OUT(finalscore,r.finalscore);
+  OUT(nmatches,r.nmatches); OUT(nmismatches,r.nmismatches); OUT(nopens,r.nopens); OUT(nindels,r.nindels);
+  *dynprogindex = r.dynprogindex_out;
+  return pairs;
+}
+
+List_T
+Dynprog_end5_splicejunction (int *dynprogindex, int *finalscore, int *nmatches, int *nmismatches,
+			     int *nopens, int *nindels, Dynprog_T dynprog,
+			     char *revsequence1, char *revsequenceuc1,
+			     char *revsequence2, char *revsequenceuc2,
+			     int length1, int length2, int revoffset1, int revoffset2_anchor, int revoffset2_far,
+			     Genomicpos_T chroffset, Genomicpos_T chrhigh,
+			     Genomicpos_T chrpos, Genomicpos_T genomiclength,
+			     int cdna_direction, bool watsonp, bool jump_late_p, Pairpool_T pairpool,
+			     int extraband_end, double defect_rate, int contlength) {
+  (void) dynprog; (void) revsequenceuc1; (void) revsequenceuc2;
+  return dropin_splicejunction(DPC_END5_SPLICEJUNCTION,dynprogindex,finalscore,nmatches,nmismatches,nopens,nindels,
+			       revsequence1,revsequence2,length1,length2,revoffset1,revoffset2_anchor,revoffset2_far,
+			       chroffset,chrhigh,chrpos,genomiclength,cdna_direction,watsonp,jump_late_p,pairpool,
+			       extraband_end,defect_rate,contlength);
+}
+
+List_T
+Dynprog_end3_splicejunction (int *dynprogindex, int *finalscore, int *nmatches, int *nmismatches,
+			     int *nopens, int *nindels, Dynprog_T dynprog,
+			     char *sequence1, char *sequenceuc1,
+			     char *sequence2, char *sequenceuc2,
+			     int length1, int length2, int offset1, int offset2_anchor, int offset2_far,
+			     Genomicpos_T chroffset, Genomicpos_T chrhigh,
+			     Genomicpos_T chrpos, Genomicpos_T genomiclength,
+			     int cdna_direction, bool watsonp, bool jump_late_p, Pairpool_T pairpool,
+			     int extraband_end, double defect_rate, int contlength) {
+  (void) dynprog; (void) sequenceuc1; (void) sequenceuc2;
+  return dropin_splicejunction(DPC_END3_SPLICEJUNCTION,dynprogindex,finalscore,nmatches,nmismatches,nopens,nindels,
+			       sequence1,sequence2,length1,length2,offset1,offset2_anchor,offset2_far,
+			       chroffset,chrhigh,chrpos,genomiclength,cdna_direction,watsonp,jump_late_p,pairpool,
+			       extraband_end,defect_rate,contlength);
 }

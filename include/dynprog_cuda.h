@@ -14,6 +14,8 @@
  *   Dynprog_genome_gap    dynprog.h:99-117       dpc_add(kind=DPC_GENOME_GAP)
  *   Dynprog_end5_gap      dynprog.h:119-132      dpc_add(kind=DPC_END5_GAP)
  *   Dynprog_end3_gap      dynprog.h:148-161      dpc_add(kind=DPC_END3_GAP)
+ *   Dynprog_end5_splicejunction dynprog.h:134-146   dpc_add(kind=DPC_END5_SPLICEJUNCTION)   
+ *   Dynprog_end3_splicejunction dynprog.h:163-175   dpc_add(kind=DPC_END3_SPLICEJUNCTION)
  *   (List_T of Pair_T via Pairpool_push)         dpc_pairs (flat dpc_pair_t records,
  *                                                in the order of the returned List_T)
  *
@@ -50,7 +52,8 @@ enum { DPC_MODE_STANDARD = 0, DPC_MODE_CMET_STRANDED = 1, DPC_MODE_CMET_NONSTRAN
        DPC_MODE_ATOI_STRANDED = 3, DPC_MODE_ATOI_NONSTRANDED = 4 };
 
 /* which solver a problem is for */
-enum { DPC_SINGLE_GAP = 0, DPC_GENOME_GAP = 1, DPC_CDNA_GAP = 2, DPC_END5_GAP = 3, DPC_END3_GAP = 4 };
+enum { DPC_SINGLE_GAP = 0, DPC_GENOME_GAP = 1, DPC_CDNA_GAP = 2, DPC_END5_GAP = 3, DPC_END3_GAP = 4,
+       DPC_END5_SPLICEJUNCTION = 5, DPC_END3_SPLICEJUNCTION = 6 };
 
 /* error codes (negative return values) */
 enum {
@@ -78,6 +81,13 @@ enum {
  *  offset2     offset2       offset2L          offset2           revoffset2      offset2
  *  offset2R    -             revoffset2R       -                 -               -
  *  extraband   _single       _paired           _paired           _end            _end
+ *
+ * The two splice-junction solvers (Dynprog_end5/3_splicejunction, dynprog.c:5411-5552, 5869-6012: an end of the
+ * query against the string Splicetrie builds from the anchor exon and one known far splice site) use the END5 /
+ * END3 columns with three differences: the genomic side IS passed as characters, because it is not a contiguous
+ * piece of the genome -- seq1R = (rev)sequence2, length2 its length, upper-case A C G T N only; offset2 =
+ * (rev)offset2_anchor, offset2R = (rev)offset2_far; length2R = contlength.  endalign is ignored (the reference
+ * always runs find_best_endpoint_to_queryend_indels here).
  *
  * "rev" pointers follow the reference convention: they point at the LAST
  * character and are indexed with non-positive offsets (dynprog.c:1674).
@@ -131,9 +141,11 @@ typedef struct dpc_result {
 
 /* One rebuilt Pair (pairdef.h:10-47), only the fields Pairpool_push /
  * Pairpool_push_gapholder set to something other than their constants
- * (pairpool.c:169-215, 352-401).  gapp != 0 is a gapholder: querypos =
+ * (pairpool.c:169-215, 352-401).  gapp == 1 is a gapholder: querypos =
  * genomepos = -1, chars ' ', queryjump = genomejump = DPC_UNKNOWNJUMP,
- * dynprogindex 0. */
+ * dynprogindex 0.  gapp == 2 is the KNOWN gapholder of the splice-junction solvers
+ * (Pairpool_push_gapholder(..., queryjump, genomejump, knownp = true), dynprog.c:5518): querypos carries
+ * queryjump (0) and genomepos carries genomejump. */
 typedef struct dpc_pair {
   int32_t querypos;
   int32_t genomepos;

@@ -30,7 +30,7 @@ cp gmap "$OUT/gmap_ref"
 
 CC="${CC:-gcc}"
 CFLAGS=(-DHAVE_CONFIG_H -I. -mpopcnt '-DTARGET="x86_64-unknown-linux-gnu"' '-DGMAPDB="/usr/share/gmapdb"' -O3)
-SYMS="Dynprog_init Dynprog_setup Dynprog_term Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap"
+SYMS="Dynprog_init Dynprog_setup Dynprog_term Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap Dynprog_end5_splicejunction Dynprog_end3_splicejunction"
 ARGS=""; for s in $SYMS; do ARGS="$ARGS --redefine-sym $s=${s}_cpu"; done
 objcopy $ARGS gmap-dynprog.o cuda-dynprog_cpu.o
 $CC "${CFLAGS[@]}" -I"$REPO/include" -Wall -c "$REPO/gmap-gsnap_b200/host/dynprog_dropin.c" -o cuda-dynprog_dropin.o

@@ -233,15 +233,18 @@ typedef struct { int nmatches, nmismatches, nopens, nindels; } Counts;
  * index i (0-based, matrix order) of the query sits at q0 + qs*i, of the
  * genome at g0 + gs*i, with qs = gs = -1 for the "rev" callers.
  * genome_rows != 0 is the cDNA layout (rows = genome). */
-static void traceback(Stack *st, Counts *ct, const Mat *m, int r, int c,
-                      const char *qch, const char *gch, int q0, int g0, int revp, int genome_rows,
-                      int cdna_direction, int idx) {
-  int step = revp ? -1 : 1;
-  while (m->dN[AT(m, r, c)] != D_STOP) {
+/* endc < 0: traceback / traceback_cdna, which stop on a STOP direction.  endc >= 0: traceback_local (2875-2969),
+ * which runs while c > endc, has no '*' test, and hands the reached (r,c) back through rp / cp. */
+static void traceback_from(Stack *st, Counts *ct, const Mat *m, int *rp, int *cp, int endc,
+                           const char *qch, const char *gch, int q0, int g0, int revp, int genome_rows,
+                           int cdna_direction, int idx) {
+  int step = revp ? -1 : 1, r = *rp, c = *cp;
+  const int local = endc >= 0;
+  while (local ? c > endc : m->dN[AT(m, r, c)] != D_STOP) {
     int qi = genome_rows ? c - 1 : r - 1, gi = genome_rows ? r - 1 : c - 1;
     char c1 = qch[qi], c2 = gch[gi];
     int consistent = genome_rows ? CONS[c2 & 127][c1 & 127] : CONS[c1 & 127][c2 & 127];   /* 2654 vs 2752 */
-    if (!genome_rows && c2 == '*') {
+    if (!genome_rows && !local && c2 == '*') {
       /* 2644: no pair past the end of the chromosome (traceback_cdna has no such test) */
     } else if (query_uc(c1) == c2) { ct->nmatches++; push(st, q0 + step * qi, g0 + step * gi, c1, '*', c2, idx, 0); }
     else if (consistent) { ct->nmatches++; push(st, q0 + step * qi, g0 + step * gi, c1, ':', c2, idx, 0); }
@@ -290,6 +293,13 @@ static void traceback(Stack *st, Counts *ct, const Mat *m, int r, int c,
       ct->nopens++; ct->nindels += dist;
     }
   }
+  *rp = r; *cp = c;
+}
+
+static void traceback(Stack *st, Counts *ct, const Mat *m, int r, int c,
+                      const char *qch, const char *gch, int q0, int g0, int revp, int genome_rows,
+                      int cdna_direction, int idx) {
+  traceback_from(st, ct, m, &r, &c, -1, qch, gch, q0, g0, revp, genome_rows, cdna_direction, idx);
 }
 
 static void traceback_nogaps(Stack *st, Counts *ct, int r, int c, const char *qch, const char *gch,
@@ -425,6 +435,36 @@ static int solve_end(const dpc_problem_t *p, dpc_result_t *res, Stack *out, int 
     else emit(out, st.v + first, st.n - first, 0);        /* returned as is, 5740 */
     res->npairs = st.n - first;
   }
+  res->null_list = res->npairs == 0;
+  free(st.v);
+  return 0;
+}
+
+/* Dynprog_end5_splicejunction 5411-5552 / Dynprog_end3_splicejunction 5869-6012: an end of the query against the
+ * splice-junction string (seq1R, use_genomicseg_p); end point on the last row; traceback_local down to contlength
+ * (length2R) with the far offset (offset2R), the known gapholder, traceback_local to column 0 with the anchor
+ * offset (offset2); the score is recomputed from the counts. */
+static int solve_splicejunction(const dpc_problem_t *p, dpc_result_t *res, Stack *out, int five) {
+  int L1 = p->length1, L2 = p->length2, br, bc, score;
+  int late = five ? !p->jump_late_p : p->jump_late_p;     /* 5504 vs 5964 */
+  if (L1 <= 0 || L1 > g_maxlength1 || L2 <= 0 || L2 > g_maxlength2) {    /* 5452-5465 */
+    res->nmatches = res->nmismatches = res->nopens = res->nindels = 0; res->finalscore = 0; return 0;
+  }
+  Counts ct = { 0, 0, 0, 0 }; Stack st = { 0, 0, 0 }; Mat m; memset(&m, 0, sizeof m);
+  char *q = gather_query(p->seq1, L1, five), *g = gather_query(p->seq1R, L2, five);
+  fill(&m, L1, L2, q, g, 1, ENDQ, -12, -1, p->extraband, 1, late);
+  best_endpoint_queryend(&score, &br, &bc, &m, L1, L2, p->extraband, late);
+  traceback_from(&st, &ct, &m, &br, &bc, p->length2R, q, g, p->offset1, p->offset2R, five, 0, p->cdna_direction, p->dynprogindex);
+  push(&st, 0, five ? p->offset2 - p->offset2R : p->offset2R - p->offset2, ' ', ' ', ' ', 0, 2);   /* 5518, 5977 */
+  traceback_from(&st, &ct, &m, &br, &bc, 0, q, g, p->offset1, p->offset2, five, 0, p->cdna_direction, p->dynprogindex);
+  mat_free(&m); free(q); free(g);
+  res->finalscore = ct.nmatches * 3 + ct.nmismatches * -5 + ct.nopens * -12 + ct.nindels * -1;      /* 5537, 5996 */
+  res->nmatches = ct.nmatches; res->nmismatches = ct.nmismatches; res->nopens = ct.nopens; res->nindels = ct.nindels;
+  res->dynprogindex_out = bump(p->dynprogindex);
+  int first = 0;                                          /* 5541-5544 */
+  while (first < st.n && st.v[first].comp == '-') first++;
+  emit(out, st.v + first, st.n - first, five);            /* 5551 vs 6011 */
+  res->npairs = st.n - first;
   res->null_list = res->npairs == 0;
   free(st.v);
   return 0;
@@ -703,6 +743,8 @@ int port_solve(const dpc_problem_t *problems, int n, dpc_result_t *results,
     case DPC_CDNA_GAP: rc = solve_cdna(p, &results[i], &out); break;
     case DPC_END5_GAP: rc = solve_end(p, &results[i], &out, 1); break;
     case DPC_END3_GAP: rc = solve_end(p, &results[i], &out, 0); break;
+    case DPC_END5_SPLICEJUNCTION: rc = solve_splicejunction(p, &results[i], &out, 1); break;
+    case DPC_END3_SPLICEJUNCTION: rc = solve_splicejunction(p, &results[i], &out, 0); break;
     default: rc = DPC_ERR_ARG;
     }
     if (rc != 0) { free(out.v); return rc; }

@@ -216,6 +216,22 @@ static List_T call_one(Worker *w, const dpc_problem_t *p, dpc_result_t *r) {
                              p->cdna_direction, p->watsonp, p->jump_late_p, w->pool,
                              p->extraband, p->defect_rate, (Endalign_T)p->endalign, /*use_genomicseg_p*/ false);
     break;
+  case DPC_END5_SPLICEJUNCTION:       /* seq1R = revsequence2 (already upper case), offset2R = revoffset2_far, length2R = contlength */
+    pairs = Dynprog_end5_splicejunction(&idx, &finalscore, &nmatches, &nmismatches, &nopens, &nindels, w->M,
+                                        (char *)p->seq1, uc_rev(w->uc, p->seq1, len1), (char *)p->seq1R, (char *)p->seq1R,
+                                        p->length1, p->length2, p->offset1, p->offset2, p->offset2R,
+                                        p->chroffset, p->chrhigh, p->chrpos, p->genomiclength,
+                                        p->cdna_direction, p->watsonp, p->jump_late_p, w->pool,
+                                        p->extraband, p->defect_rate, /*contlength*/ p->length2R);
+    break;
+  case DPC_END3_SPLICEJUNCTION:
+    pairs = Dynprog_end3_splicejunction(&idx, &finalscore, &nmatches, &nmismatches, &nopens, &nindels, w->M,
+                                        (char *)p->seq1, uc_fwd(w->uc, p->seq1, len1), (char *)p->seq1R, (char *)p->seq1R,
+                                        p->length1, p->length2, p->offset1, p->offset2, p->offset2R,
+                                        p->chroffset, p->chrhigh, p->chrpos, p->genomiclength,
+                                        p->cdna_direction, p->watsonp, p->jump_late_p, w->pool,
+                                        p->extraband, p->defect_rate, /*contlength*/ p->length2R);
+    break;
   default:
     break;
   }
@@ -248,6 +264,9 @@ int ref_solve(const dpc_problem_t *problems, int n, dpc_result_t *results,
         dpc_pair_t *o = &pairs[used];
         o->querypos = pr->querypos; o->genomepos = (int32_t)pr->genomepos; o->dynprogindex = pr->dynprogindex;
         o->cdna = pr->cdna; o->comp = pr->comp; o->genome = pr->genome; o->gapp = pr->gapp;
+        if (pr->gapp && pr->knowngapp) {      /* the known gapholder of the splice-junction solvers (dynprog.c:5518) */
+          o->gapp = 2; o->querypos = pr->queryjump; o->genomepos = pr->genomejump;
+        }
       }
       used++;
     }

@@ -86,8 +86,11 @@ int dpc_add(dpc_ctx_t *c, const dpc_problem_t *q) {
   }
   dpc_problem_t *d = &c->p[c->n];
   *d = *q;
-  d->seq1 = copy_seq(q->seq1, q->length1, q->kind == DPC_END5_GAP, &c->own[2 * c->n]);
+  const int five = q->kind == DPC_END5_GAP || q->kind == DPC_END5_SPLICEJUNCTION;
+  d->seq1 = copy_seq(q->seq1, q->length1, five, &c->own[2 * c->n]);
   if (q->kind == DPC_CDNA_GAP) d->seq1R = copy_seq(q->seq1R, q->length1R, 1, &c->own[2 * c->n + 1]);
+  if (q->kind == DPC_END5_SPLICEJUNCTION || q->kind == DPC_END3_SPLICEJUNCTION)
+    d->seq1R = copy_seq(q->seq1R, q->length2, five, &c->own[2 * c->n + 1]);
   return c->n++;
 }
 

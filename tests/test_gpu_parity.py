@@ -188,3 +188,14 @@ def test_full_size_exact_against_compiled_reference(kind, n):
         assert not api.compare(*ref.solve(head), *lib.solve(head), rtol=RTOL)
     finally:
         lib.close()
+
+
+def test_splicejunction_solvers(workload, ref, port, cuda, fill_mode):
+    """Dynprog_end5/3_splicejunction: junction string as characters, end point on the last
+    row, two-part traceback around the known gapholder; against the compiled reference and the restatement."""
+    probs = workload.splicejunction_gaps(6000, seed=31, len_hi=100)
+    got = cuda.solve(probs)
+    assert not api.compare(*ref.solve(probs), *got)
+    assert not api.compare(*port.solve(probs), *got)
+    mixed = np.concatenate([probs[:500], workload.end_gaps(500, seed=32), workload.single_gaps(500, seed=33)])
+    assert not api.compare(*port.solve(mixed), *cuda.solve(mixed))

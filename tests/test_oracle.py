@@ -142,3 +142,45 @@ def test_pairdistance_matches_compiled_reference(ref):
     for i in range(128):
         for j in range(128):
             assert ref.lib.ref_pairdistance(i, j) == lib.lib.dpc_pairdistance(0, i, j)   # Dynprog_pairdistance = HIGHQ table
+
+
+# ---- Dynprog_end5/3_splicejunction (kinds 5, 6) -------------------------------------------
+def test_splicejunction_restatement_matches_compiled_reference(workload, ref, port):
+    probs = workload.splicejunction_gaps(3000, seed=21)
+    want = ref.solve(probs)
+    assert (want[1]["gapp"] == 2).sum() == len(probs)            # one known gapholder per solution (dynprog.c:5518)
+    assert (want[1]["gapp"] == 1).sum() > 0                      # and some intron-like genome runs (2448-2507)
+    assert not api.compare(*want, *port.solve(probs))
+
+
+@pytest.mark.parametrize("fill", [0, 1], ids=["row_sweep_32_lanes", "memory_fill_1_lane"])
+def test_splicejunction_device_routines_on_cpu(workload, port, emul, fill):
+    probs = workload.splicejunction_gaps(3000, seed=22, len_hi=90)
+    emul.set_fill(fill)
+    try:
+        got = emul.solve(probs)
+    finally:
+        emul.set_fill(0)
+    assert not api.compare(*port.solve(probs), *got)
+
+
+def test_splicejunction_edges(workload, port, emul):
+    """contlength 0 / beyond the string, too-long inputs (early return without index bump, dynprog.c:5452-5465),
+    junction strings with a byte outside ACGTN (rejected by the library, never guessed)."""
+    probs = workload.splicejunction_gaps(64, seed=23)
+    probs["length2R"][:16] = 0
+    probs["length2R"][16:32] = probs["length2"][16:32] + 5
+    want = port.solve(probs)
+    assert not api.compare(*want, *emul.solve(probs))
+    big = probs[:4].copy()
+    big["length1"] = 700
+    w2, g2 = port.solve(big), emul.solve(big)
+    assert not api.compare(*w2, *g2)
+    assert (w2[0]["null_list"] == 1).all() and (w2[0]["finalscore"] == 0).all()
+    assert (w2[0]["dynprogindex_out"] == big["dynprogindex"]).all()
+    bad = probs[32:33].copy()
+    import ctypes as C
+    addr = int(bad["seq1R"][0]) - (int(bad["length2"][0]) - 1 if int(bad["kind"][0]) == api.END5_SPLICEJUNCTION else 0)
+    C.memset(addr, ord("*"), 1)
+    with pytest.raises(RuntimeError):
+        emul.solve(bad)
