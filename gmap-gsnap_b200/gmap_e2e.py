@@ -40,6 +40,7 @@ def make_transcripts(chroms, n, seed, length=2000, sub=0.01, indel=0.002):
     indels, both strands.  The intron dinucleotides are planted in the genome (so call this BEFORE writing it)."""
     rng = np.random.default_rng(seed + 1)
     out = []
+    sites = []          # (chromosome index, 1-based last exon base, "donor") / (.., last intron base, "acceptor")
     acgt = np.frombuffer(b"ACGT", np.uint8)
     for t in range(n):
         c = int(rng.integers(0, len(chroms)))
@@ -58,7 +59,9 @@ def make_transcripts(chroms, n, seed, length=2000, sub=0.01, indel=0.002):
             if e < nex - 1:
                 g[pos:pos + 2] = (71, 84)                              # GT
                 g[pos + ilens[e] - 2:pos + ilens[e]] = (65, 71)         # AG
+                sites.append((c, pos, "donor"))
                 pos += int(ilens[e])
+                sites.append((c, pos, "acceptor"))
         s = np.concatenate(parts)
         u = rng.random(len(s))
         subs = u < sub
@@ -74,6 +77,7 @@ def make_transcripts(chroms, n, seed, length=2000, sub=0.01, indel=0.002):
         if t & 1:
             s2 = _COMP[s2[::-1]]
         out.append(s2)
+    make_transcripts.sites = sites
     return out
 
 
@@ -115,7 +119,7 @@ def build_db(workdir, genome_fa, dbname="synth", k=12):
     return b, dbname
 
 
-def prepare(workdir, genome_bases, n_chr, n_transcripts, seed=5):
+def prepare(workdir, genome_bases, n_chr, n_transcripts, seed=5, known_sites_frac=0.0):
     os.makedirs(workdir, exist_ok=True)
     chroms = make_genome(genome_bases, n_chr, seed)
     tx = make_transcripts(chroms, n_transcripts, seed)
@@ -125,8 +129,24 @@ def prepare(workdir, genome_bases, n_chr, n_transcripts, seed=5):
     write_fasta(qfa, ["t%d" % i for i in range(n_transcripts)], tx)
     t0 = time.time()
     dbdir, dbname = build_db(workdir, gfa)
-    return {"dbdir": dbdir, "dbname": dbname, "queries": qfa, "n": n_transcripts, "bases": int(sum(len(s) for s in tx)),
+    case = {"dbdir": dbdir, "dbname": dbname, "queries": qfa, "n": n_transcripts, "bases": int(sum(len(s) for s in tx)),
             "db_build_s": time.time() - t0}
+    if known_sites_frac > 0 and os.path.exists(os.path.join(BIN, "iit_store")):
+        # a known-splice-site map (gmap -s): the format gtf_splicesites / gff3_splicesites print, stored with iit_store
+        rng = np.random.default_rng(seed + 2)
+        txt = os.path.join(workdir, "sites.txt")
+        with open(txt, "w") as f:
+            for i, (c, pos, kind) in enumerate(make_transcripts.sites):
+                if rng.random() < known_sites_frac:
+                    f.write(">site%d chr%d:%d..%d %s\n" % (i, c + 1, pos, pos + 1, kind))
+        maps = os.path.join(dbdir, dbname, dbname + ".maps")
+        r = subprocess.run(f"cat {txt} | {BIN}/iit_store -o {maps}/sites.iit", shell=True, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("iit_store: " + r.stderr[-1000:])
+        # full path: this reference version dereferences a NULL user_splicingdir when the file is not found
+        # "locally" first (gmap.c:3287)
+        case["splicing"] = os.path.join(maps, "sites.iit")
+    return case
 
 
 def run_gmap(binary, case, threads, fibers=None, device=None, extra=(), out=None, timeout=3600):
@@ -138,6 +158,8 @@ def run_gmap(binary, case, threads, fibers=None, device=None, extra=(), out=None
         env["DPC_DEVICE"] = str(device)
     env["DPC_FIBER_STATS"] = "1"
     out = out or os.path.join(case["dbdir"], os.path.basename(binary) + ".out")
+    if case.get("splicing"):
+        extra = ("-s", case["splicing"], *extra)
     cmd = [os.path.join(REFDIR, binary), "-D", case["dbdir"], "-d", case["dbname"], "-t", str(threads), "-O", "-A", *extra, case["queries"]]
     import resource
     ru0 = resource.getrusage(resource.RUSAGE_CHILDREN)

@@ -224,7 +224,7 @@ typedef struct dropin_sched {
   void *(*start_routine) (void *);
   void *arg;
   int nexcept;			/* Except_stack_create calls outstanding on this OS thread */
-  long nrounds, nproblems;
+  long nrounds, nproblems, njunction;	/* njunction: splice-junction solver calls among nproblems */
   double t_device, t_start;	/* seconds blocked in flush + wait; start of the scheduler (DPC_FIBER_STATS) */
   double t_add, t_post;		/* seconds in dpc_add; in dpc_result + dpc_pairs + Pairpool_push (DPC_FIBER_STATS) */
   int stats;
@@ -335,9 +335,9 @@ dropin_scheduler (void *data) {
   } while (live > 0);
 
   if (stats) {
-    fprintf(stderr,"libdynprog_cuda drop-in: %d fibers, %ld device batches, %ld gaps (%.1f per batch), %.2f s in flush+wait, %.2f s in add, %.2f s in result+pairs+push, of %.2f s; memo %ld hits, %ld misses\n",
+    fprintf(stderr,"libdynprog_cuda drop-in: %d fibers, %ld device batches, %ld gaps (%.1f per batch), %.2f s in flush+wait, %.2f s in add, %.2f s in result+pairs+push, of %.2f s; memo %ld hits, %ld misses; %ld splice-junction solves\n",
 	    s->nfibers,s->nrounds,s->nproblems,s->nrounds ? (double) s->nproblems/(double) s->nrounds : 0.0,
-	    s->t_device,s->t_add,s->t_post,dropin_now() - s->t_start,dropin_memo_hits,dropin_memo_misses);
+	    s->t_device,s->t_add,s->t_post,dropin_now() - s->t_start,dropin_memo_hits,dropin_memo_misses,s->njunction);
   }
   for (i = 0; i < s->nfibers; i++) munmap(s->fibers[i].stack,FIBER_STACK_BYTES);
   dpc_ctx_free(s->ctx[0]); dpc_ctx_free(s->ctx[1]);
@@ -563,6 +563,7 @@ dropin_solve (dpc_result_t *r, const dpc_problem_t *p, Pairpool_T pairpool) {
     ctx = s->ctx[s->fill];
     if ((ticket = dpc_add(ctx,p)) < 0) dropin_fatal("dpc_add",ticket);
     s->npending++;
+    if (p->kind == DPC_END5_SPLICEJUNCTION || p->kind == DPC_END3_SPLICEJUNCTION) s->njunction++;
     f->state = FIBER_PARKED;
     if (s->stats) s->t_add += dropin_now() - t0;
     dropin_to_scheduler(s,f);

@@ -46,10 +46,10 @@ OBJS=$(ls gmap-*.o | grep -v -e '^gmap-dynprog.o$' -e '^gmap-gmap.o$')
 $CC -O3 -o "$OUT/gmap_cuda" $OBJS cuda-dynprog_cpu.o cuda-dynprog_dropin.o cuda-gmap.o \
     -L"$REPO/gmap-gsnap_b200/csrc" -ldynprog_cuda -Wl,-rpath,'$ORIGIN/../../gmap-gsnap_b200/csrc' -lz -lm -lpthread
 # index-building tools of the reference (for the whole-program bench on a synthetic genome database, BASELINE config 5)
-make -j"$(nproc)" gmapindex >> make.log 2>&1
+make -j"$(nproc)" gmapindex iit_store >> make.log 2>&1
 (cd ../util && make -s fa_coords gmap_process gmap_build >> ../src/make.log 2>&1)
 mkdir -p "$OUT/bin"
-cp gmapindex ../util/fa_coords ../util/gmap_process ../util/gmap_build "$OUT/bin/"
+cp gmapindex iit_store ../util/fa_coords ../util/gmap_process ../util/gmap_build "$OUT/bin/"
 # measurement scaffolding: the unmodified reference with a timer around its five gap-fill solvers
 ARGS5=""; for s in Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap; do ARGS5="$ARGS5 --redefine-sym $s=${s}_cpu"; done
 objcopy $ARGS5 gmap-dynprog.o timed-dynprog_cpu.o

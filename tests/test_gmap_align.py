@@ -183,3 +183,48 @@ def test_database_run_with_fibers_identical_to_reference(tmp_path):
     _, got_out, err = g.run_gmap("gmap_cuda", case, 4, fibers=16)
     assert filecmp.cmp(ref_out, got_out, shallow=False)
     assert "device batches" in err
+
+
+def _known_splicing_case(tmp_path):
+    from gmap_gsnap_b200 import gmap_e2e as g
+    if not g.have_binaries() or not os.path.exists(os.path.join(g.BIN, "iit_store")):
+        pytest.skip("oracle/_ref binaries not built")
+    return g, g.prepare(str(tmp_path), 4_000_000, 4, 100, seed=13, known_sites_frac=0.7)
+
+
+def _junction_solves(err):
+    return sum(int(l.split("; ")[-1].split(" splice-junction")[0]) for l in err.splitlines() if "splice-junction solves" in l)
+
+
+def test_known_splicing_run_on_cpu_test_double(tmp_path):
+    """gmap -s <known splice sites>: Splicetrie_solve_end5/3 (splicetrie.c:306-520) call Dynprog_end5/3_splicejunction
+    once per candidate far site, and the genome gaps get their known-site rewards through the splice_known hook.
+    Host logic on the CPU test double; byte-identical to the unmodified reference."""
+    import filecmp
+    if not os.path.exists(os.path.join(MOCK, "libdynprog_cuda.so")) or not os.path.exists(os.path.join(REFDIR, "libdynprog_ref.so")):
+        pytest.skip("test double not built")
+    g, case = _known_splicing_case(tmp_path)
+    _, ref_out, _ = g.run_gmap("gmap_ref", case, 2)
+    old = os.environ.get("LD_LIBRARY_PATH")
+    os.environ["LD_LIBRARY_PATH"] = MOCK
+    try:
+        _, got_out, err = g.run_gmap("gmap_cuda", case, 2, fibers=8, out=os.path.join(str(tmp_path), "mock.out"))
+    finally:
+        if old is None:
+            del os.environ["LD_LIBRARY_PATH"]
+        else:
+            os.environ["LD_LIBRARY_PATH"] = old
+    assert filecmp.cmp(ref_out, got_out, shallow=False)
+    assert _junction_solves(err) > 0
+
+
+@pytest.mark.gpu
+def test_known_splicing_run_identical_to_reference(tmp_path):
+    """The same run with the real library: the splice-junction solvers (kinds 5/6) and the known-site genome gaps
+    on the GPU, inside an unmodified stage 3 / splicetrie."""
+    import filecmp
+    g, case = _known_splicing_case(tmp_path)
+    _, ref_out, _ = g.run_gmap("gmap_ref", case, 4)
+    _, got_out, err = g.run_gmap("gmap_cuda", case, 4, fibers=16)
+    assert filecmp.cmp(ref_out, got_out, shallow=False)
+    assert _junction_solves(err) > 0
