@@ -43,6 +43,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def int32_alu_gops():
+    """Measured throughput of the integer ALU pipe (VIMNMX / LOP3), giga lane-operations per second."""
+    path = os.path.join(ROOT, "profiles", "int32_peak_r1.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["max_xor_gops"])
+    return 148 * 64 * 1.965          # the same figure from the data sheet: 64 lanes per clock per SM
+
+
 def band_cells(probs):
     """In-band cells of every matrix, for single gaps: one matrix each."""
     L1 = probs["length1"].astype(np.int64)
@@ -351,8 +359,9 @@ def main():
                      "note": "fused fill+traceback keeps matrices and direction nibbles in shared memory; algorithmic HBM bytes are "
                              "descriptors, sequences and result records only, so the kernel is integer-ALU/latency bound (see alu_roofline)"},
         "alu_roofline": {"achieved_gcups_per_gpu": cells / (float(np.mean(ms)) * 1e-3) / 1e9,
-                         "peak_gcups": 148 * 64 * sm_max * 1e6 / 25 / 1e9,
-                         "note": "peak = 148 SMs x 64 int32 ALU lanes/clk x max SM clock / 25 ALU ops per cell (DESIGN.md)"},
+                         "peak_gcups": int32_alu_gops() / 25,
+                         "note": "peak = measured integer-ALU-pipe throughput (tools/int_peak.cu on this pool's B200: 18.5 T "
+                                 "VIMNMX+LOP3 lane-ops/s = 63.7 per clock per SM, profiles/int32_peak_r1.json) / 25 ALU ops per cell (DESIGN.md)"},
     }
     line["roofline"]["achieved"] = algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9
     line["alu_roofline"]["frac"] = line["alu_roofline"]["achieved_gcups_per_gpu"] / line["alu_roofline"]["peak_gcups"]
