@@ -456,13 +456,16 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
         const int cL = rL - mL.lband + k, cR = rR - mR.lband + k;
         if (cL >= cloL && cL <= chighL && rR < p.gap - cL) {
           const int s = vL[u] - (int)((hL[u] >> k) & 1U) + itab[ldi[cL] & diR] + dR[u];
+          /* with one diagonal per lane (ln.n == 32, the GPU) a lane meets its candidates in ascending key order --
+             rows ascending, left scan before right scan -- so "first best" inside the lane is a strict comparison;
+             ties between lanes are settled by key afterwards.  A single lane walking all diagonals needs the key. */
           const int key = rL * 8192 + (cL - cloL);
-          if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+          if (ln.n == 32 ? s > best.score : dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
         }
         if (cR >= cloR && cR <= chighR && rL < p.gap - cR) {
           const int s = vR[u] - (int)((hR[u] >> k) & 1U) + itab[diL & rdi[cR]] + dL[u];
           const int key = rL * 8192 + nL + (cR - cloR);
-          if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+          if (ln.n == 32 ? s > best.score : dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
         }
       }
     }
