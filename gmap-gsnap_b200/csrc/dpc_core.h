@@ -69,7 +69,11 @@ struct DevProb {
   int8_t open, extend, reward, cdna_direction;
   uint8_t kind, endalign, type, pad;
   uint32_t flags;
+  uint32_t gout;            /* where the staged genome characters of this problem go in the output byte stream
+                               (the host rebuilds the Pair records from them instead of decoding the genome again) */
 };
+#define DPC_NO_GOUT 0xffffffffu
+DPC_HB uint32_t dpc_gout_span(int len) { return ((uint32_t)len + 7u) & ~7u; }     /* second span of a genome gap starts here */
 
 #define DPC_INLINE_OPS 38
 /* device-side result record, 128 bytes */
@@ -689,7 +693,9 @@ DPC_HD void dpc_emit_ops(DevRes *res, const uint16_t *opsL, int nL, const uint16
 template <class FILL, int KG>
 DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint32_t *blocks, const DevTables *tb,
                               uint8_t *arena, uint32_t arena_bytes, uint8_t *scratch, DevRes *res, const OvfArena &ovf,
-                              FILL &fill, const Lanes &ln) {
+                              uint8_t *gout, FILL &fill, const Lanes &ln) {
+  /* gout: output byte stream for the genome characters this problem stages (NULL or p.gout == DPC_NO_GOUT: none) */
+  uint8_t *const gch = (gout && p.gout != DPC_NO_GOUT) ? gout + p.gout : (uint8_t *)0;
   /* arena: this warp's shared-memory (or HBM) arena of arena_bytes; scratch: this problem's HBM scratch, used for
    * the bulk region when small + bulk does not fit the arena (the host sized both with the same dpc_layout) */
   /* FILL provides: fillmode (layout), operator() = the matrix fill, walk() = the traceback walk */
@@ -706,6 +712,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
     for (int i = ln.lane; i < n; i += ln.n) {
       int q = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
       int g = dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+      if (gch) gch[i] = (uint8_t)dpc_code_char(g);
       if (g == DPC_GSTAR) star++;
       else if (dpc_query_uc(q) == dpc_code_char(g)) nm++;
       else if ((tb->cons[q & 127] >> g) & 1) nm++;
@@ -736,7 +743,11 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         /* Dynprog_end5/3_splicejunction 5411-5552, 5869-6012: use_genomicseg_p, sequence2 = the splice-junction string */
         for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = pool[p.q1 + (uint32_t)i];
       } else {
-        for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+        for (int i = ln.lane; i < p.L2; i += ln.n) {
+          const int g = dpc_genomic_code(p, blocks, five ? p.off2 - i : p.off2 + i);
+          m0.colch[i] = (uint8_t)g;
+          if (gch) gch[i] = (uint8_t)dpc_code_char(g);
+        }
       }
       if (ln.lane == 0) m0.colch[p.L2] = 7;                               /* sentinel one past the last column */
       DPC_SYNC();
@@ -764,8 +775,16 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
           m0.rowch[i] = (uint8_t)qf; m1.rowch[i] = (uint8_t)qr;
           if (m0.planes || m1.planes) m0.prof[i] = dpc_pack_prof(score, qf);      /* m1 reads the same array backwards */
         }
-        for (int i = ln.lane; i < p.L2; i += ln.n) m0.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2 + i);
-        for (int i = ln.lane; i < p.L2R; i += ln.n) m1.colch[i] = (uint8_t)dpc_genomic_code(p, blocks, p.off2R - i);
+        for (int i = ln.lane; i < p.L2; i += ln.n) {
+          const int g = dpc_genomic_code(p, blocks, p.off2 + i);
+          m0.colch[i] = (uint8_t)g;
+          if (gch) gch[i] = (uint8_t)dpc_code_char(g);
+        }
+        for (int i = ln.lane; i < p.L2R; i += ln.n) {
+          const int g = dpc_genomic_code(p, blocks, p.off2R - i);
+          m1.colch[i] = (uint8_t)g;
+          if (gch) gch[dpc_gout_span(p.L2) + (uint32_t)i] = (uint8_t)dpc_code_char(g);
+        }
         if (ln.lane == 0) { m0.colch[p.L2] = 7; m1.colch[p.L2R] = 7; }    /* leftdi[length2L-1] = rightdi[length2R-1] = 0, 3354, 3376 */
       } else {
         /* Dynprog_cdna_gap 4577-4793: rows = genome (fwd from offset2 / rev from offset2+length2-1) */

@@ -221,6 +221,7 @@ struct HostProb {
   uint32_t aux;         /* pool offset of probability / known-site arrays */
   int32_t dev;          /* index into the device arrays, -1 when resolved on the host (early returns) */
   int32_t L1, L2;       /* lengths after clipping (end gaps) */
+  uint32_t gout;        /* offset of the device-staged genome characters in the returned byte stream, or DPC_NO_GOUT */
 };
 
 /* pair records are written through a bare cursor: every caller sizes the destination first */
@@ -312,8 +313,14 @@ struct Batch {
   const dpc_problem_t *ext; dpc_result_t *ext_res;
   std::vector<dpc_problem_t> own; std::vector<dpc_result_t> own_res;
 
-  Batch() : ext(NULL), ext_res(NULL) {}
-  void clear() { probs.clear(); pool.clear(); dprobs.clear(); dev2host.clear(); own.clear(); own_res.clear(); ext = NULL; ext_res = NULL; }
+  /* genome characters as the device staged them (one span per matrix), returned with the results: the rebuild reads
+     them instead of decoding the 2-bit genome a second time at an unpredictable address per problem */
+  uint32_t gout_total;
+  const uint8_t *gout_host;
+
+  Batch() : ext(NULL), ext_res(NULL), gout_total(8), gout_host(NULL) {}
+  void clear() { probs.clear(); pool.clear(); dprobs.clear(); dev2host.clear(); own.clear(); own_res.clear(); ext = NULL; ext_res = NULL;
+                 gout_total = 8; gout_host = NULL; }
   const dpc_problem_t &P(int i) const { return ext ? ext[i] : own[i]; }
   dpc_result_t &R(int i) { return ext_res ? ext_res[i] : own_res[i]; }
 
@@ -399,7 +406,7 @@ struct Batch {
     Globals &g = G();
     if (!g.inited || !g.setup_done) return DPC_ERR_STATE;
     HostProb h;
-    h.q0 = h.q1 = h.aux = 0; h.dev = -1; h.L1 = p.length1; h.L2 = p.length2;
+    h.q0 = h.q1 = h.aux = 0; h.dev = -1; h.L1 = p.length1; h.L2 = p.length2; h.gout = DPC_NO_GOUT;
     result_init(r, p);
     dprobs.reserve(dprobs.size() + 1);
     DevProb &d = dprobs.data()[dprobs.size()];      /* built in place; committed below when it goes to the device */
@@ -556,6 +563,11 @@ struct Batch {
     default:
       return DPC_ERR_ARG;
     }
+    d.gout = DPC_NO_GOUT;
+    if (todev && !(d.flags & DPC_F_SEQ2) && p.kind != DPC_CDNA_GAP) {
+      const uint32_t need = dpc_gout_span(d.L2) + (p.kind == DPC_GENOME_GAP ? dpc_gout_span(d.L2R) : 0u) + 8u;
+      if ((uint64_t)gout_total + need < 0xfff00000ull) { d.gout = h.gout = gout_total; gout_total += need; }
+    }
     if (todev) {
       if (!(d.flags & DPC_F_SEQ2) && !segment_ok(p)) return DPC_ERR_ARG;
       h.dev = (int32_t)dprobs.size();
@@ -656,7 +668,11 @@ struct Batch {
   static dpc_pair_t *fit(std::vector<dpc_pair_t> &v, int n) { if ((int)v.size() < n + 8) v.resize((size_t)n + 64); return v.data(); }
 
   /* The rebuild reads the genome at an unpredictable place per problem: ask for the lines ahead of time. */
+  const char *staged(const HostProb &h) const {
+    return (gout_host && h.gout != DPC_NO_GOUT) ? (const char *)gout_host + h.gout : NULL;
+  }
   void prefetch_genome(int i) const {
+    if (gout_host) return;
     const dpc_problem_t &p = P(i);
     const uint32_t *blocks = G().setup.genome_blocks;
     const uint32_t base = p.chroffset + p.chrpos;
@@ -691,11 +707,11 @@ struct Batch {
     const bool nostar = !(dr.status & DPC_ST_STAR);
     switch (p.kind) {
     case DPC_SINGLE_GAP: {
-      char *ga = fit(s.ga, h.L2);
+      const char *ga = staged(h);
 #ifdef DPC_PROFILE_REBUILD
       unsigned long long t0 = __rdtsc();
 #endif
-      gather_genome(p, blocks, p.offset2, h.L2, false, ga);
+      if (!ga) { char *buf = fit(s.ga, h.L2); gather_genome(p, blocks, p.offset2, h.L2, false, buf); ga = buf; }
 #ifdef DPC_PROFILE_REBUILD
       unsigned long long t1 = __rdtsc();
 #endif
@@ -708,9 +724,10 @@ struct Batch {
     }
     case DPC_END5_GAP: case DPC_END3_GAP: {
       const bool five = p.kind == DPC_END5_GAP;
-      char *qa = fit(s.qa, h.L1), *ga = fit(s.ga, h.L2);
+      char *qa = fit(s.qa, h.L1);
+      const char *ga = staged(h);
       for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
-      gather_genome(p, blocks, p.offset2, h.L2, five, ga);
+      if (!ga) { char *buf = fit(s.ga, h.L2); gather_genome(p, blocks, p.offset2, h.L2, five, buf); ga = buf; }
       Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0;
       replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex, nostar);
       if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) break;   /* 5259 */
@@ -765,10 +782,15 @@ struct Batch {
     case DPC_GENOME_GAP: {
       if (!(dr.status & DPC_ST_OK)) break;
       const int L1 = p.length1, L2L = p.length2, L2R = p.length2R, revoffset1 = p.offset1 + L1 - 1;
-      char *qb = fit(s.qb, L1), *ga = fit(s.ga, L2L), *gb = fit(s.gb, L2R);
+      char *qb = fit(s.qb, L1);
+      const char *ga = staged(h), *gb = ga ? ga + dpc_gout_span(L2L) : NULL;
       for (int k = 0; k < L1; k++) qb[k] = q[L1 - 1 - k];
-      gather_genome(p, blocks, p.offset2, L2L, false, ga);
-      gather_genome(p, blocks, p.offset2R, L2R, true, gb);
+      if (!ga) {
+        char *bufa = fit(s.ga, L2L), *bufb = fit(s.gb, L2R);
+        gather_genome(p, blocks, p.offset2, L2L, false, bufa);
+        gather_genome(p, blocks, p.offset2R, L2R, true, bufb);
+        ga = bufa; gb = bufb;
+      }
       Out sR, sL; sR.p = fit(s.sR, L1 + L2R + 2); sR.n = 0; sL.p = fit(s.sL, L1 + L2L + 2); sL.n = 0;
       replay(sR, ops + dr.nopsL, dr.nopsR, dr.bestrR, dr.bestcR, qb, gb, revoffset1, p.offset2R, true, false, p.dynprogindex, nostar);
       replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, q, ga, p.offset1, p.offset2, false, false, p.dynprogindex, nostar);

@@ -35,6 +35,7 @@ struct KernelArgs {
   DevRes *res;
   OvfArena ovf;
   uint8_t *scratch;            /* HBM arenas (SMEM == false) */
+  uint8_t *gout;               /* staged genome characters, returned to the host with the results */
   uint32_t arena_bytes;        /* per-warp shared-memory arena (SMEM == true) */
   unsigned int *counter;       /* dynamic work distribution */
 };
@@ -83,10 +84,10 @@ __global__ void __launch_bounds__(256, (KG == 0 ? DPC_MIN_BLOCKS_1M : 2)) dpc_so
     const uint32_t arena_bytes = SMEM ? a.arena_bytes : 0xffffffffu;
     if (GEN) {
       GenericFill fill;
-      dpc_solve_problem<GenericFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
+      dpc_solve_problem<GenericFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
     } else {
       RowFill fill;
-      dpc_solve_problem<RowFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, fill, ln);
+      dpc_solve_problem<RowFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
     }
     __syncwarp();
   }
@@ -213,13 +214,14 @@ struct Engine {
   bool live;
   Batch batch;
   DBuf<DevProb> d_probs;
-  DBuf<uint8_t> d_pool, d_scratch;
+  DBuf<uint8_t> d_pool, d_scratch, d_gout;
   DBuf<DevRes> d_res;
   DBuf<uint32_t> d_list;
   DBuf<uint16_t> d_ovf;
   DBuf<unsigned int> d_counters;
   PBuf<DevRes> h_res;
   PBuf<uint16_t> h_ovf;
+  PBuf<uint8_t> h_gout;
   PBuf<unsigned int> h_counters;
   PBuf<uint32_t> list;
   std::vector<uint16_t> cls;
@@ -242,7 +244,7 @@ struct Engine {
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     batch.pool.set_alloc(pinned()); batch.dprobs.set_alloc(pinned());
-    h_res.set_alloc(pinned()); h_ovf.set_alloc(pinned()); h_counters.set_alloc(pinned()); list.set_alloc(pinned());
+    h_res.set_alloc(pinned()); h_ovf.set_alloc(pinned()); h_gout.set_alloc(pinned()); h_counters.set_alloc(pinned()); list.set_alloc(pinned());
     live = true;
     return DPC_OK;
   }
@@ -250,7 +252,7 @@ struct Engine {
     if (!live) return;
     cudaSetDevice(device);
     cudaStreamSynchronize(stream);
-    d_probs.release(); d_pool.release(); d_scratch.release(); d_res.release(); d_list.release();
+    d_probs.release(); d_pool.release(); d_scratch.release(); d_gout.release(); d_res.release(); d_list.release();
     d_ovf.release(); d_counters.release();
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaStreamDestroy(stream);
     live = false;
@@ -276,7 +278,7 @@ struct Engine {
       a.probs = d_probs.p; a.list = d_list.p + L.list_off; a.n = L.n;
       a.pool = d_pool.p; a.blocks = d.d_blocks; a.tables = d.d_tables; a.res = d_res.p;
       a.ovf.ops = d_ovf.p; a.ovf.used = d_counters.p; a.ovf.cap = (unsigned int)ovf_cap;
-      a.scratch = d_scratch.p; a.arena_bytes = L.arena_bytes; a.counter = d_counters.p + 1 + k;
+      a.scratch = d_scratch.p; a.gout = d_gout.p; a.arena_bytes = L.arena_bytes; a.counter = d_counters.p + 1 + k;
       const int threads = L.wpb * 32;
       const size_t smem = L.smem ? (size_t)L.wpb * L.arena_bytes : 0;
       int per_sm = 1;
@@ -373,8 +375,10 @@ struct Engine {
     int rc;
     if ((rc = d_probs.need(n)) || (rc = d_pool.need(b.pool.size())) || (rc = d_res.need(n)) ||
         (rc = d_list.need(n)) || (rc = d_ovf.need(ovf_cap)) || (rc = d_counters.need(NCLASS * 3 + 2)) ||
-        (rc = d_scratch.need((size_t)scratch_total + 16)))
+        (rc = d_scratch.need((size_t)scratch_total + 16)) || (rc = d_gout.need((size_t)b.gout_total + 64)))
       return rc;
+    h_gout.clear(); h_gout.grow((size_t)b.gout_total + 64);
+    b.gout_host = NULL;
     h_res.clear(); h_res.grow(n);
     h_counters.clear(); h_counters.grow(NCLASS * 3 + 2);
     CK(cudaMemcpyAsync(d_probs.p, b.dprobs.data(), n * sizeof(DevProb), cudaMemcpyHostToDevice, stream));
@@ -384,7 +388,8 @@ struct Engine {
     if ((rc = launch_all()) != DPC_OK) return rc;
     CK(cudaMemcpyAsync(h_res.data(), d_res.p, n * sizeof(DevRes), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_counters.data(), d_counters.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-    d2h_bytes = (int64_t)(n * sizeof(DevRes) + sizeof(unsigned int));
+    CK(cudaMemcpyAsync(h_gout.data(), d_gout.p, b.gout_total, cudaMemcpyDeviceToHost, stream));
+    d2h_bytes = (int64_t)(n * sizeof(DevRes) + sizeof(unsigned int) + b.gout_total);
     return DPC_OK;
   }
 
@@ -402,6 +407,7 @@ struct Engine {
       CK(cudaSetDevice(device));
       CK(cudaStreamSynchronize(stream));
       CK(cudaEventElapsedTime(&ms_total, ev0, ev1));
+      b.gout_host = h_gout.data();
       unsigned int used = h_counters[0];
       if (used > 0) {
         if (used > ovf_cap) return DPC_ERR_NOMEM;

@@ -21,7 +21,8 @@ extern "C" int emul_setup(const dpc_setup_t *s) {
   return 0;
 }
 static int g_force_generic = 0;
-extern "C" int emul_set_fill(int force_generic) { g_force_generic = force_generic; return 0; }
+static int g_no_gout = 0;
+extern "C" int emul_set_fill(int force_generic) { g_force_generic = force_generic & 1; g_no_gout = (force_generic >> 1) & 1; return 0; }
 extern "C" int emul_pairdistance(int type, int c1, int c2) { return dpc::G().P[type & 3][c1 & 127][c2 & 127]; }
 
 extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *results,
@@ -39,6 +40,7 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
   GenericFill gfill;     /* single lane: memory-state fill + serial walk */
   RowFill rfill;         /* 32 simulated lanes: row-sweep fill + lane-parallel walk (dpc_vec.h host build) */
   std::vector<uint8_t> arena;
+  std::vector<uint8_t> gout((size_t)b.gout_total + 64, 0xEE);     /* the staged genome characters the device returns */
   b.pool_align(16);
   for (size_t k = 0; k < b.dprobs.size(); k++) {
     ArenaLayout a;
@@ -51,10 +53,11 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
     uint8_t *sbase = scratch.data() + ((16 - ((uintptr_t)scratch.data() & 15)) & 15);
     const uint32_t arena_bytes = (k & 1) ? a.total : a.small;
     if (g_force_generic)
-      dpc_solve_problem<GenericFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gfill, ln);
+      dpc_solve_problem<GenericFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), gfill, ln);
     else
-      dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, rfill, ln);
+      dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), rfill, ln);
   }
+  b.gout_host = g_no_gout ? NULL : gout.data();     /* NULL: the rebuild decodes the 2-bit genome itself (ticket users without the stream) */
   int64_t out = 0;
   dpc::Scratch sc;
   std::vector<dpc_pair_t> st;
@@ -95,6 +98,7 @@ extern "C" double emul_time_rebuild(const dpc_problem_t *problems, int n, int re
   Lanes ln; ln.lane = 0; ln.n = 1;
   RowFill rfill;
   std::vector<uint8_t> arena;
+  std::vector<uint8_t> gout((size_t)b.gout_total + 64, 0xEE);
   b.pool_align(16);
   for (size_t k = 0; k < b.dprobs.size(); k++) {
     ArenaLayout a;
@@ -102,8 +106,9 @@ extern "C" double emul_time_rebuild(const dpc_problem_t *problems, int n, int re
     arena.assign(a.total + 64, 0);
     uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
     memset(&dres[k], 0, sizeof(DevRes));
-    dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, a.total, base, &dres[k], ovf, rfill, ln);
+    dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, a.total, base, &dres[k], ovf, gout.data(), rfill, ln);
   }
+  b.gout_host = getenv("EMUL_NO_GOUT") ? NULL : gout.data();
   dpc::Scratch sc;
   int64_t total = 0;
   for (int i = 0; i < n; i++) if (b.probs[i].dev >= 0) { const DevRes &dr = dres[b.probs[i].dev]; b.finalize(i, dr, dr.nopsL + dr.nopsR > DPC_INLINE_OPS ? ovfbuf.data() + dr.ovf : dr.ops, sc); total += results[i].npairs; }

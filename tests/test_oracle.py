@@ -184,3 +184,16 @@ def test_splicejunction_edges(workload, port, emul):
     C.memset(addr, ord("*"), 1)
     with pytest.raises(RuntimeError):
         emul.solve(bad)
+
+
+def test_rebuild_without_the_staged_genome_stream(workload, port, emul):
+    """The Pair rebuild normally reads the genome characters the device staged and returned; without that stream it
+    decodes the 2-bit genome itself (gather_genome).  Both give the reference's records."""
+    probs = mixed_problems(workload, 800, 41, long_frac=0.03, long_hi=400)
+    probs = probs[probs["use_probabilities_p"] == 0]
+    emul.set_fill(2)            # bit 1: no staged-genome stream
+    try:
+        got = emul.solve(probs)
+    finally:
+        emul.set_fill(0)
+    assert not api.compare(*port.solve(probs), *got)
