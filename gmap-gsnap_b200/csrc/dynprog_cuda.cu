@@ -810,7 +810,8 @@ static void add_stats(const Engine &e, dpc_stats_t *out) {
   for (size_t i = 0; i < b.dprobs.size(); i++) {
     const DevProb &p = b.dprobs[i];
     if ((p.kind == DPC_END5_GAP || p.kind == DPC_END3_GAP) && p.endalign == DPC_QUERYEND_NOGAPS) {
-      out->fill_bytes += (int64_t)sizeof(DevProb) + 4 + p.L1 + (p.L2 + 3) / 4 + (int64_t)sizeof(DevRes);
+      out->fill_bytes += (int64_t)sizeof(DevProb) + 4 + p.L1 + (p.L2 + 3) / 4 + (int64_t)sizeof(DevRes) +
+                         (p.gout != DPC_NO_GOUT ? p.L2 : 0);
       continue;
     }
     ArenaLayout a;
@@ -822,8 +823,9 @@ static void add_stats(const Engine &e, dpc_stats_t *out) {
         int lo = cc - d.rband < 1 ? 1 : cc - d.rband, hi = cc + d.lband > d.rows ? d.rows : cc + d.lband;
         if (hi >= lo) out->cells += hi - lo + 1;
       }
-      /* algorithmic HBM bytes: query bytes + 2-bit genome in */
+      /* algorithmic HBM bytes: query bytes + 2-bit genome in, staged genome characters out */
       out->fill_bytes += (p.kind == DPC_CDNA_GAP) ? d.cols + (d.rows + 3) / 4 : d.rows + (d.cols + 3) / 4;
+      if (p.gout != DPC_NO_GOUT) out->fill_bytes += d.cols;
     }
     out->fill_bytes += (int64_t)sizeof(DevProb) + 4 + (int64_t)sizeof(DevRes);   /* descriptor + list entry in, result out */
   }
