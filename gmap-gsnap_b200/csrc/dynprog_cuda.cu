@@ -407,7 +407,8 @@ struct Engine {
       CK(cudaSetDevice(device));
       CK(cudaStreamSynchronize(stream));
       CK(cudaEventElapsedTime(&ms_total, ev0, ev1));
-      b.gout_host = h_gout.data();
+      static const bool no_gout = getenv("DPC_NO_GOUT") != NULL;      /* measurement aid: rebuild from the host's 2-bit genome */
+      b.gout_host = no_gout ? NULL : h_gout.data();
       unsigned int used = h_counters[0];
       if (used > 0) {
         if (used > ovf_cap) return DPC_ERR_NOMEM;
