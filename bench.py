@@ -352,7 +352,7 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms[len(ms) // 2] * 1e-3) / 1e9 if rank == 0 else None,
                      "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9 / hbm_peak,
-                     "traffic": 474.4e6 if (args.workload == "single" and n == 1_000_000) else None,
+                     "traffic": 620.4e6 if (args.workload == "single" and n == 1_000_000) else None,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the step's two launches, "
                                        "profiles/r1_final_single_gap_ncu_full.csv (bytes per step)",
                      "peak_source": peak_src,
