@@ -20,7 +20,7 @@
  *
  * Batching.  The gaps of ONE alignment depend on each other (peel-back can eat the pairs of the previous fill,
  * stage3.c:5546), so the unit of parallelism is the alignment.  Instead of rewriting stage3.c's path traversal
- * as an explicit state machine, every worker thread runs DPC_FIBERS (default 64) copies of the reference's
+ * as an explicit state machine, every worker thread runs DPC_FIBERS (default 16) copies of the reference's
  * worker loop (gmap.c:2254 worker_thread) as cooperative fibers, each with its own stack, Pairpool and request
  * in flight: a fiber that reaches one of the five solvers below ENQUEUES its gap (dpc_add) and yields; when
  * every fiber of the thread is parked on a gap (or finished) the scheduler flushes the collected batch to the
@@ -352,7 +352,7 @@ dropin_scheduler (void *data) {
 int
 Dynprog_cuda_worker_create (pthread_t *thread, const pthread_attr_t *attr, void *(*start_routine) (void *), void *arg) {
   const char *e = getenv("DPC_FIBERS");
-  int nfibers = e != NULL ? atoi(e) : 64;
+  int nfibers = e != NULL ? atoi(e) : 16;
   dropin_sched_t *s;
 
   if (nfibers <= 1) return pthread_create(thread,attr,start_routine,arg);
