@@ -470,6 +470,26 @@ dropin_memo_find (const dpc_problem_t *p, dpc_problem_t *key, uint64_t *hash, in
   /* single and end gaps see cdna_direction only in add_genomeskip's intron test of genome runs of 9 or more
      (dynprog.c:2416-2512): GMAP solves every gap once per direction, and a result without such a run serves both */
   if (p->kind != DPC_GENOME_GAP && p->kind != DPC_CDNA_GAP) key->cdna_direction = 0;
+  /* genomiclength only bounds the segment (get_genomic_nt returns '*' outside it, dynprog.c:415) and, on the Crick
+     strand, places it: position = chrpos + genomiclength - 1 - genomicpos (428).  When every position the solver can
+     touch lies inside the segment, two calls that differ only in how far the segment extends are the same
+     problem: Watson keys drop genomiclength, Crick keys carry chrpos + genomiclength instead.  (get_splicesite_probs
+     uses the same two forms, 3219-3243.) */
+  {
+    int lo, hi;		/* segment-relative positions the solver reads: [lo, hi] */
+    switch (p->kind) {
+    case DPC_END5_GAP: lo = p->offset2 - (p->length2 - 1); hi = p->offset2; break;
+    case DPC_GENOME_GAP:
+      lo = p->offset2 < p->offset2R - (p->length2R - 1) ? p->offset2 : p->offset2R - (p->length2R - 1);
+      hi = p->offset2 + p->length2 - 1 > p->offset2R ? p->offset2 + p->length2 - 1 : p->offset2R;
+      break;
+    default: lo = p->offset2; hi = p->offset2 + p->length2 - 1; break;
+    }
+    if (lo >= 0 && hi >= lo && (Genomicpos_T) hi < p->genomiclength) {
+      if (!p->watsonp) key->chrpos = p->chrpos + p->genomiclength;
+      key->genomiclength = 0;
+    }
+  }
   *hash = dropin_fnv(dropin_fnv(dropin_fnv(1469598103934665603ULL,key,sizeof(*key)),a,(size_t) na),b,(size_t) nb);
   /* direction-independent results live in the slot of the hash; a single / end gap whose result does depend on
      cdna_direction (rare) lives one or two slots further, by direction, so the two directions do not evict each other */
