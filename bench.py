@@ -185,7 +185,16 @@ def run_gmap_workload(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
-    dt, out, err = g.run_gmap("gmap_cuda", case, threads, fibers=args.fibers, device=local_rank)
+    # two passes of each binary, alternating (rank 0 also runs the reference arm); the faster pass of each counts:
+    # the host CPUs of these boxes are shared and single passes vary by +-10 %
+    times, ref_times, rout = [], [], None
+    for rep in range(2):
+        dt1, out, err = g.run_gmap("gmap_cuda", case, threads, fibers=args.fibers, device=local_rank)
+        times.append(dt1)
+        if rank == 0 and not args.no_cpu_baseline:
+            rdt1, rout, rerr = g.run_gmap("gmap_ref", case, cores)
+            ref_times.append(rdt1)
+    dt = min(times)
     stats = [l for l in err.splitlines() if "device batches" in l]
     gaps = sum(int(l.split(" device batches, ")[1].split(" gaps")[0]) for l in stats)
     batches = sum(int(l.split(" fibers, ")[1].split(" device batches")[0]) for l in stats)
@@ -202,8 +211,9 @@ def run_gmap_workload(args, rank, world, local_rank):
                      "gap_fills": int(total_gaps), "device_batches_rank0": batches, "gpu_launches": batches,
                      "e2e": {"value": total_n / total_dt, "unit": "queries/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                              "includes": "process start, index load, stage 1-3 on the host, gap fills on the device, output"}})
+        line["pass_seconds"] = {"gmap_cuda": times, "gmap_ref": ref_times}
         if not args.no_cpu_baseline:
-            rdt, rout, rerr = g.run_gmap("gmap_ref", case, cores)
+            rdt = min(ref_times)
             line["cpu_baseline"] = {"value": n / rdt, "unit": "queries/s", "cores": cores, "kind": "reference",
                                     "sample": "the same %d transcripts of rank 0, unmodified gmap -t %d" % (n, cores)}
             line["outputs_identical_to_reference"] = bool(filecmp.cmp(rout, out, shallow=False))
