@@ -14,10 +14,14 @@ for t in (cores // 2, cores):
     print("gmap_ref -t %d: %.2f s  %s  user/sys/minflt %s" % (t, dt, err.strip().splitlines()[-1], g.run_gmap.last_cpu), flush=True)
 for c in combos.split(","):
     t, f = (int(x) for x in c.split(":")[0].split("x"))
-    for k in ("MALLOC_MMAP_MAX_", "MALLOC_TRIM_THRESHOLD_", "MALLOC_TOP_PAD_", "DPC_SYNC"):
+    for k in ("MALLOC_MMAP_MAX_", "MALLOC_TRIM_THRESHOLD_", "MALLOC_TOP_PAD_", "DPC_SYNC", "DPC_MEMO", "DPC_MALLOC_TUNING"):
         os.environ.pop(k, None)
     for opt in c.split(":")[1:]:
-        if opt == "nommap":
+        if opt == "memo0":
+            os.environ["DPC_MEMO"] = "0"
+        elif opt == "notune":
+            os.environ["DPC_MALLOC_TUNING"] = "0"
+        elif opt == "nommap":
             os.environ.update(MALLOC_MMAP_MAX_="0", MALLOC_TRIM_THRESHOLD_="17179869184", MALLOC_TOP_PAD_="268435456")
         else:
             os.environ["DPC_SYNC"] = opt
