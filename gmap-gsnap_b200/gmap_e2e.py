@@ -160,7 +160,7 @@ def run_gmap(binary, case, threads, fibers=None, device=None, extra=(), out=None
     out = out or os.path.join(case["dbdir"], os.path.basename(binary) + ".out")
     if case.get("splicing"):
         extra = ("-s", case["splicing"], *extra)
-    cmd = [os.path.join(REFDIR, binary), "-D", case["dbdir"], "-d", case["dbname"], "-t", str(threads), "-O", "-A", *extra, case["queries"]]
+    cmd = [os.path.join(REFDIR, binary), "-D", case["dbdir"], "-d", case["dbname"], "-t", str(threads), "-O", *os.environ.get("GMAP_OUTFMT", "-A").split(), *extra, case["queries"]]
     import resource
     ru0 = resource.getrusage(resource.RUSAGE_CHILDREN)
     t0 = time.time()
