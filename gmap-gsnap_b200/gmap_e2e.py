@@ -172,3 +172,15 @@ def run_gmap(binary, case, threads, fibers=None, device=None, extra=(), out=None
     if r.returncode != 0:
         raise RuntimeError("%s exited %d\n%s" % (binary, r.returncode, r.stderr.decode()[-3000:]))
     return dt, out, r.stderr.decode()
+
+
+def processed_seconds(err, default):
+    """GMAP's own stopwatch ("Processed N queries in S seconds", gmap.c:3940): starts when the index is loaded and
+    the workers are created, stops when the last result is out; excludes process start-up and tear-down of either arm."""
+    for line in err.splitlines():
+        if line.startswith("Processed ") and " seconds" in line:
+            try:
+                return float(line.split(" in ")[1].split(" seconds")[0])
+            except (IndexError, ValueError):
+                pass
+    return default
