@@ -87,6 +87,41 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
 /* Host-side micro-benchmark aid (no GPU needed): solves once with the simulated device routines, then times
  * `reps` passes of the Pair rebuild alone.  Returns nanoseconds per problem of one pass. */
 #include <time.h>
+/* Host-side micro-benchmark aid: nanoseconds per problem of packing (Batch::add_ext) and of finalisation. */
+extern "C" void emul_time_pack_finalize(const dpc_problem_t *problems, int n, int reps, double out[2]) {
+  std::vector<dpc_result_t> results((size_t)n);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int rep = 0; rep < reps; rep++) { dpc::Batch b; b.add_ext(problems, results.data(), n); }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  out[0] = ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / reps / n;
+  dpc::Batch b;
+  if (b.add_ext(problems, results.data(), n) < 0) { out[1] = -1; return; }
+  std::vector<DevRes> dres(b.dprobs.size());
+  std::vector<uint16_t> ovfbuf(1 << 22);
+  unsigned int used = 0;
+  OvfArena ovf; ovf.ops = ovfbuf.data(); ovf.used = &used; ovf.cap = (unsigned int)ovfbuf.size();
+  Lanes ln; ln.lane = 0; ln.n = 1;
+  RowFill rfill;
+  std::vector<uint8_t> arena, gout((size_t)b.gout_total + 64, 0);
+  b.pool_align(16);
+  for (size_t k = 0; k < b.dprobs.size(); k++) {
+    ArenaLayout a;
+    dpc_layout(b.dprobs[k], a, 2);
+    arena.assign(a.total + 64, 0);
+    uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
+    memset(&dres[k], 0, sizeof(DevRes));
+    dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, a.total, base, &dres[k], ovf, gout.data(), rfill, ln);
+  }
+  b.gout_host = gout.data();
+  dpc::Scratch sc;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int rep = 0; rep < reps; rep++)
+    for (int i = 0; i < n; i++) if (b.probs[i].dev >= 0) { const DevRes &dr = dres[b.probs[i].dev]; b.finalize(i, dr, dr.nopsL + dr.nopsR > DPC_INLINE_OPS ? ovfbuf.data() + dr.ovf : dr.ops, sc); }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  out[1] = ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / reps / n;
+}
+
 extern "C" double emul_time_rebuild(const dpc_problem_t *problems, int n, int reps, int64_t *npairs_out) {
   dpc::Batch b;
   std::vector<dpc_result_t> results((size_t)n);
