@@ -14,9 +14,11 @@
  *   Dynprog_end5_splicejunction  dynprog.c:5411   (called by Splicetrie_solve_end5, splicetrie.c:352, 447, once per
  *   Dynprog_end3_splicejunction  dynprog.c:5869    known far splice site: runs with a known-splicing file, gmap -s)
  *
- * The originals stay linked under the names <name>_cpu (objcopy --redefine-sym, or eight #defines on top of
- * dynprog.c) because Dynprog_init/_setup must still run for the solvers this library does not replace
- * (Dynprog_end5_known, Dynprog_microexon_*, ...).  The five solvers below never call their _cpu twins.
+ * In dynprog.c the DEFINITIONS of these functions are renamed <name>_cpu (oracle/build_gmap.sh does it with sed on a
+ * scratch copy; a maintainer would delete the seven solver bodies).  Dynprog_init/_setup/_term_cpu are still called
+ * from here, because the reference's own tables must exist for the functions this library does not replace
+ * (Dynprog_end5_known, Dynprog_microexon_*, ...); the renamed solver bodies are dead code: every call, including
+ * the ones Dynprog_end5_known / Dynprog_end3_known make from inside dynprog.c (6474-6900), lands here.
  *
  * Batching.  The gaps of ONE alignment depend on each other (peel-back can eat the pairs of the previous fill,
  * stage3.c:5546), so the unit of parallelism is the alignment.  Instead of rewriting stage3.c's path traversal

@@ -5,7 +5,7 @@
 # reference source is copied into this repository):
 #   oracle/_ref/gmap_ref    the unmodified reference + oracle/genome_hr_standin.c (the checkout lacks genome_hr.c)
 #   oracle/_ref/gmap_cuda   the same objects, except that the five gap-fill solvers of dynprog.c (and
-#                           Dynprog_init/_setup/_term) are renamed *_cpu with objcopy and replaced by
+#                           Dynprog_init/_setup/_term) have their definitions renamed *_cpu and are replaced by
 #                           gmap-gsnap_b200/host/dynprog_dropin.c on top of libdynprog_cuda.so, and that gmap.c gets
 #                           the two edits INTEGRATION.md describes (registering a user segment's genome blocks;
 #                           worker threads created through Dynprog_cuda_worker_create, which runs DPC_FIBERS copies
@@ -31,8 +31,16 @@ cp gmap "$OUT/gmap_ref"
 CC="${CC:-gcc}"
 CFLAGS=(-DHAVE_CONFIG_H -I. -mpopcnt '-DTARGET="x86_64-unknown-linux-gnu"' '-DGMAPDB="/usr/share/gmapdb"' -O3)
 SYMS="Dynprog_init Dynprog_setup Dynprog_term Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap Dynprog_end5_splicejunction Dynprog_end3_splicejunction"
-ARGS=""; for s in $SYMS; do ARGS="$ARGS --redefine-sym $s=${s}_cpu"; done
-objcopy $ARGS gmap-dynprog.o cuda-dynprog_cpu.o
+# Only the DEFINITIONS of the replaced functions are renamed (<name>_cpu), in a scratch copy of dynprog.c: the
+# reference writes a function's name at the start of a line where it defines it and indented where it calls it.
+# Calls from the unreplaced functions of dynprog.c (Dynprog_end5_known / Dynprog_end3_known call Dynprog_end5_gap /
+# Dynprog_end3_gap, dynprog.c:6474-6900) therefore reach the drop-in too; nothing in the product calls a _cpu solver
+# (Dynprog_init/_setup/_term_cpu are called by the drop-in to keep the reference's own tables for the functions
+# that are not replaced).  A maintainer would simply delete the replaced bodies from dynprog.c.
+SEDARGS=(); for s in $SYMS; do SEDARGS+=(-e "s/^$s (/${s}_cpu (/"); done
+sed "${SEDARGS[@]}" dynprog.c > cuda-dynprog_cpu.c
+for s in $SYMS; do grep -q "^${s}_cpu (" cuda-dynprog_cpu.c; done
+$CC "${CFLAGS[@]}" -w -c cuda-dynprog_cpu.c -o cuda-dynprog_cpu.o
 $CC "${CFLAGS[@]}" -I"$REPO/include" -Wall -c "$REPO/gmap-gsnap_b200/host/dynprog_dropin.c" -o cuda-dynprog_dropin.o
 # the one-line change to gmap.c: hand the user segment's blocks to the library
 sed 's|^    Genome_user_setup(genome_blocks);|    Genome_user_setup(genome_blocks);\n    { extern void Dynprog_cuda_register_blocks (UINT4 *blocks, unsigned int nwords); Dynprog_cuda_register_blocks(genome_blocks,((Sequence_fulllength(usersegment) + 31)/32U)*3 + 4); }|' gmap.c > cuda-gmap.c
