@@ -663,6 +663,7 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
   int chunk = n / (4 * T) + 1;
   if (chunk < 2048) chunk = 2048;
   if (chunk > 16384) chunk = 16384;
+  { static const int forced = getenv("DPC_CHUNK") ? atoi(getenv("DPC_CHUNK")) : 0; if (forced >= 256) chunk = forced; }   /* tuning aid */
   const int nchunks = (n + chunk - 1) / chunk;
   const int nengines = std::min(nchunks, 4 * T);              /* chunks in flight */
   while ((int)c->subs.size() < nengines) {
