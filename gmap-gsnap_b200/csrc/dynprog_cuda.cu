@@ -746,17 +746,28 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
       t_stall += (int64_t)((a4 - a3) * 1e9); t_pairs += (int64_t)((now_s() - a4) * 1e9);
     }
   };
-  /* every host thread keeps two chunks in flight: it launches the next one before it waits for the current one */
+  /* Launch tickets and finish tickets are handed out separately, both in chunk order; a thread launches one chunk
+     (two before its first finish, so that every thread keeps two in flight) and then finishes the OLDEST chunk
+     nobody has taken yet -- not necessarily one it launched.  Finishing in order keeps the ordered hand-off of the
+     pair offsets short: chunk j-1 is always in somebody's hands before chunk j is.  (No deadlock: a launch only
+     waits for the engine of chunk l - nengines, whose finish ticket is taken by then because nengines = 4T and a
+     thread is never more than two launches ahead of its finishes.) */
+  std::vector<std::atomic<int>> launched((size_t)nchunks);
+  for (int j = 0; j < nchunks; j++) launched[(size_t)j].store(0);
+  std::atomic<int> next_finish(0);
   c->workers->run(T, [&](int) {
     cudaSetDevice(device);
-    int cur = next_chunk.fetch_add(1);
-    if (cur >= nchunks) return;
-    launch(cur);
-    while (cur < nchunks) {
-      int nxt = next_chunk.fetch_add(1);
-      if (nxt < nchunks) launch(nxt);
-      finish(cur);
-      cur = nxt;
+    auto try_launch = [&]() {
+      const int l = next_chunk.fetch_add(1);
+      if (l < nchunks) { launch(l); launched[(size_t)l].store(1, std::memory_order_release); }
+    };
+    try_launch();
+    for (;;) {
+      try_launch();
+      const int f = next_finish.fetch_add(1);
+      if (f >= nchunks) break;
+      while (!launched[(size_t)f].load(std::memory_order_acquire)) std::this_thread::yield();
+      finish(f);
     }
   });
 #if defined(__SSE2__) && defined(__x86_64__)
