@@ -33,6 +33,7 @@ struct Globals {
   int mode;
   int P[4][128][128];            /* pairdistance_array, dynprog.c:1045 */
   uint8_t CONS[128][128];        /* consistent_array, dynprog.c:1046 */
+  bool acgt_plain;               /* no two different upper-case bases are "consistent" (false in the CMET modes, 1215-1219) */
   DevTables tables;
   dpc_setup_t setup;
   uint64_t genome_nbases;
@@ -72,6 +73,11 @@ inline void build_tables(Globals &g, int mode) {
     set_pair(g, 'A', 'G', 3, true);
   }
   for (int c = 'A'; c < 'Z'; c++) set_pair(g, c, c, 3, false);       /* sic: 'Z' excluded, 1221 */
+
+  g.acgt_plain = true;
+  for (const char *x = "ACGT"; *x; x++)
+    for (const char *y = "ACGT"; *y; y++)
+      if (*x != *y && g.CONS[(int)*x][(int)*y]) g.acgt_plain = false;
 
   static const char codes[6] = { 'A', 'C', 'G', 'T', 'N', '*' };
   memset(&g.tables, 0, sizeof g.tables);
@@ -261,7 +267,8 @@ struct Scratch {
  * characters differ get '?' here and are fixed by the caller (it knows the case / ambiguity rules).  No column may
  * be '*' (the caller checks the device's flag).  Returns the number of columns written (a multiple of 8). */
 __attribute__((target("avx2"))) inline int mrun_avx2(dpc_pair_t *dst, const char *qlast, const char *glast, int len,
-                                                     int qpos, int gpos, int step, int idx, bool stream, uint32_t *diffmask) {
+                                                     int qpos, int gpos, int step, int idx, bool stream, uint32_t *diffmask,
+                                                     bool acgt_plain) {
   /* qlast / glast point at the characters of the run's FIRST column; column j reads qlast[-j] */
   const __m256i rev = _mm256_setr_epi32(7, 6, 5, 4, 3, 2, 1, 0);
   const __m256i iota = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
@@ -270,7 +277,9 @@ __attribute__((target("avx2"))) inline int mrun_avx2(dpc_pair_t *dst, const char
   __m256i vg = _mm256_sub_epi32(_mm256_set1_epi32(gpos), _mm256_mullo_epi32(iota, vstep));
   const __m256i dec = _mm256_slli_epi32(vstep, 3);
   const __m256i vidx = _mm256_set1_epi32(idx);
-  const __m256i star = _mm256_set1_epi32('*' << 8), qm = _mm256_set1_epi32('?' << 8);
+  const __m256i star = _mm256_set1_epi32('*' << 8), qm = _mm256_set1_epi32('?' << 8), space = _mm256_set1_epi32(' ' << 8);
+  const __m256i vplain = _mm256_set1_epi32(acgt_plain ? -1 : 0);
+  const __m256i cA = _mm256_set1_epi32('A'), cC = _mm256_set1_epi32('C'), cG = _mm256_set1_epi32('G'), cT = _mm256_set1_epi32('T');
   int j = 0, w = 0;
   for (; j + 8 <= len; j += 8, w++) {
     __m256i q = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i *)(qlast - j - 7)));
@@ -278,8 +287,16 @@ __attribute__((target("avx2"))) inline int mrun_avx2(dpc_pair_t *dst, const char
     q = _mm256_permutevar8x32_epi32(q, rev);
     g = _mm256_permutevar8x32_epi32(g, rev);
     const __m256i eq = _mm256_cmpeq_epi32(q, g);
-    diffmask[w] = ~(uint32_t)_mm256_movemask_ps(_mm256_castsi256_ps(eq)) & 0xffu;
-    const __m256i tail = _mm256_or_si256(_mm256_or_si256(q, _mm256_slli_epi32(g, 16)), _mm256_blendv_epi8(qm, star, eq));
+    /* two different upper-case bases are a plain mismatch (consistent_array is false for them, dynprog.c:1150-1157);
+       only columns with anything else on either side (lower case, N, IUPAC codes) go to the exact rule */
+    const __m256i qb = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi32(q, cA), _mm256_cmpeq_epi32(q, cC)),
+                                       _mm256_or_si256(_mm256_cmpeq_epi32(q, cG), _mm256_cmpeq_epi32(q, cT)));
+    const __m256i gb = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi32(g, cA), _mm256_cmpeq_epi32(g, cC)),
+                                       _mm256_or_si256(_mm256_cmpeq_epi32(g, cG), _mm256_cmpeq_epi32(g, cT)));
+    const __m256i plain = _mm256_or_si256(eq, _mm256_and_si256(_mm256_and_si256(qb, gb), vplain));
+    diffmask[w] = ~(uint32_t)_mm256_movemask_ps(_mm256_castsi256_ps(plain)) & 0xffu;
+    const __m256i tail = _mm256_or_si256(_mm256_or_si256(q, _mm256_slli_epi32(g, 16)),
+                                         _mm256_blendv_epi8(_mm256_blendv_epi8(qm, space, plain), star, eq));
     const __m256i ab_lo = _mm256_unpacklo_epi32(vq, vg), ab_hi = _mm256_unpackhi_epi32(vq, vg);
     const __m256i cd_lo = _mm256_unpacklo_epi32(vidx, tail), cd_hi = _mm256_unpackhi_epi32(vidx, tail);
     const __m256i r04 = _mm256_unpacklo_epi64(ab_lo, cd_lo), r15 = _mm256_unpackhi_epi64(ab_lo, cd_lo);
@@ -598,7 +615,7 @@ struct Batch {
           uint32_t diff[512];
           dpc_pair_t *base = st.p + st.n;
           const bool stream = st.stream && (((uintptr_t)base) & 15) == 0;
-          const int done = mrun_avx2(base, qch + qi, gch + gi, len > 4096 ? 4096 : len, qpos, gpos, step, idx, stream, diff);
+          const int done = mrun_avx2(base, qch + qi, gch + gi, len > 4096 ? 4096 : len, qpos, gpos, step, idx, stream, diff, g.acgt_plain);
           for (int w = 0; w < done / 8; w++)
             for (uint32_t mask = diff[w]; mask; mask &= mask - 1) {
               const int jj = 8 * w + __builtin_ctz(mask);
