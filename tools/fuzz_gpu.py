@@ -19,7 +19,7 @@ for seed in range(1000, 1000 + nseeds):
     eb = int(rng.choice([0, 1, 3, 7, 15, 30, 40]))
     try:
       sets = [
-          w.single_gaps(4000, extraband=eb, seed=seed, len_lo=int(rng.choice([1, 2, 10])), len_hi=int(rng.choice([8, 40, 100, 300])),
+          w.single_gaps(4000, extraband=eb, seed=seed, len_lo=int(rng.choice([1, 2, 8])), len_hi=int(rng.choice([8, 40, 100, 300])),
                       edge_frac_pm=30, lower_case=1, iupac_pm=10),
           w.end_gaps(4000, extraband=int(rng.choice([0, 3, 10])), seed=seed + 1, len_hi=int(rng.choice([5, 40, 120])), edge_frac_pm=30, lower_case=1, iupac_pm=10),
           w.genome_gaps(2000, extraband=int(rng.choice([3, 7, 12])), seed=seed + 2, finalp_mode=2, long_frac=0.05, long_hi=int(rng.choice([200, 611]))),
