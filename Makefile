@@ -5,10 +5,13 @@ NVFLAGS = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcom
 
 all: cuda synth oracle emul
 
-cuda: $(PKG)/csrc/libdynprog_cuda.so
-$(PKG)/csrc/libdynprog_cuda.so: $(PKG)/csrc/*.cu $(PKG)/csrc/*.h include/dynprog_cuda.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/dynprog_cuda.cu -lcudart 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; exit 1)
-	@grep -E "registers|spill" $(PKG)/csrc/ptxas.log | sort | uniq -c | head -40
+CUDA_SO ?= $(PKG)/csrc/libdynprog_cuda.so
+cuda: $(CUDA_SO)
+# DPC_DEFS: extra -D flags for tuning experiments (e.g. make cuda DPC_DEFS=-DDPC_MIN_BLOCKS_NARROW=4 CUDA_SO=/tmp/x.so)
+$(CUDA_SO): $(PKG)/csrc/*.cu $(PKG)/csrc/*.h include/dynprog_cuda.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) $(DPC_DEFS) -shared -o $@ $(PKG)/csrc/dynprog_cuda.cu -lcudart 2> build/ptxas.log || (cat build/ptxas.log; exit 1)
+	@grep -E "registers|spill" build/ptxas.log | sort | uniq -c | head -40
 
 synth: $(PKG)/host/libdpc_synth.so
 $(PKG)/host/libdpc_synth.so: $(PKG)/host/synth.c include/dynprog_cuda.h
@@ -31,6 +34,6 @@ gmap: cuda
 	bash oracle/build_gmap.sh
 
 clean:
-	rm -f $(PKG)/csrc/*.so $(PKG)/host/*.so $(PKG)/csrc/ptxas.log tests/emul/*.so
+	rm -f $(PKG)/csrc/*.so $(PKG)/host/*.so build/ptxas.log tests/emul/*.so
 	$(MAKE) -C oracle clean
 .PHONY: all cuda synth oracle emul gmap clean

@@ -107,10 +107,13 @@ WORKLOADS = {
 }
 
 
-def make_workload(rank, n, kind="single"):
+def make_workload(rank, n, kind="single", genome_mix=False):
+    """The synthetic inputs of BASELINE configs[1..3].  genome_mix: config 3's stated mix -- finalp and
+    halfp both ways, a 10 % subset marked for the probability-mode second call (arm it with api.arm_probability_mode)."""
     w = api.Workload(GENOME_BASES, seed=0x9E3779B9 + rank, nchr=4)
     if kind == "genome":
-        probs = w.genome_gaps(n, extraband=7, seed=0x5EED0003 + 1000 * rank, finalp_mode=0, long_frac=0.1, long_hi=600)
+        probs = w.genome_gaps(n, extraband=7, seed=0x5EED0003 + 1000 * rank, finalp_mode=2 if genome_mix else 0,
+                              prob_mode_pm=100 if genome_mix else 0, long_frac=0.1, long_hi=600)
     elif kind == "end":
         probs = w.end_gaps(n, extraband=3, seed=0x5EED0004 + 1000 * rank)
     else:

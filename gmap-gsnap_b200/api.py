@@ -56,13 +56,15 @@ class Pair(C.Structure):
 
 PROB_FN = C.CFUNCTYPE(C.c_double, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p)
 KNOWN_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p)
+INTRON_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p)
 
 
 class Setup(C.Structure):
     _fields_ = [
         ("genome_blocks", C.c_void_p), ("genome_nwords", C.c_uint64),
-        ("novelsplicingp", C.c_int32), ("reserved", C.c_int32),
+        ("novelsplicingp", C.c_int32), ("intron_level", C.c_int32),
         ("splice_prob", C.c_void_p), ("splice_known", C.c_void_p), ("user", C.c_void_p),
+        ("splice_intron", C.c_void_p),
     ]
 
 
@@ -266,7 +268,7 @@ class Workload:
         self._keep.append(qbuf)
         return probs
 
-    def make_setup(self, splice_prob=None, splice_known=None, novelsplicingp=1):
+    def make_setup(self, splice_prob=None, splice_known=None, novelsplicingp=1, splice_intron=None, intron_level=0):
         s = Setup()
         s.genome_blocks = self.blocks.ctypes.data
         s.genome_nwords = self.blocks.size
@@ -274,7 +276,9 @@ class Workload:
         s.splice_prob = C.cast(splice_prob, C.c_void_p).value if splice_prob is not None else None
         s.splice_known = C.cast(splice_known, C.c_void_p).value if splice_known is not None else None
         s.user = None
-        self._keep.append((splice_prob, splice_known))
+        s.intron_level = intron_level
+        s.splice_intron = C.cast(splice_intron, C.c_void_p).value if splice_intron is not None else None
+        self._keep.append((splice_prob, splice_known, splice_intron))
         s._workload = self
         return s
 

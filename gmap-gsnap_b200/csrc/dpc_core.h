@@ -52,6 +52,7 @@ enum { DPC_GN = 4, DPC_GSTAR = 5 };
 enum {
   DPC_F_WATSON = 1, DPC_F_LATE = 2, DPC_F_WIDEBAND = 4, DPC_F_HALFP = 8, DPC_F_FINALP = 16,
   DPC_F_PROBMODE = 32, DPC_F_ALLSTAR = 64, DPC_F_KNOWN = 128, DPC_F_NOVEL = 256,
+  DPC_F_INTRONS = 1024,     /* bridge constrained to the given introns listed after the known flags (dynprog.c:3552-3696) */
   DPC_F_SEQ2 = 512          /* the columns' genome codes are in the byte pool at q1, in matrix order (splice-junction solvers) */
 };
 
@@ -76,6 +77,7 @@ struct DevProb {
 DPC_HB uint32_t dpc_gout_span(int len) { return ((uint32_t)len + 7u) & ~7u; }     /* second span of a genome gap starts here */
 
 #define DPC_INLINE_OPS 38
+#define DPC_OP_MAXLEN 16383                 /* (length << 2) | type in 16 bits */
 /* device-side result record, 128 bytes */
 struct DevRes {
   int32_t finalscore;
@@ -129,12 +131,9 @@ struct Mat {
                                0: rows = genome, columns = query (_fwd_12/_rev_12, 1741-2044) */
   uint8_t *rowch, *colch;   /* characters in matrix order: raw query bytes / genome codes */
   int planes, cpl, cplsh;   /* planes != 0: directions are bit planes; every lane owns cpl = 1 << cplsh adjacent diagonals */
-  uint32_t *prof;           /* planes, query rows: per row the 6 biased 4-bit scores of its query character */
-  int prof_base, prof_step; /* row r reads prof[prof_base + r * prof_step]: (-1, 1), or (L1, -1) when the array belongs to
-                               the forward query and this matrix runs over the reversed one */
   uint32_t *dir;            /* nibbles: rows 1..L1, nibble (r-1)*wstride*8 + (c-r+lband);
                                planes:  word ((r-1)*cpl + k%cpl)*4 + p, bit k/cpl, k = c-r+lband, with plane
-                               p = 0 nogap came from gap1 (HORIZ), 1 nogap came from gap2 (VERT),
+                               p = 0 nogap did not come from nogap (HORIZ or VERT), 1 nogap came from gap2 (VERT),
                                    2 gap1 of cell k+1 came from gap1 (HORIZ), 3 gap2 came from gap2 (VERT) */
   int16_t *nband;           /* nogap score of rows 1..L1, (r-1)*W + (c-r+lband), 16 bit (real scores are within
                                +-28000 for any size dpc_init accepts); NULL when no bridge follows */
@@ -164,15 +163,14 @@ DPC_HD int dpc_dirN(const Mat &m, int r, int c) {
   if (!dpc_inband(m, r, c)) return -1;
   if (!m.planes) return dpc_nib(m, r, c) & 3;
   int k = c - r + m.lband;
-  if (dpc_plane_bit(m, r, k, 1)) return DPC_VERT;
-  return dpc_plane_bit(m, r, k, 0) ? DPC_HORIZ : DPC_DIAG;
+  if (!dpc_plane_bit(m, r, k, 0)) return DPC_DIAG;
+  return dpc_plane_bit(m, r, k, 1) ? DPC_VERT : DPC_HORIZ;
 }
 /* 1 when the nogap direction of an IN-BAND cell is HORIZ or VERT (the bridges' -1, dynprog.c:3724) */
 DPC_HD int dpc_nondiag(const Mat &m, int r, int c) {
   const int k = c - r + m.lband;
   if (!m.planes) return (dpc_nib(m, r, c) & 3) != DPC_DIAG;
-  const uint32_t *w = m.dir + ((r - 1) * m.cpl + (k & (m.cpl - 1))) * 4;
-  return (int)(((w[0] | w[1]) >> (k >> m.cplsh)) & 1U);
+  return dpc_plane_bit(m, r, k, 0);
 }
 DPC_HD bool dpc_g1_horiz(const Mat &m, int r, int c) {
   if (r == 0) return c >= 2 && c <= m.rband && c <= m.L2;
@@ -416,7 +414,7 @@ struct Bridge { int have, finalscore, rL, cL, rR, cR, introntype; };
  * construction (their column ranges are clipped to the band, 3545-3549), so the nogap band is read directly. */
 DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const DevProb &p,
                               const uint8_t *lknown, const uint8_t *rknown, const double *lp, const double *rp,
-                              uint8_t *ldi, uint8_t *rdi, int8_t *itab, const Lanes &ln) {
+                              const uint8_t *introns, uint8_t *ldi, uint8_t *rdi, int8_t *itab, const Lanes &ln) {
   const int L1 = mL.L1, L2L = mL.L2, L2R = mR.L2, eb = p.extraband;
   const int rbandL = L2L - L1 + eb, lbandL = eb, rbandR = L2R - L1 + eb, lbandR = eb;   /* 3545-3549 */
   const int finalp = (p.flags & DPC_F_FINALP) != 0, halfp = (p.flags & DPC_F_HALFP) != 0;
@@ -430,12 +428,42 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
   for (int t = ln.lane; t < 64; t += ln.n) itab[t] = (int8_t)dpc_intron_score(&it, t, t, p.cdna_direction, p.reward, finalp);
   DPC_SYNC();
   const bool fast = mL.planes && mR.planes && mL.cpl == 1 && mR.cpl == 1 && !lknown && !rknown && !probmode;
+  if (introns) {
+    /* novelsplicingp == false with an intron-level IIT, 3552-3696: only (cL, cR) pairs that are given introns (the
+       host looked them up), both sites known, no intron score and no known-site reward; the pair (cL, cR) can be
+       met by the left scan of row pair (length1 - cR, cR) and by the right scan of row pair (cL, length1 - cL) */
+    const uint32_t n = *(const uint32_t *)introns;
+    const uint16_t *pr = (const uint16_t *)(introns + 4);
+    for (uint32_t i = (uint32_t)ln.lane; i < n; i += (uint32_t)ln.n) {
+      const int cL = pr[2 * i], cR = pr[2 * i + 1];
+      {
+        const int rR = cR, rL = L1 - rR;
+        const int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
+        if (rL >= 1 && rL < L1 && cL >= cloL && cL <= chighL && cR < p.gap - cL) {
+          const int s = dpc_nscore(mL, rL, cL) - dpc_nondiag(mL, rL, cL) + dpc_nscore(mR, rR, cR);
+          const int key = rL * 8192 + (cL - cloL);
+          if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+        }
+      }
+      {
+        const int rL = cL, rR = L1 - rL;
+        const int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
+        const int cloR = rR - lbandR < 1 ? 1 : rR - lbandR, chighR = rR + rbandR > L2R - 1 ? L2R - 1 : rR + rbandR;
+        const int nL = chighL >= cloL ? chighL - cloL + 1 : 0;
+        if (rL >= 1 && rL < L1 && cR >= cloR && cR <= chighR && cL < p.gap - cR) {
+          const int s = dpc_nscore(mR, rR, cR) - dpc_nondiag(mR, rR, cR) + dpc_nscore(mL, rL, cL);
+          const int key = rL * 8192 + nL + (cR - cloR);
+          if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
+        }
+      }
+    }
+  }
   /* common case (bands of at most 32 diagonals, no known sites, integer mode): lane = diagonal, exactly like the
      fill -- one candidate per lane and side, rows of the nogap band and of the direction planes read directly.
      Four row pairs at a time, loads first: for long gaps the bands and planes sit in HBM scratch (L2), and one
      row pair at a time is a chain of dependent load latencies (ncu: half of the long-gap launch was spent here). */
   enum { BR = 4 };
-  for (int rL0 = 1; rL0 < L1 && fast; rL0 += BR) {
+  for (int rL0 = 1; rL0 < L1 && fast && !introns; rL0 += BR) {
     for (int k = ln.lane; k < 32; k += ln.n) {                   /* one trip per lane on the GPU */
       const int kL = k < mL.W ? k : mL.W - 1, kR = k < mR.W ? k : mR.W - 1;
       int vL[BR], vR[BR], dL[BR], dR[BR];
@@ -447,7 +475,7 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
         const uint32_t *wL = mL.dir + (rL - 1) * 4, *wR = mR.dir + (rR - 1) * 4;
         vL[u] = rowL[kL]; vR[u] = rowR[kR];
         dL[u] = rowL[mL.lband]; dR[u] = rowR[mR.lband];          /* the main-diagonal cells (rL,rL) and (rR,rR) */
-        hL[u] = wL[0] | wL[1]; hR[u] = wR[0] | wR[1];
+        hL[u] = wL[0]; hR[u] = wR[0];
       }
 #pragma unroll
       for (int u = 0; u < BR; u++) {
@@ -474,7 +502,7 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
       }
     }
   }
-  for (int rL = 1; rL < L1 && !fast; rL++) {
+  for (int rL = 1; rL < L1 && !fast && !introns; rL++) {
     const int rR = L1 - rL;
     int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
     int cloR = rR - lbandR < 1 ? 1 : rR - lbandR, chighR = rR + rbandR > L2R - 1 ? L2R - 1 : rR + rbandR;
@@ -525,7 +553,7 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
   }
   br.introntype = 0;
   if (!br.have) {
-    br.finalscore = probmode ? DPC_BRIDGE_FLOOR : (halfp ? DPC_BRIDGE_FLOOR - DPC_BRIDGE_FLOOR / 2 : DPC_BRIDGE_FLOOR);
+    br.finalscore = (probmode || introns) ? DPC_BRIDGE_FLOOR : (halfp ? DPC_BRIDGE_FLOOR - DPC_BRIDGE_FLOOR / 2 : DPC_BRIDGE_FLOOR);
     br.rL = br.cL = br.rR = br.cR = 0;
     return;
   }
@@ -538,7 +566,10 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
     int left = j < nL, cL = left ? cloL + j : rL, cR = left ? rR : cloR + (j - nL);
     int sI = dpc_intron_score(&it, dpc_leftdi(gL[cL], gL[cL + 1]), dpc_rightdi(gR[cR + 1], gR[cR]), p.cdna_direction, p.reward, finalp);
     br.rL = rL; br.cL = cL; br.rR = rR; br.cR = cR;
-    if (probmode) {                                                     /* 4055-4080: -1 on both sides */
+    if (introns) {                                                      /* 3694-3695 */
+      br.finalscore = best.score;
+      br.introntype = 0;
+    } else if (probmode) {                                                     /* 4055-4080: -1 on both sides */
       int sL = dpc_nscore(mL, rL, cL) + (lknown && lknown[cL] ? 20 : 0) - (dpc_dirN(mL, rL, cL) > 0 ? 1 : 0);
       int sR = dpc_nscore(mR, rR, cR) + (rknown && rknown[cR] ? 20 : 0) - (dpc_dirN(mR, rR, cR) > 0 ? 1 : 0);
       br.finalscore = halfp ? sL + sI + sR - sI / 2 : sL + sI + sR;
@@ -588,14 +619,6 @@ DPC_HD void dpc_bridge_cdna(Bridge &br, const Mat &mL, const Mat &mR, const DevP
   br.finalscore = bs; br.rL = brL; br.rR = brR; br.cL = bcL; br.cR = bcR; br.introntype = 0;
 }
 
-/* the 6 scores of one query character against A C G T N *, 4 bits each, stored as score + 8 (scores are -5..3) */
-DPC_HD uint32_t dpc_pack_prof(const int8_t *score, int q) {
-  const int8_t *s = score + (q & 127) * 8;
-  uint32_t w = 0;
-  for (int g = 0; g < 6; g++) w |= ((uint32_t)(s[g] + 8) & 15u) << (4 * g);
-  return w;
-}
-
 /* ---- arena layout (shared by host sizing and the kernel) --------------------------------- */
 struct MatDims { int rows, cols, lband, rband, W, wstride, planes, cpl; };
 struct ArenaLayout {
@@ -604,7 +627,7 @@ struct ArenaLayout {
   /* two regions: `small` (characters, profiles, bridge tables: read on the fill's critical path, always in shared
    * memory when the problem runs in the shared-memory class) and `bulk` (direction bits, nogap bands, op strings,
    * fallback-fill state: written once per row, read by bridge and traceback; goes to HBM scratch when it does not fit) */
-  uint32_t rowch[2], colch[2], prof[2], di[2], itab, small;
+  uint32_t rowch[2], colch[2], di[2], itab, small;
   uint32_t dir[2], nband[2], ops[2], state, bulk;
   uint32_t total;                        /* small + bulk */
 };
@@ -631,8 +654,6 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
     if (d.rows > maxrows) maxrows = d.rows;
     a.rowch[i] = so; so = dpc_al(so + (uint32_t)d.rows + 2, 4);
     a.colch[i] = so; so = dpc_al(so + (uint32_t)d.cols + 2, 4);
-    if (i == 1 && p.kind == 1) a.prof[1] = a.prof[0];                 /* R rows are the same query, reversed */
-    else { a.prof[i] = so; if ((d.planes || (p.kind == 1 && fillmode == 2)) && p.kind != 2) so += (uint32_t)d.rows * 4; }
     a.di[i] = so;
     if (p.kind == 1) so = dpc_al(so + (uint32_t)d.cols + 2, 4);         /* dinucleotide code per column (intron bridge) */
     a.dir[i] = bo;
@@ -655,8 +676,6 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *small, ui
   m.open = p.open; m.extend = p.extend; m.late = late; m.query_rows = query_rows;
   m.rowch = small + a.rowch[i]; m.colch = small + a.colch[i];
   m.planes = d.planes; m.cpl = d.cpl; m.cplsh = d.cpl == 1 ? 0 : d.cpl == 2 ? 1 : 2;
-  m.prof = (uint32_t *)(small + a.prof[i]);
-  if (i == 1 && p.kind == 1) { m.prof_base = d.rows; m.prof_step = -1; } else { m.prof_base = -1; m.prof_step = 1; }
   m.dir = (uint32_t *)(bulk + a.dir[i]);
   m.nband = a.nmat == 2 ? (int16_t *)(bulk + a.nband[i]) : (int16_t *)0;
 }
@@ -690,7 +709,10 @@ DPC_HD void dpc_emit_ops(DevRes *res, const uint16_t *opsL, int nL, const uint16
 /* KG selects what is compiled in: 0 the one-matrix solvers (single gap, end gaps), 1 genome gap, 2 cDNA gap,
  * -1 everything (the CPU simulation).  The CUDA build instantiates one kernel per group so that each carries only
  * its own code and register needs. */
-template <class FILL, int KG>
+/* BULK says where the bulk region lives: 1 in the warp's arena right after the small region, 0 in the problem's HBM
+ * scratch, -1 decided per problem (the CPU simulation).  The CUDA build makes it a launch property, so that every
+ * access to direction planes, bands and op strings has a known address space (STS/LDS instead of generic ST/LD). */
+template <class FILL, int KG, int BULK>
 DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint32_t *blocks, const DevTables *tb,
                               uint8_t *arena, uint32_t arena_bytes, uint8_t *scratch, DevRes *res, const OvfArena &ovf,
                               uint8_t *gout, FILL &fill, const Lanes &ln) {
@@ -721,14 +743,20 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
     ct.nmatches = dpc_warp_sum(nm, ln); ct.nmismatches = dpc_warp_sum(nmm, ln); ct.star = dpc_warp_sum(star, ln);
     finalscore = 3 * ct.nmatches - 5 * ct.nmismatches;                    /* 5243, 5700 */
     brL = bcL = n;
-    if (ln.lane == 0) res->ops[0] = (uint16_t)((n << 2) | DPC_OP_M);
-    if (ln.lane == 0) { res->nopsL = 1; res->nopsR = 0; res->ovf = 0; }
+    /* one run of n aligned columns; an op carries 14 bits of length, so a long unaligned end (QUERYEND_NOGAPS is not
+       clipped to maxlength1/2) becomes several M ops -- the host accepts at most DPC_INLINE_OPS of them */
+    const int nrun = (n + DPC_OP_MAXLEN - 1) / DPC_OP_MAXLEN;
+    for (int k = ln.lane; k < nrun; k += ln.n) {
+      const int len = n - k * DPC_OP_MAXLEN < DPC_OP_MAXLEN ? n - k * DPC_OP_MAXLEN : DPC_OP_MAXLEN;
+      res->ops[k] = (uint16_t)((len << 2) | DPC_OP_M);
+    }
+    if (ln.lane == 0) { res->nopsL = (uint16_t)nrun; res->nopsR = 0; res->ovf = 0; }
     status |= DPC_ST_HAVE | DPC_ST_OK;
   } else {
     ArenaLayout a;
     dpc_layout(p, a, FILL::fillmode);
     Mat m0, m1;
-    uint8_t *bulk = a.total <= arena_bytes ? arena + a.small : scratch;
+    uint8_t *bulk = BULK == 1 ? arena + a.small : BULK == 0 ? scratch : (a.total <= arena_bytes ? arena + a.small : scratch);
     int32_t *st = (int32_t *)(bulk + a.state);
     if (KG == 0 || (KG == -1 && (p.kind == 0 || p.kind == 3 || p.kind == 4))) {
       /* Dynprog_single_gap 4450-4572, Dynprog_end5_gap 5094-5284, Dynprog_end3_gap 5556-5741 */
@@ -737,7 +765,6 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       for (int i = ln.lane; i < p.L1; i += ln.n) {
         int q = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
         m0.rowch[i] = (uint8_t)q;
-        if (m0.planes) m0.prof[i] = dpc_pack_prof(score, q);
       }
       if (p.flags & DPC_F_SEQ2) {
         /* Dynprog_end5/3_splicejunction 5411-5552, 5869-6012: use_genomicseg_p, sequence2 = the splice-junction string */
@@ -755,8 +782,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       if (p.kind == 0) { es.mode = 3; es.best.score = -2147483647; es.best.key = 0; }
       else if (p.endalign == 1) { es.mode = 2; es.best.score = DPC_NEG; es.best.key = p.L1 * (p.L2 + 1); }
       else { es.mode = 1; es.best.score = 0; es.best.key = 0; }
-      fill(m0, st, score, es, ln);
-      dpc_warp_best(es.best, m0.late, ln);
+      fill(m0, st, score, es, ln);                                      /* leaves es.best reduced over the lanes */
       finalscore = es.best.score;
       brL = es.best.key / (p.L2 + 1); bcL = es.best.key % (p.L2 + 1);
       uint16_t *ops = (uint16_t *)(bulk + a.ops[0]);
@@ -773,7 +799,6 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         for (int i = ln.lane; i < p.L1; i += ln.n) {
           int qf = pool[p.q0 + (uint32_t)i], qr = pool[p.q0 + (uint32_t)(p.L1 - 1 - i)];
           m0.rowch[i] = (uint8_t)qf; m1.rowch[i] = (uint8_t)qr;
-          if (m0.planes || m1.planes) m0.prof[i] = dpc_pack_prof(score, qf);      /* m1 reads the same array backwards */
         }
         for (int i = ln.lane; i < p.L2; i += ln.n) {
           const int g = dpc_genomic_code(p, blocks, p.off2 + i);
@@ -804,11 +829,13 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       if (!cdna) {
         const uint8_t *aux = pool + p.aux, *lknown = 0, *rknown = 0;
         const double *lp = 0, *rp = 0;
-        if (p.flags & DPC_F_PROBMODE) { lp = (const double *)aux; rp = lp + p.L2; aux += 8 * (uint32_t)(p.L2 + p.L2R); }
-        if (p.flags & DPC_F_KNOWN) { lknown = aux; rknown = aux + p.L2; }
-        dpc_bridge_intron(br, m0, m1, p, lknown, rknown, lp, rp, arena + a.di[0], arena + a.di[1], (int8_t *)(arena + a.itab), ln);
+        const uint8_t *introns = 0;
+        if (p.flags & DPC_F_PROBMODE) { lp = (const double *)aux; rp = lp + p.L2 + 1; aux += 8 * (uint32_t)(p.L2 + p.L2R + 2); }
+        if (p.flags & DPC_F_KNOWN) { lknown = aux; rknown = aux + p.L2 + 1; aux += (uint32_t)(p.L2 + p.L2R + 2); }
+        if (p.flags & DPC_F_INTRONS) introns = pool + (((uint32_t)(aux - pool) + 3u) & ~3u);
+        dpc_bridge_intron(br, m0, m1, p, lknown, rknown, lp, rp, introns, arena + a.di[0], arena + a.di[1], (int8_t *)(arena + a.itab), ln);
         ok = br.have && br.finalscore >= 0;                               /* 4083-4101 */
-        if (ok && !(p.flags & DPC_F_NOVEL) && (p.flags & DPC_F_KNOWN) && (!lknown[br.cL] || !rknown[br.cR])) ok = 0;
+        if (ok && !(p.flags & (DPC_F_NOVEL | DPC_F_INTRONS)) && (p.flags & DPC_F_KNOWN) && (!lknown[br.cL] || !rknown[br.cR])) ok = 0;
       } else {
         dpc_bridge_cdna(br, m0, m1, p, ln);
         ok = br.have;
@@ -840,6 +867,7 @@ struct GenericFill {
   enum { fillmode = 1 };
   DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
     dpc_fill_generic(m, st, score, es, ln);
+    dpc_warp_best(es.best, m.late, ln);
   }
   DPC_HDM void pair(const Mat &mA, const Mat &mB, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
     dpc_fill_generic(mA, st, score, es, ln);

@@ -477,6 +477,8 @@ struct Batch {
         if (L2 > g.maxlength2) L2 = g.maxlength2;
       } else {
         L1 = L2 = (L1 < L2 ? L1 : L2);                                 /* 2358-2369 */
+        /* not clipped by the reference; the diagonal leaves the device as M runs of at most DPC_OP_MAXLEN columns */
+        if (L1 > DPC_INLINE_OPS * DPC_OP_MAXLEN) return DPC_ERR_UNSUPPORTED;
       }
       h.L1 = L1; h.L2 = L2;
       if (!alphabet_ok(five ? p.seq1 - (L1 - 1) : p.seq1, L1)) return DPC_ERR_ALPHABET;
@@ -536,23 +538,58 @@ struct Batch {
       d.L1 = L1; d.L2 = L2L; d.L2R = L2R; d.off2 = p.offset2; d.off2R = p.offset2R;
       d.gap = p.offset2R - p.offset2;
       d.q0 = h.q0 = pool_put(p.seq1, L1);
-      if (p.use_probabilities_p || g.setup.splice_known) {
+      /* novelsplicingp == false with an intron-level IIT: the bridge only looks at given introns and ignores
+         use_probabilities_p (the test at 3552 comes first) */
+      const bool constrained = !g.setup.novelsplicingp && g.setup.splice_known && g.setup.intron_level;
+      if (constrained && g.setup.splice_intron == NULL) return DPC_ERR_STATE;
+      const bool probmode = p.use_probabilities_p && !constrained;
+      if (probmode || g.setup.splice_known) {
+        /* aux block: [probabilities: (L2L+1) + (L2R+1) doubles] [known flags: (L2L+1) + (L2R+1) bytes]
+           [given introns: uint32 count, then (cL, cR) uint16 pairs].  One spare entry per side, zero like the
+           reference's CALLOC(length2+1) arrays: the bridge reads index length1-1, which may equal length2 */
         pool_align(8);
         d.aux = h.aux = (uint32_t)pool.size();
-        std::vector<uint8_t> known((size_t)L2L + L2R, 0);
+        std::vector<uint8_t> known((size_t)L2L + L2R + 2, 0);
+        uint8_t *lknown = known.data(), *rknown = known.data() + L2L + 1;
         if (g.setup.splice_known) {
           d.flags |= DPC_F_KNOWN;
-          for (int c = 0; c < L2L - 1; c++) known[c] = site_known(p, true, c);
-          for (int c = 0; c < L2R - 1; c++) known[L2L + c] = site_known(p, false, c);
+          for (int c = 0; c < L2L - 1; c++) lknown[c] = site_known(p, true, c);
+          for (int c = 0; c < L2R - 1; c++) rknown[c] = site_known(p, false, c);
         }
-        if (p.use_probabilities_p) {
+        if (probmode) {
           d.flags |= DPC_F_PROBMODE;
-          std::vector<double> pr((size_t)L2L + L2R, 0.0);
-          for (int c = 0; c < L2L - 1; c++) pr[c] = site_prob(p, true, c, known[c] != 0);
-          for (int c = 0; c < L2R - 1; c++) pr[L2L + c] = site_prob(p, false, c, known[L2L + c] != 0);
+          std::vector<double> pr((size_t)L2L + L2R + 2, 0.0);
+          for (int c = 0; c < L2L - 1; c++) pr[c] = site_prob(p, true, c, lknown[c] != 0);
+          for (int c = 0; c < L2R - 1; c++) pr[L2L + 1 + c] = site_prob(p, false, c, rknown[c] != 0);
           pool_put((const char *)pr.data(), (int)(pr.size() * sizeof(double)));
         }
         if (g.setup.splice_known) pool_put((const char *)known.data(), (int)known.size());
+        if (constrained) {
+          /* the given introns among the known (left, right) site pairs, 3596-3615: the IIT lookup happens here */
+          d.flags |= DPC_F_INTRONS;
+          std::vector<uint16_t> pairs;
+          const dpc_setup_t &su = g.setup;
+          for (int cL = 1; cL < L2L - 1; cL++) {
+            if (!lknown[cL]) continue;
+            for (int cR = 1; cR < L2R - 1; cR++) {
+              if (!rknown[cR]) continue;
+              int yes;
+              if (p.watsonp) {
+                const uint32_t pos1 = p.chrpos + p.offset2 + cL, pos2 = p.chrpos + p.offset2R - cR + 1;
+                yes = su.splice_intron(p.chrnum, pos1, pos2 + 1U, p.cdna_direction, su.user);
+              } else {
+                const uint32_t pos1 = p.chrpos + (p.genomiclength - 1) - p.offset2 - cL + 1;
+                const uint32_t pos2 = p.chrpos + (p.genomiclength - 1) - p.offset2R + cR;
+                yes = su.splice_intron(p.chrnum, pos2, pos1 + 1U, -p.cdna_direction, su.user);
+              }
+              if (yes) { pairs.push_back((uint16_t)cL); pairs.push_back((uint16_t)cR); }
+            }
+          }
+          pool_align(4);
+          const uint32_t npairs = (uint32_t)(pairs.size() / 2);
+          pool_put((const char *)&npairs, 4);
+          if (npairs) pool_put((const char *)pairs.data(), (int)(pairs.size() * sizeof(uint16_t)));
+        }
       }
       todev = true;
       break;
@@ -888,14 +925,16 @@ struct Batch {
       break;                                                           /* npairs: counted by rebuilding */
     case DPC_GENOME_GAP: {
       r.finalscore = dr.finalscore;
-      r.introntype = ((dr.status & DPC_ST_HAVE) && !p.use_probabilities_p) ? dr.introntype : DPC_UNSET;
+      const uint32_t dflags = dprobs[h.dev].flags;
+      if (dflags & DPC_F_INTRONS) r.introntype = 0;                   /* *best_introntype = NONINTRON, 3695 */
+      else r.introntype = ((dr.status & DPC_ST_HAVE) && !p.use_probabilities_p) ? dr.introntype : DPC_UNSET;
       npairs = 0;
       if (dr.status & DPC_ST_OK) {
         const uint8_t *known = (G().setup.splice_known != NULL)
-            ? &pool[h.aux + (p.use_probabilities_p ? 8u * (uint32_t)(p.length2 + p.length2R) : 0u)] : NULL;
+            ? &pool[h.aux + ((dflags & DPC_F_PROBMODE) ? 8u * (uint32_t)(p.length2 + p.length2R + 2) : 0u)] : NULL;
         if (p.finalp) {                                                /* 4104-4108 */
           r.left_prob = site_prob(p, true, dr.bestcL, known && known[dr.bestcL]);
-          r.right_prob = site_prob(p, false, dr.bestcR, known && known[p.length2 + dr.bestcR]);
+          r.right_prob = site_prob(p, false, dr.bestcR, known && known[p.length2 + 1 + dr.bestcR]);
         }
         r.new_leftgenomepos = p.offset2 + (dr.bestcL - 1);             /* 5000-5004 */
         r.new_rightgenomepos = p.offset2R - (dr.bestcR - 1);
@@ -934,7 +973,7 @@ inline const char *strerror_(int code) {
   case DPC_ERR_CUDA: return "CUDA device or driver error (there is no CPU fallback)";
   case DPC_ERR_ARG: return "malformed problem";
   case DPC_ERR_ALPHABET: return "query byte >= 128";
-  case DPC_ERR_UNSUPPORTED: return "unsupported bridge mode";
+  case DPC_ERR_UNSUPPORTED: return "run too long for the traceback op format (QUERYEND_NOGAPS end of more than 622 554 columns)";
   case DPC_ERR_STATE: return "library not initialised / bad ticket / missing hook";
   case DPC_ERR_NOMEM: return "out of memory or output capacity too small";
   default: return "unknown error";

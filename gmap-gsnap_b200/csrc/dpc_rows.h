@@ -48,10 +48,17 @@
  * NEG-ish operands belong to cells the traceback cannot reach (it follows real-valued chains) and the bridges
  * only read in-band cells.  Everything a reachable cell can observe is exact. */
 template <int CPL> struct RowState {
-  vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL], bias[CPL];
+  vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL];
   vec::VM kok[CPL], ebok[CPL];
   vec::VI bs, bk;
+  int rowq;                       /* score-table row of the NEXT matrix row's character (loaded one row ahead) */
 };
+
+/* offset of the score-table row of matrix row r (1-based): query rows index score[q][.], genome rows score[.][g] */
+template <bool QROWS> DPC_VFN int dpc_rows_rowq(const Mat &m, int r) {
+  const int ch = (int)m.rowch[r - 1];
+  return QROWS ? (ch & 127) << 3 : ch;
+}
 
 template <int CPL, bool QROWS>
 DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) {
@@ -59,23 +66,25 @@ DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) 
   const int L2 = m.L2, lband = m.lband, W = m.W, open = m.open, extend = m.extend;
   const VI lane = lane_index();
   s.bs = splat(es.best.score); s.bk = splat(es.best.key);
+  s.rowq = dpc_rows_rowq<QROWS>(m, 1);
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
     const VI k = lane * CPL + j;
     s.kok[j] = k < W;
-    s.kE[j] = k * extend;
+    /* diagonals past the band (k >= W; they exist because a lane owns CPL of them) get NEG here: their gap1 then
+       stays NEG-ish instead of inheriting the real prefix maximum of the band, and with it their nogap value */
+    s.kE[j] = vsel(s.kok[j], k * extend, DPC_NEG);
     s.ebok[j] = vand(k >= lband - es.eb, k <= lband + es.eb);
     const VI c0 = k - lband;                              /* column of this diagonal in row 0 */
     s.cm1[j] = vsel(s.kok[j], c0 - 1, 1 << 24);           /* c - 1 = r + cm1; diagonals past the band never become valid */
-    s.bias[j] = vsel(s.kok[j], QROWS ? -8 : 0, DPC_NEG);  /* score bias of the 4-bit profile; NEG on the diagonals past the band */
     /* row 0 (1460-1475): (0,0) nogap 0; (0,c) gap1 = open + c*extend for 1 <= c <= min(rband, L2) */
     s.Np[j] = vsel(c0 == 0, 0, DPC_NEG);
     s.G1p[j] = vsel(vand(vand(c0 >= 1, c0 <= L2), s.kok[j]), open + c0 * extend, DPC_NEG);
     s.G2p[j] = splat(DPC_NEG);
     /* column characters of row 1 (a window that slides one column per row, so it is filled for every
-       diagonal, in or out of the band) */
+       diagonal, in or out of the band): genome code, or score-table row of the query character */
     const VI ch = load_u8(m.colch, vsel(vlt_u(c0, L2), c0, 0));
-    s.sh[j] = QROWS ? (ch << 2) : ((ch & 127) << 3);
+    s.sh[j] = QROWS ? ch : ((ch & 127) << 3);
   }
 }
 
@@ -85,8 +94,10 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
   using namespace vec;
   const int L1 = m.L1, L2 = m.L2, lband = m.lband, W = m.W, open = m.open, extend = m.extend;
   const VI lane = lane_index();
-  const int prof = QROWS ? (int)m.prof[m.prof_base + r * m.prof_step] : 0;
-  const int rowg = QROWS ? 0 : (int)m.rowch[r - 1];
+  /* this row's scores: one byte load per cell from the 8-byte table row of (row character, column code) -- the
+     load/store pipe has room, the integer pipe that a shift-and-mask extract would use does not */
+  const int8_t *srow = score + s.rowq;
+  s.rowq = dpc_rows_rowq<QROWS>(m, r + 1);                /* rowch has two bytes of padding past the last row */
   (void)L1;
   /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */
   const VI upN = shfl_down1(s.Np[0], DPC_NEG), upG2 = shfl_down1(s.G2p[0], DPC_NEG);
@@ -94,17 +105,18 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
   VM p1[CPL], p2[CPL], pv[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
-    /* nogap, 1545-1561.  x > y is !(y >= x): each max also yields the tie-break predicate (vmax_ge) */
-    VM ge;
-    VI mx, best;
-    if (LATE) { mx = vmax_ge(s.G1p[j], s.Np[j], ge); p1[j] = ge; } else { mx = vmax_ge(s.Np[j], s.G1p[j], ge); p1[j] = vnot(ge); }
-    if (LATE) { best = vmax_ge(s.G2p[j], mx, ge); p2[j] = ge; } else { best = vmax_ge(mx, s.G2p[j], ge); p2[j] = vnot(ge); }
-    if (QROWS) Nn[j] = best + ((prof >> s.sh[j]) & 15) + s.bias[j];
-    else Nn[j] = best + load_i8(score, s.sh[j] + rowg) + s.bias[j];
+    /* nogap, 1545-1561: one three-way maximum; the direction follows from which operands attain it.  Without
+       jump_late_p the earlier candidate wins a tie (DIAG, then HORIZ), with it the later one (VERT, then HORIZ).
+       Plane 0 = the nogap state did NOT come from nogap (the traceback turns here), plane 1 = it came from gap2. */
+    const VI best = vmax3(s.Np[j], s.G1p[j], s.G2p[j]);
+    if (LATE) { p2[j] = s.G2p[j] == best; p1[j] = vor(p2[j], s.G1p[j] == best); }
+    else { p1[j] = s.Np[j] != best; p2[j] = vand(p1[j], s.G1p[j] != best); }
+    Nn[j] = best + load_i8(srow, s.sh[j]);
     /* gap2, 1532-1542 */
     const VI Nu = j + 1 < CPL ? s.Np[j + 1 < CPL ? j + 1 : j] : upN;
     const VI G2u = j + 1 < CPL ? s.G2p[j + 1 < CPL ? j + 1 : j] : upG2;
     const VI a = Nu + open;
+    VM ge;
     VI g2m;
     if (LATE) { g2m = vmax_ge(G2u, a, ge); pv[j] = ge; } else { g2m = vmax_ge(a, G2u, ge); pv[j] = vnot(ge); }
     G2n[j] = g2m + extend;
@@ -126,7 +138,7 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
        past the matrix the staged sentinel colch[L2] is read (those diagonals are out of the matrix anyway) */
     const int gi = r + 32 * CPL - lband - 1;
     const int chn = (int)m.colch[gi < L2 ? gi : L2];
-    const VI nxt = shfl_down1(s.sh[0], QROWS ? (chn << 2) : ((chn & 127) << 3));
+    const VI nxt = shfl_down1(s.sh[0], QROWS ? chn : ((chn & 127) << 3));
 #pragma unroll
     for (int j = 0; j + 1 < CPL; j++) s.sh[j] = s.sh[j + 1];
     s.sh[CPL - 1] = nxt;
@@ -136,7 +148,7 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
     const VI G1n = (j == 0 ? t : vmax(t, li[j > 0 ? j - 1 : 0])) + s.kE[j];
     const VM h = LATE ? (G1n >= a2[j]) : (G1n > a2[j]);
     /* directions: four ballots, one 16-byte store */
-    const uint32_t b1 = vballot(p2[j]), b0 = vballot(p1[j]) & ~b1, b2 = vballot(h), b3 = vballot(pv[j]);
+    const uint32_t b0 = vballot(p1[j]), b1 = vballot(p2[j]), b2 = vballot(h), b3 = vballot(pv[j]);
     store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
     if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), s.kok[j]);
     if (EP) {
@@ -153,14 +165,22 @@ template <int CPL, bool LATE>
 DPC_VFN void dpc_rows_finish(RowState<CPL> &s, const Mat &m, EndSearch &es) {
   using namespace vec;
   const int L1 = m.L1, L2 = m.L2;
-  if (es.mode == 2 || es.mode == 3) {
-    /* last row: best of the band (2293-2355) or the corner (4541) */
+  if (es.mode == 3) {
+    /* the corner (L1, L2) (4541): one diagonal, owned by one lane -- no search, no reduction */
+    const int k = L2 - L1 + m.lband;
+    VI v = s.Np[0];
+#pragma unroll
+    for (int j = 1; j < CPL; j++) v = vsel(splat(k % CPL) == j, s.Np[j], v);
+    es.best.score = extract(v, k / CPL);
+    es.best.key = L1 * (L2 + 1) + L2;
+    return;
+  }
+  if (es.mode == 2) {
+    /* last row: best of the band (2293-2355) */
 #pragma unroll
     for (int j = 0; j < CPL; j++) {
       const VI xl = s.cm1[j] + L1;
-      VM cand = vlt_u(xl, L2);
-      if (es.mode == 3) cand = vand(cand, xl == L2 - 1);
-      keep_better(s.bs, s.bk, s.Np[j], xl + (L1 * (L2 + 1) + 1), cand, LATE);
+      keep_better(s.bs, s.bk, s.Np[j], xl + (L1 * (L2 + 1) + 1), vlt_u(xl, L2), LATE);
     }
   }
   reduce_better(s.bs, s.bk, LATE, &es.best.score, &es.best.key);
@@ -209,7 +229,7 @@ DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_dir
     const VM inb = vand(rr >= 1, (c - lane) >= 1);
     const VI widx = (vsel(inb, rr, 1) - 1) * cpl4 + ((k & cmask) << 2);
     const VI w0 = load_u32(m.dir, widx), w1 = load_u32(m.dir, widx + 1);
-    const VI turn = ((w0 | w1) >> (k >> csh)) & 1;
+    const VI turn = (w0 >> (k >> csh)) & 1;
     const uint32_t b = vballot(vor(vnot(inb), turn != 0));
     if (b == 0) { run += 32; r -= 32; c -= 32; continue; }
     const int f = first_set(b);
@@ -265,47 +285,62 @@ DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_dir
   return nops;
 }
 
-/* The product's fill policy: row sweep for bands of up to 128 diagonals, memory-state fill beyond. */
-struct RowFill {
-  enum { fillmode = 2 };
+/* The product's fill policy: row sweep for bands of up to 128 diagonals, memory-state fill beyond.
+ * MAXCPL = 2 compiles only the 1- and 2-diagonals-per-lane sweeps (bands of up to 64 diagonals, which is every
+ * band the reference's callers produce and most of the band-30 bench): the host puts wider problems into a launch
+ * of the MAXCPL = 4 instantiation, so the common kernel carries neither the 4-diagonal loops nor the memory-state
+ * fill and fits a smaller register budget. */
+template <int MAXCPL, int KG>
+struct RowFillT {
+  enum { fillmode = 2, maxcpl = MAXCPL };
+  /* KG (kind group of the kernel: 0 one-matrix solvers, 1 genome gap, 2 cDNA gap, -1 any) prunes the variants a
+     kernel cannot meet, which halves the code of the one-matrix kernels */
   template <int CPL, bool LATE>
   DPC_HDM void go(const Mat &m, const int8_t *score, EndSearch &es) const {
-    if (!m.query_rows) dpc_fill_rows<CPL, LATE, false, true, false>(m, score, es);          /* cDNA gap */
-    else if (m.nband) dpc_fill_rows<CPL, LATE, false, true, true>(m, score, es);            /* genome gap */
+    if ((KG == 2 || KG == -1) && !m.query_rows) dpc_fill_rows<CPL, LATE, false, true, false>(m, score, es);          /* cDNA gap */
+    else if ((KG == 1 || KG == -1) && m.nband) dpc_fill_rows<CPL, LATE, false, true, true>(m, score, es);            /* genome gap */
+    else if (KG == 1 || KG == 2) return;
     else if (es.mode == 1) dpc_fill_rows<CPL, LATE, true, false, true>(m, score, es);       /* end gap, best end point */
     else dpc_fill_rows<CPL, LATE, false, false, true>(m, score, es);                        /* single gap, end to query end */
   }
   DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
-    if (!m.planes) { dpc_fill_generic(m, st, score, es, ln); return; }
+    if (MAXCPL > 2 && !m.planes) { dpc_fill_generic(m, st, score, es, ln); dpc_warp_best(es.best, m.late, ln); return; }
     if (m.late) {
       if (m.cpl == 1) go<1, true>(m, score, es);
-      else if (m.cpl == 2) go<2, true>(m, score, es);
-      else go<4, true>(m, score, es);
+      else if (MAXCPL <= 2 || m.cpl == 2) go<2, true>(m, score, es);
+      else go<MAXCPL, true>(m, score, es);
     } else {
       if (m.cpl == 1) go<1, false>(m, score, es);
-      else if (m.cpl == 2) go<2, false>(m, score, es);
-      else go<4, false>(m, score, es);
+      else if (MAXCPL <= 2 || m.cpl == 2) go<2, false>(m, score, es);
+      else go<MAXCPL, false>(m, score, es);
     }
   }
   /* both matrices of a genome / cDNA gap (mA.late == !mB.late, same rows) */
   DPC_HDM void pair(const Mat &mA, const Mat &mB, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {
-    if (mA.planes && mB.planes && mA.cpl == mB.cpl && mA.cpl <= 2 && mA.L1 == mB.L1) {
+    if (MAXCPL <= 2 || (mA.planes && mB.planes && mA.cpl == mB.cpl && mA.cpl <= 2 && mA.L1 == mB.L1)) {
       const bool q = mA.query_rows != 0;
-      if (mA.cpl == 1) {
+      if (mA.cpl == 1 && mB.cpl == 1) {
         if (mA.late) { if (q) dpc_fill_rows2<1, true, true>(mA, mB, score, es); else dpc_fill_rows2<1, true, false>(mA, mB, score, es); }
         else { if (q) dpc_fill_rows2<1, false, true>(mA, mB, score, es); else dpc_fill_rows2<1, false, false>(mA, mB, score, es); }
-      } else {
+        return;
+      } else if (mA.cpl == 2 && mB.cpl == 2) {
         if (mA.late) { if (q) dpc_fill_rows2<2, true, true>(mA, mB, score, es); else dpc_fill_rows2<2, true, false>(mA, mB, score, es); }
         else { if (q) dpc_fill_rows2<2, false, true>(mA, mB, score, es); else dpc_fill_rows2<2, false, false>(mA, mB, score, es); }
+        return;
       }
-      return;
     }
     (*this)(mA, st, score, es, ln);
     (*this)(mB, st, score, es, ln);
   }
   DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {
-    if (!m.planes) return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);
+    if (MAXCPL > 2 && !m.planes) return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);
     return dpc_walk_planes(m, r, c, revp, cdna_direction, ops);
   }
 };
+typedef RowFillT<DPC_MAX_CPL, -1> RowFill;
+/* true when every matrix of the problem runs in the 1- or 2-diagonals-per-lane sweep (RowFillT<2>) */
+DPC_HB bool dpc_narrow(const ArenaLayout &a) {
+  for (int i = 0; i < a.nmat; i++) if (!a.d[i].planes || a.d[i].cpl > 2) return false;
+  return true;
+}
 #endif /* DPC_ROWS_H */

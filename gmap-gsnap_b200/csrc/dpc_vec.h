@@ -20,6 +20,7 @@ DPC_V VI splat(int x) { return x; }
 DPC_V VI vsel(VM m, VI a, VI b) { return m ? a : b; }
 DPC_V VI vmax(VI a, VI b) { return max(a, b); }
 DPC_V VI vmin(VI a, VI b) { return min(a, b); }
+DPC_V VI vmax3(VI a, VI b, VI c) { return __vimax3_s32(a, b, c); }
 /* max(a, b) and, in the same instruction (VIMNMX with a predicate result), whether a >= b */
 DPC_V VI vmax_ge(VI a, VI b, VM &ge) { return __vibmax_s32(a, b, &ge); }
 DPC_V VM vand(VM a, VM b) { return a && b; }
@@ -99,6 +100,7 @@ DPC_V VI vsel(const VM &m, int a, int b) { return vsel(m, splat(a), splat(b)); }
 DPC_V VI vmax(const VI &a, const VI &b) { VI r; DPC_VLOOP r.v[l] = a.v[l] > b.v[l] ? a.v[l] : b.v[l]; return r; }
 DPC_V VI vmin(const VI &a, const VI &b) { VI r; DPC_VLOOP r.v[l] = a.v[l] < b.v[l] ? a.v[l] : b.v[l]; return r; }
 DPC_V VI vmax(const VI &a, int b) { return vmax(a, splat(b)); }
+DPC_V VI vmax3(const VI &a, const VI &b, const VI &c) { return vmax(vmax(a, b), c); }
 DPC_V VI vmax_ge(const VI &a, const VI &b, VM &ge) { VI r; DPC_VLOOP { ge.v[l] = a.v[l] >= b.v[l]; r.v[l] = ge.v[l] ? a.v[l] : b.v[l]; } return r; }
 DPC_V VI vmin(const VI &a, int b) { return vmin(a, splat(b)); }
 DPC_V VM vand(const VM &a, const VM &b) { VM r; DPC_VLOOP r.v[l] = a.v[l] && b.v[l]; return r; }

@@ -41,14 +41,26 @@ struct KernelArgs {
 };
 
 /* resident blocks per SM the compiler must leave room for: the one-matrix kernels fit DPC_MIN_BLOCKS_1M x 256
- * threads (3 -> 80 registers, no spills in the row loop); the two-matrix kernels keep 2 (128 registers) */
+ * threads (3 -> 80 registers); their narrow-band instantiation (1 or 2 diagonals per lane only) is asked for
+ * DPC_MIN_BLOCKS_NARROW; the two-matrix kernels keep 2 (128 registers) */
 #ifndef DPC_MIN_BLOCKS_1M
 #define DPC_MIN_BLOCKS_1M 3
 #endif
-/* SMEM: arenas in shared memory (else everything in HBM scratch); KG: kind group (0 one-matrix solvers, 1 genome
- * gap, 2 cDNA gap); GEN: route every matrix through the memory-state fill (test hook) */
-template <bool SMEM, int KG, bool GEN>
-__global__ void __launch_bounds__(256, (KG == 0 ? DPC_MIN_BLOCKS_1M : 2)) dpc_solve_kernel(const KernelArgs a) {
+#ifndef DPC_MIN_BLOCKS_NARROW
+#define DPC_MIN_BLOCKS_NARROW 4
+#endif
+/* Launch variants (one kernel instantiation each, so that each carries only its own code and address spaces):
+ *   V_NARROW  arenas in shared memory, bulk region in the arena, bands of at most 64 diagonals (RowFillT<2>)
+ *   V_WIDE    arenas in shared memory, bulk region in the arena, any band
+ *   V_SPILL   small region in shared memory, bulk region (direction planes, nogap bands, ops) in HBM scratch
+ *   V_HBM     everything in HBM scratch
+ * KG: kind group (0 one-matrix solvers, 1 genome gap, 2 cDNA gap); GEN: every matrix through the memory-state fill
+ * (test hook; not instantiated for V_NARROW). */
+enum { V_NARROW = 0, V_WIDE = 1, V_SPILL = 2, V_HBM = 3, NVARIANT = 4 };
+template <int V, int KG, bool GEN>
+__global__ void __launch_bounds__(256, (KG == 0 ? (V == V_NARROW ? DPC_MIN_BLOCKS_NARROW : DPC_MIN_BLOCKS_1M) : 2)) dpc_solve_kernel(const KernelArgs a) {
+  constexpr bool SMEM = V != V_HBM;
+  constexpr int BULK = (V == V_NARROW || V == V_WIDE) ? 1 : 0;
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DevTables s_tables;
   {
@@ -76,34 +88,40 @@ __global__ void __launch_bounds__(256, (KG == 0 ? DPC_MIN_BLOCKS_1M : 2)) dpc_so
       if (ln.lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + 64 * ln.lane));
     }
     const DevProb p = a.probs[pi];
-    /* shared-memory classes: the warp's arena holds the small region and, when it fits, the bulk region too;
-       otherwise the bulk region (direction planes, nogap bands) lives in this problem's HBM scratch.  The
-       scratch-only class (SMEM == false) keeps both regions in HBM. */
     uint8_t *scratch = a.scratch + (((uint64_t)p.scratch_hi << 32) | p.scratch_lo);
     uint8_t *arena = SMEM ? smem + (size_t)warp * a.arena_bytes : scratch;
     const uint32_t arena_bytes = SMEM ? a.arena_bytes : 0xffffffffu;
     if (GEN) {
       GenericFill fill;
-      dpc_solve_problem<GenericFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
+      dpc_solve_problem<GenericFill, KG, BULK>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
+    } else if (V == V_NARROW) {
+      RowFillT<2, KG> fill;
+      dpc_solve_problem<RowFillT<2, KG>, KG, BULK>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
     } else {
-      RowFill fill;
-      dpc_solve_problem<RowFill, KG>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
+      RowFillT<DPC_MAX_CPL, KG> fill;
+      dpc_solve_problem<RowFillT<DPC_MAX_CPL, KG>, KG, BULK>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
     }
     __syncwarp();
   }
 }
 
 typedef void (*kernel_fn)(const KernelArgs);
-/* [smem][kind group][generic] */
-static kernel_fn kernel_of(bool smem, int kg, bool gen) {
-  static const kernel_fn tab[2][3][2] = {
-    { { dpc_solve_kernel<false, 0, false>, dpc_solve_kernel<false, 0, true> },
-      { dpc_solve_kernel<false, 1, false>, dpc_solve_kernel<false, 1, true> },
-      { dpc_solve_kernel<false, 2, false>, dpc_solve_kernel<false, 2, true> } },
-    { { dpc_solve_kernel<true, 0, false>, dpc_solve_kernel<true, 0, true> },
-      { dpc_solve_kernel<true, 1, false>, dpc_solve_kernel<true, 1, true> },
-      { dpc_solve_kernel<true, 2, false>, dpc_solve_kernel<true, 2, true> } } };
-  return tab[smem ? 1 : 0][kg][gen ? 1 : 0];
+/* [variant][kind group][generic]; the generic test hook runs the narrow class in the V_WIDE instantiation */
+static kernel_fn kernel_of(int v, int kg, bool gen) {
+  static const kernel_fn tab[NVARIANT][3][2] = {
+    { { dpc_solve_kernel<V_NARROW, 0, false>, dpc_solve_kernel<V_WIDE, 0, true> },
+      { dpc_solve_kernel<V_NARROW, 1, false>, dpc_solve_kernel<V_WIDE, 1, true> },
+      { dpc_solve_kernel<V_NARROW, 2, false>, dpc_solve_kernel<V_WIDE, 2, true> } },
+    { { dpc_solve_kernel<V_WIDE, 0, false>, dpc_solve_kernel<V_WIDE, 0, true> },
+      { dpc_solve_kernel<V_WIDE, 1, false>, dpc_solve_kernel<V_WIDE, 1, true> },
+      { dpc_solve_kernel<V_WIDE, 2, false>, dpc_solve_kernel<V_WIDE, 2, true> } },
+    { { dpc_solve_kernel<V_SPILL, 0, false>, dpc_solve_kernel<V_SPILL, 0, true> },
+      { dpc_solve_kernel<V_SPILL, 1, false>, dpc_solve_kernel<V_SPILL, 1, true> },
+      { dpc_solve_kernel<V_SPILL, 2, false>, dpc_solve_kernel<V_SPILL, 2, true> } },
+    { { dpc_solve_kernel<V_HBM, 0, false>, dpc_solve_kernel<V_HBM, 0, true> },
+      { dpc_solve_kernel<V_HBM, 1, false>, dpc_solve_kernel<V_HBM, 1, true> },
+      { dpc_solve_kernel<V_HBM, 2, false>, dpc_solve_kernel<V_HBM, 2, true> } } };
+  return tab[v][kg][gen ? 1 : 0];
 }
 
 /* ---- process-wide device state ------------------------------------------------------------ */
@@ -155,10 +173,11 @@ static int ensure_device(int dev) {
   CK(cudaMemcpy(d.d_blocks, g.setup.genome_blocks, g.setup.genome_nwords * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d.d_tables, sizeof(DevTables)));
   CK(cudaMemcpy(d.d_tables, &g.tables, sizeof(DevTables), cudaMemcpyHostToDevice));
-  for (int kg = 0; kg < 3; kg++)
-    for (int gen = 0; gen < 2; gen++)
-      CK(cudaFuncSetAttribute((const void *)kernel_of(true, kg, gen != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              d.max_smem - (int)sizeof(DevTables) - 1024));
+  for (int v = 0; v < V_HBM; v++)
+    for (int kg = 0; kg < 3; kg++)
+      for (int gen = 0; gen < 2; gen++)
+        CK(cudaFuncSetAttribute((const void *)kernel_of(v, kg, gen != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                d.max_smem - (int)sizeof(DevTables) - 1024));
   d.version = g_version;
   d.ready = true;
   return DPC_OK;
@@ -188,7 +207,7 @@ static void pinned_release(void *p) { cudaFreeHost(p); }
 static Alloc pinned() { Alloc a = { pinned_alloc, pinned_release }; return a; }
 
 struct ClassLaunch {
-  bool smem;
+  int variant;                     /* V_* */
   int kg;
   uint32_t arena_bytes;
   int wpb;
@@ -196,13 +215,15 @@ struct ClassLaunch {
   int n;
 };
 
-/* The register file allows 2 blocks of 8 warps per SM, so shared memory never limits occupancy below 13 KB per
- * warp (2 x (8 x 13 KB + tables) fits in 227 KB).  Two shared-memory classes: 6 KB per warp leaves most of the
- * 228 KB to L1 (descriptors, genome blocks and query bytes are read through it), 13 KB takes what is bigger.  A
- * problem whose bulk region does not fit keeps it in HBM scratch; a problem whose small region alone does not fit
- * runs entirely from HBM scratch (last class). */
-#define NCLASS 3
-static uint32_t k_class_bytes[NCLASS] = { 6 << 10, 13 << 10, 0 };
+/* Launch classes.  Two shared-memory arena sizes: 6 KB per warp leaves most of the 228 KB to L1 (descriptors,
+ * genome blocks and query bytes are read through it), 13 KB takes what is bigger (the register file allows at most
+ * 2-4 blocks of 8 warps per SM, so 13 KB per warp never limits occupancy below that of the two-matrix kernels).  A
+ * problem whose bulk region does not fit keeps it in HBM scratch (V_SPILL); a problem whose small region alone does
+ * not fit runs entirely from HBM scratch (V_HBM).  Narrow problems (every band <= 64 diagonals) get the narrow
+ * instantiation. */
+#define NCLASS 6
+static const int k_class_variant[NCLASS] = { V_NARROW, V_NARROW, V_WIDE, V_WIDE, V_SPILL, V_HBM };
+static uint32_t k_class_bytes[NCLASS] = { 6 << 10, 13 << 10, 6 << 10, 13 << 10, 13 << 10, 0 };
 #define NBUCKET 64                       /* work buckets for longest-first scheduling */
 #define SCRATCH_BUDGET (16ull << 30)
 
@@ -229,12 +250,15 @@ struct Engine {
   Scratch scratch;
   size_t ovf_cap;
   bool flushed, waited;
+  bool dirty;                      /* something may be queued on the stream (set when a flush starts, even one that fails) */
+  int flush_err;                   /* why the last flush failed (dpc_wait reports it) */
+  int fill_gen;                    /* g_force_generic as it was when this batch was laid out */
   int nlaunch;
   float ms_total;
   int64_t h2d_bytes, d2h_bytes;
   double t_finalize;
 
-  Engine() : device(0), stream(0), ev0(0), ev1(0), live(false), ovf_cap(0), flushed(false), waited(false), nlaunch(0),
+  Engine() : device(0), stream(0), ev0(0), ev1(0), live(false), ovf_cap(0), flushed(false), waited(false), dirty(false), flush_err(0), fill_gen(0), nlaunch(0),
              ms_total(0), h2d_bytes(0), d2h_bytes(0), t_finalize(0) {}
 
   int open(int dev) {
@@ -260,9 +284,10 @@ struct Engine {
   ~Engine() { close(); }
 
   int reset() {
-    if (flushed && !waited) { cudaSetDevice(device); cudaStreamSynchronize(stream); }
+    if (dirty) { cudaSetDevice(device); cudaStreamSynchronize(stream); dirty = false; }
     batch.clear();
     flushed = waited = false;
+    flush_err = 0;
     return DPC_OK;
   }
 
@@ -280,9 +305,9 @@ struct Engine {
       a.ovf.ops = d_ovf.p; a.ovf.used = d_counters.p; a.ovf.cap = (unsigned int)ovf_cap;
       a.scratch = d_scratch.p; a.gout = d_gout.p; a.arena_bytes = L.arena_bytes; a.counter = d_counters.p + 1 + k;
       const int threads = L.wpb * 32;
-      const size_t smem = L.smem ? (size_t)L.wpb * L.arena_bytes : 0;
+      const size_t smem = L.variant != V_HBM ? (size_t)L.wpb * L.arena_bytes : 0;
       int per_sm = 1;
-      const kernel_fn fn = kernel_of(L.smem, L.kg, g_force_generic != 0);
+      const kernel_fn fn = kernel_of(L.variant, L.kg, fill_gen != 0);
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, threads, smem));
       if (per_sm < 1) per_sm = 1;
       int grid = (L.n + L.wpb - 1) / L.wpb;
@@ -298,16 +323,24 @@ struct Engine {
   /* H2D + kernels + D2H, all asynchronous on this engine's stream */
   int flush() {
     if (flushed) return DPC_ERR_STATE;
+    /* `flushed` is only set once everything is queued: a failed flush leaves the context open for dpc_reset (or a
+       retry after the caller freed memory), and dpc_wait reports the stored reason instead of a stale event */
+    dirty = true; waited = false;
+    flush_err = flush_impl();
+    if (flush_err == DPC_OK) flushed = true;
+    return flush_err;
+  }
+  int flush_impl() {
     CK(cudaSetDevice(device));
     DeviceState &d = g_dev[device];
     Batch &b = batch;
     const size_t n = b.dprobs.size();
-    flushed = true; waited = false;
     launches.clear();
     h2d_bytes = d2h_bytes = 0;
     if (n == 0) return DPC_OK;
 
-    const int with_state = g_force_generic ? 1 : 2;   /* must match FILL::fillmode of the kernel */
+    fill_gen = g_force_generic;                       /* one snapshot per batch: layout and kernels must agree */
+    const int with_state = fill_gen ? 1 : 2;          /* must match FILL::fillmode of the kernel */
     /* class (shared-memory arena or HBM only) and a work bucket per problem: within a class the list is ordered
        by descending work so that the long problems start first and the tail of the launch is made of short ones */
     cls.resize(n);
@@ -320,10 +353,11 @@ struct Engine {
         ArenaLayout a;
         dpc_layout(p, a, with_state);
         uint64_t need = 0;                 /* HBM scratch of this problem */
-        if (a.total <= k_class_bytes[0]) k = 0;
-        else if (a.total <= k_class_bytes[1]) k = 1;
-        else if (a.small <= k_class_bytes[1]) { k = 1; need = a.bulk; }
-        else { k = 2; need = a.total; }
+        const int wide = dpc_narrow(a) ? 0 : 2;
+        if (a.total <= k_class_bytes[0]) k = wide;
+        else if (a.total <= k_class_bytes[1]) k = wide + 1;
+        else if (a.small <= k_class_bytes[4]) { k = 4; need = a.bulk; }
+        else { k = 5; need = a.total; }
         if (need) {
           if (scratch_total + need > SCRATCH_BUDGET) return DPC_ERR_NOMEM;
           p.scratch_lo = (uint32_t)scratch_total; p.scratch_hi = (uint32_t)(scratch_total >> 32);
@@ -360,7 +394,7 @@ struct Engine {
       for (int q = 0; q < NBUCKET; q++) cnt += count[k * NBUCKET + q];
       if (!cnt) continue;
       ClassLaunch L;
-      L.smem = k / 3 < NCLASS - 1;
+      L.variant = k_class_variant[k / 3];
       L.kg = k % 3;
       L.arena_bytes = k_class_bytes[k / 3];
       L.wpb = 8;
@@ -399,13 +433,14 @@ struct Engine {
 
   /* blocks until the batch is back, then turns every device record into the reference's outputs */
   int wait() {
-    if (!flushed) return DPC_ERR_STATE;
+    if (!flushed) return flush_err ? flush_err : DPC_ERR_STATE;
     if (waited) return DPC_OK;
     Batch &b = batch;
     const size_t n = b.dprobs.size();
     if (n > 0) {
       CK(cudaSetDevice(device));
       CK(cudaStreamSynchronize(stream));
+      dirty = false;
       CK(cudaEventElapsedTime(&ms_total, ev0, ev1));
       static const bool no_gout = getenv("DPC_NO_GOUT") != NULL;      /* measurement aid: rebuild from the host's 2-bit genome */
       b.gout_host = no_gout ? NULL : h_gout.data();
@@ -498,7 +533,7 @@ int dpc_init(int maxlookback, int extraquerygap, int maxpeelback, int extramater
   int rc = host_init(maxlookback, extraquerygap, maxpeelback, extramaterial_end, extramaterial_paired, mode);
   g_version++;
   const char *kb = getenv("DPC_CLASS0_KB");          /* tuning aid: size of the small shared-memory class */
-  if (kb && atoi(kb) >= 1 && atoi(kb) <= 13) k_class_bytes[0] = (uint32_t)atoi(kb) << 10;
+  if (kb && atoi(kb) >= 1 && atoi(kb) <= 13) k_class_bytes[0] = k_class_bytes[2] = (uint32_t)atoi(kb) << 10;
   const char *e = getenv("DPC_FORCE_GENERIC_FILL");
   g_force_generic = (e && *e && *e != '0') ? 1 : 0;
   return rc;

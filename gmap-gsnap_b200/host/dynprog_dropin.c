@@ -112,9 +112,25 @@ static int
 dropin_splice_known (int which, int chrnum, uint32_t splicesitepos, int sign, void *user) {
   int type = (which == 0 || which == 2) ? dropin_donor_typeint : dropin_acceptor_typeint;
   (void) user;
+  if (dropin_donor_typeint < 0 || dropin_acceptor_typeint < 0) {
+    /* intron-level IIT, dynprog.c:3460-3542: donors and antiacceptors are low ends of introns, acceptors and
+       antidonors high ends (looked up one past the splice site) */
+    if (which == 0 || which == 3) {
+      return IIT_low_exists_signed_p(dropin_iit,dropin_crosstable[chrnum],splicesitepos,sign) == true;
+    } else {
+      return IIT_high_exists_signed_p(dropin_iit,dropin_crosstable[chrnum],splicesitepos+1U,sign) == true;
+    }
+  }
   /* dynprog.c:3377-3458 */
   return IIT_exists_with_divno_typed_signed(dropin_iit,dropin_crosstable[chrnum],
 					    splicesitepos,splicesitepos+1U,type,sign) == true;
+}
+
+static int
+dropin_splice_intron (int chrnum, uint32_t pos1, uint32_t pos2, int sign, void *user) {
+  (void) user;
+  /* the given-introns test of the constrained bridge, dynprog.c:3600-3615 */
+  return IIT_exists_with_divno_signed(dropin_iit,dropin_crosstable[chrnum],pos1,pos2,sign) == true;
 }
 
 static int dropin_device (void);
@@ -164,10 +180,6 @@ Dynprog_setup (bool novelsplicingp_in,
   dropin_crosstable = splicesites_divint_crosstable_in;
   dropin_donor_typeint = donor_typeint_in;
   dropin_acceptor_typeint = acceptor_typeint_in;
-  if (splicesites_iit_in != NULL && (donor_typeint_in < 0 || acceptor_typeint_in < 0)) {
-    /* intron-level known splicing (dynprog.c:3460-3542, 3552-3696) needs IIT pair lookups the library does not model */
-    dropin_fatal("Dynprog_setup: intron-level splicing IIT",DPC_ERR_UNSUPPORTED);
-  }
   if (genome_in != NULL) {
     dropin_blocks = Genome_blocks(genome_in);
     dropin_nwords = (uint64_t) (Genome_totallength(genome_in)/32U + 1)*3;
@@ -181,6 +193,8 @@ Dynprog_setup (bool novelsplicingp_in,
   s.novelsplicingp = novelsplicingp_in == true;
   s.splice_prob = dropin_splice_prob;
   s.splice_known = splicesites_iit_in != NULL ? dropin_splice_known : NULL;
+  s.splice_intron = splicesites_iit_in != NULL ? dropin_splice_intron : NULL;
+  s.intron_level = splicesites_iit_in != NULL && (donor_typeint_in < 0 || acceptor_typeint_in < 0);
   if ((rc = dpc_setup(&s)) != DPC_OK) {
     dropin_fatal("dpc_setup",rc);
   }

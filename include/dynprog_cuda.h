@@ -61,7 +61,7 @@ enum {
   DPC_ERR_CUDA = -1,          /* no device, driver error, kernel fault: fatal, like exit(9) in gmap.c:2287 */
   DPC_ERR_ARG = -2,           /* malformed problem (negative length where the reference abort()s, ...) */
   DPC_ERR_ALPHABET = -3,      /* query byte >= 128, or genome byte outside ACGTNX* */
-  DPC_ERR_UNSUPPORTED = -4,   /* known-introns-only bridge mode (dynprog.c:3552-3696): needs IIT pair lookups */
+  DPC_ERR_UNSUPPORTED = -4,   /* a run length the 16-bit traceback ops cannot carry (a QUERYEND_NOGAPS end of 16384+ columns) */
   DPC_ERR_STATE = -5,         /* called before dpc_init/dpc_setup, ticket out of range, ... */
   DPC_ERR_NOMEM = -6
 };
@@ -160,18 +160,29 @@ typedef struct dpc_pair {
  *   Needed for finalp (dynprog.c:3195-3287) and use_probabilities_p (3829-3903).
  * splice_known: known-splice-site lookup (dynprog.c:3377-3542); returns nonzero when
  *   the position is a known site.  which as above; sign as the reference passes it.
- *   NULL means splicing_iit == NULL. */
+ *   NULL means splicing_iit == NULL.
+ * With an intron-level splicing IIT (donor_typeint < 0 || acceptor_typeint < 0 in Dynprog_setup; set
+ *   dpc_setup_t.intron_level) the same hook answers dynprog.c:3460-3542 instead: the host program maps which
+ *   0 / 3 (donor, antiacceptor) to IIT_low_exists_signed_p(splicesitepos, sign) and which 1 / 2 (acceptor,
+ *   antidonor) to IIT_high_exists_signed_p(splicesitepos + 1, sign) -- the library passes the same splicesitepos
+ *   in both flavours.
+ * splice_intron: IIT_exists_with_divno_signed(iit, crosstable[chrnum], pos1, pos2, sign) (dynprog.c:3600-3615):
+ *   nonzero when (pos1, pos2) is a known intron.  Needed only for intron_level && !novelsplicingp, where the bridge
+ *   is constrained to the given introns (dynprog.c:3552-3696). */
 typedef double (*dpc_splice_prob_fn)(int which, uint32_t splice_pos, uint32_t chroffset, void *user);
 typedef int (*dpc_splice_known_fn)(int which, int chrnum, uint32_t splicesitepos, int sign, void *user);
+typedef int (*dpc_splice_intron_fn)(int chrnum, uint32_t pos1, uint32_t pos2, int sign, void *user);
 
 typedef struct dpc_setup {
   const uint32_t *genome_blocks;   /* 3 x UINT4 per 32 nt: high, low, flags (genome.c:9325-9362) */
   uint64_t genome_nwords;          /* number of UINT4 in genome_blocks */
   int32_t novelsplicingp;          /* Dynprog_setup novelsplicingp_in */
-  int32_t reserved;
+  int32_t intron_level;            /* nonzero: the splicing IIT holds introns, not typed splice sites
+                                      (donor_typeint < 0 || acceptor_typeint < 0, dynprog.c:3459) */
   dpc_splice_prob_fn splice_prob;
   dpc_splice_known_fn splice_known;
   void *user;
+  dpc_splice_intron_fn splice_intron;
 } dpc_setup_t;
 
 typedef struct dpc_ctx dpc_ctx_t;

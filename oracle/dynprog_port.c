@@ -532,9 +532,9 @@ static int solve_genome(const dpc_problem_t *p, dpc_result_t *res, Stack *out) {
   }
   if (L2L <= 0 || L2R <= 0) return DPC_ERR_ARG;
   if (L2L < L1 - 1 || L2R < L1 - 1) return DPC_ERR_ARG;   /* the reference would index rightdi/leftdi out of bounds */
-  if (!g_setup.novelsplicingp && g_setup.splice_known) {
-    /* 3552: constrained-to-known-introns needs IIT pair lookups; 4090: site-level needs both known */
-  }
+  /* 3552: with novelsplicingp == false and an intron-level IIT the scan is constrained to the given introns */
+  const int constrained = !g_setup.novelsplicingp && g_setup.splice_known && g_setup.intron_level;
+  if (constrained && !g_setup.splice_intron) return DPC_ERR_STATE;
 
   char *q = gather_query(p->seq1, L1, 0), *qr = gather_query(p->seq1 + (L1 - 1), L1, 1);
   char *gL = gather_genome(p, lo, L2L, 0), *gR = gather_genome(p, ro, L2R, 1);
@@ -561,7 +561,38 @@ static int solve_genome(const dpc_problem_t *p, dpc_result_t *res, Stack *out) {
   int finalscore, introntype = DPC_UNSET, it;
   #define NONDIAG(m, r, c) ((m).dN[AT(&(m), r, c)] == D_HORIZ || (m).dN[AT(&(m), r, c)] == D_VERT)
 
-  if (!p->use_probabilities_p) {
+  if (constrained) {
+    int best = -100000;                                                 /* 3552-3696 */
+    for (int rL = 1, rR = L1 - 1; rL < L1; rL++, rR--) {
+      int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
+      int cloR = rR - lbandR < 1 ? 1 : rR - lbandR, chighR = rR + rbandR > L2R - 1 ? L2R - 1 : rR + rbandR;
+      for (int side = 0; side < 2; side++) {
+        int lo_c = side == 0 ? cloL : cloR, hi_c = side == 0 ? chighL : chighR;
+        for (int cc = lo_c; cc <= hi_c; cc++) {
+          int cL = side == 0 ? cc : rL, cR = side == 0 ? rR : cc;
+          /* 3573-3583 / 3635-3650: the scanned side must be known, then the offset test, then the other side */
+          if (side == 0 ? lknown[cL] <= 0 : rknown[cR] <= 0) continue;
+          if (!(side == 0 ? cR < ro - lo - cL : cL < ro - lo - cR)) continue;
+          if (side == 0 ? rknown[cR] <= 0 : lknown[cL] <= 0) continue;
+          int sL = mL.N[AT(&mL, rL, cL)], sR = mR.N[AT(&mR, rR, cR)];
+          if (side == 0 ? NONDIAG(mL, rL, cL) : NONDIAG(mR, rR, cR)) { if (side == 0) sL -= 1; else sR -= 1; }
+          if (sL + sR > best) {
+            int yes;
+            if (p->watsonp) {
+              uint32_t pos1 = p->chrpos + lo + cL, pos2 = p->chrpos + ro - cR + 1;
+              yes = g_setup.splice_intron(p->chrnum, pos1, pos2 + 1U, p->cdna_direction, g_setup.user);
+            } else {
+              uint32_t pos1 = p->chrpos + (p->genomiclength - 1) - lo - cL + 1, pos2 = p->chrpos + (p->genomiclength - 1) - ro + cR;
+              yes = g_setup.splice_intron(p->chrnum, pos2, pos1 + 1U, -p->cdna_direction, g_setup.user);
+            }
+            if (yes) { best = sL + sR; bestrL = rL; bestrR = rR; bestcL = cL; bestcR = cR; have = 1; }
+          }
+        }
+      }
+    }
+    finalscore = best;                                                  /* 3694-3695 */
+    introntype = 0;
+  } else if (!p->use_probabilities_p) {
     int best = -100000, bestI = -100000;                                /* 3698-3827 */
     for (int rL = 1, rR = L1 - 1; rL < L1; rL++, rR--) {
       int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
@@ -628,7 +659,7 @@ static int solve_genome(const dpc_problem_t *p, dpc_result_t *res, Stack *out) {
   res->introntype = introntype;
 
   int ok = finalscore >= 0;                                             /* 4083-4101 */
-  if (ok && !g_setup.novelsplicingp && g_setup.splice_known && (lknown[bestcL] == 0 || rknown[bestcR] == 0)) ok = 0;
+  if (ok && !g_setup.novelsplicingp && g_setup.splice_known && !g_setup.intron_level && (lknown[bestcL] == 0 || rknown[bestcR] == 0)) ok = 0;
   if (ok && p->finalp) {                                                /* 4104-4108 */
     res->left_prob = site_prob(p, 1, bestcL, lo, ro, lknown[bestcL] > 0);
     res->right_prob = site_prob(p, 0, bestcR, lo, ro, rknown[bestcR] > 0);

@@ -58,14 +58,22 @@ static int known_hook(int divno, unsigned int x, int type, int sign) {
 bool IIT_exists_with_divno_typed_signed(IIT_T iit, int divno, unsigned int x, unsigned int y, int type, int sign) {
   (void)iit; (void)y; return (bool)known_hook(divno, x, type, sign);
 }
+/* intron-level IIT (donor_typeint < 0, dynprog.c:3460-3542): low ends are donors / antiacceptors, high ends (asked
+ * with splicesitepos + 1) acceptors / antidonors; the hook gets splicesitepos in both flavours */
 bool IIT_exists_with_divno_signed(IIT_T iit, int divno, unsigned int x, unsigned int y, int sign) {
-  (void)iit; (void)divno; (void)x; (void)y; (void)sign; return false;
+  (void)iit;
+  if (!ref_setup_.splice_intron) return false;
+  return ref_setup_.splice_intron(divno, x, y, sign, ref_setup_.user) != 0;
 }
 bool IIT_low_exists_signed_p(IIT_T iit, int divno, unsigned int x, int sign) {
-  (void)iit; (void)divno; (void)x; (void)sign; return false;
+  (void)iit;
+  if (!ref_setup_.splice_known) return false;
+  return ref_setup_.splice_known(sign > 0 ? 0 : 3, divno, x, sign, ref_setup_.user) != 0;
 }
 bool IIT_high_exists_signed_p(IIT_T iit, int divno, unsigned int x, int sign) {
-  (void)iit; (void)divno; (void)x; (void)sign; return false;
+  (void)iit;
+  if (!ref_setup_.splice_known) return false;
+  return ref_setup_.splice_known(sign > 0 ? 1 : 2, divno, x - 1U, sign, ref_setup_.user) != 0;
 }
 List_T Pair_protect(List_T pairs) { return pairs; }
 
@@ -85,7 +93,7 @@ int ref_setup(const dpc_setup_t *s) {
   Maxent_hr_setup((UINT4 *)s->genome_blocks);
   Dynprog_setup((bool)(s->novelsplicingp != 0),
                 s->splice_known ? (IIT_T)ref_crosstable_ : (IIT_T)NULL, ref_crosstable_,
-                DONOR_TYPEINT, ACCEPTOR_TYPEINT,
+                s->intron_level ? -1 : DONOR_TYPEINT, s->intron_level ? -1 : ACCEPTOR_TYPEINT,
                 NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL, /*genome*/ (Genome_T)NULL);
   return 0;
 }

@@ -53,9 +53,9 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
     uint8_t *sbase = scratch.data() + ((16 - ((uintptr_t)scratch.data() & 15)) & 15);
     const uint32_t arena_bytes = (k & 1) ? a.total : a.small;
     if (g_force_generic)
-      dpc_solve_problem<GenericFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), gfill, ln);
+      dpc_solve_problem<GenericFill, -1, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), gfill, ln);
     else
-      dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), rfill, ln);
+      dpc_solve_problem<RowFill, -1, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), rfill, ln);
   }
   b.gout_host = g_no_gout ? NULL : gout.data();     /* NULL: the rebuild decodes the 2-bit genome itself (ticket users without the stream) */
   int64_t out = 0;
@@ -111,7 +111,7 @@ extern "C" void emul_time_pack_finalize(const dpc_problem_t *problems, int n, in
     arena.assign(a.total + 64, 0);
     uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
     memset(&dres[k], 0, sizeof(DevRes));
-    dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, a.total, base, &dres[k], ovf, gout.data(), rfill, ln);
+    dpc_solve_problem<RowFill, -1, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, a.total, base, &dres[k], ovf, gout.data(), rfill, ln);
   }
   b.gout_host = gout.data();
   dpc::Scratch sc;
@@ -141,7 +141,7 @@ extern "C" double emul_time_rebuild(const dpc_problem_t *problems, int n, int re
     arena.assign(a.total + 64, 0);
     uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
     memset(&dres[k], 0, sizeof(DevRes));
-    dpc_solve_problem<RowFill, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, a.total, base, &dres[k], ovf, gout.data(), rfill, ln);
+    dpc_solve_problem<RowFill, -1, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, a.total, base, &dres[k], ovf, gout.data(), rfill, ln);
   }
   b.gout_host = getenv("EMUL_NO_GOUT") ? NULL : gout.data();
   dpc::Scratch sc;

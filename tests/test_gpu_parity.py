@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from gmap_gsnap_b200 import api
-from util import GOLDEN_SETS, Golden, mixed_problems
+from util import GOLDEN_SETS, SPLICING_IIT_MODES, Golden, long_nogaps_ends, mixed_problems, splicing_iit_hooks
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-6
@@ -107,6 +107,49 @@ def test_known_splice_sites(workload, prob_hook):
             lib.close()
 
 
+@pytest.mark.parametrize("intron_level,novel", SPLICING_IIT_MODES)
+def test_splicing_iit_modes(workload, ref, intron_level, novel):
+    """splicing_iit != NULL in all four flavours (splice-site / intron level x novel splicing allowed or not); the
+    last one is the bridge constrained to the given introns, dynprog.c:3552-3696.  Against the compiled reference."""
+    known, intron = splicing_iit_hooks(known_mod=(3 if novel else 17) if intron_level else 3, intron_mod=3)
+    r = api.RefOracle()
+    r.init()
+    s = workload.make_setup(splice_prob=r.splice_prob, splice_known=known, novelsplicingp=novel,
+                            splice_intron=intron, intron_level=intron_level)
+    r.setup(s)
+    lib = api.CudaLib()
+    lib.init()
+    lib.setup(s)
+    lib.open(0)
+    try:
+        probs = workload.genome_gaps(1500, seed=51 + 2 * intron_level + novel, finalp_mode=2, prob_mode_pm=100, long_frac=0.03, long_hi=611)
+        probs = api.arm_probability_mode(probs, r)
+        for force in (0, 1):
+            lib.lib.dpc_set_fill(force)
+            assert not api.compare(*r.solve(probs), *lib.solve(probs), rtol=RTOL)
+    finally:
+        lib.lib.dpc_set_fill(0)
+        lib.close()
+
+
+def test_long_nogaps_ends(workload, ref, cuda):
+    """QUERYEND_NOGAPS ends of 16 383 .. 40 000 columns (several M ops per problem), bulk and ticket API."""
+    probs = long_nogaps_ends(workload)
+    want = ref.solve(probs)
+    got = cuda.solve(probs)
+    assert not api.compare(*want, *got)
+    L = cuda.lib
+    cuda.refresh_genome()
+    assert L.dpc_reset(cuda.ctx) == 0
+    assert L.dpc_add_bulk(cuda.ctx, probs.ctypes.data_as(C.c_void_p), len(probs)) == 0
+    assert L.dpc_flush(cuda.ctx) == 0 and L.dpc_wait(cuda.ctx) == 0
+    buf = np.zeros(50000, dtype=api.PAIR_DT)
+    for t in range(len(probs)):
+        n = L.dpc_pairs(cuda.ctx, t, buf.ctypes.data_as(C.c_void_p), len(buf))
+        assert n == want[2][t + 1] - want[2][t] and (buf[:n] == want[1][want[2][t]:want[2][t + 1]]).all()
+    assert L.dpc_reset(cuda.ctx) == 0
+
+
 def test_empty_and_degenerate_batches(workload, port, cuda):
     probs = workload.end_gaps(8, seed=7)
     res, pairs, off = cuda.solve(probs[:0])
@@ -162,22 +205,30 @@ def test_full_size_properties(workload, port, cuda):
     assert not api.compare(*port.solve(sample), *cuda.solve(sample))
 
 
-@pytest.mark.parametrize("kind,n", [("single", 1_000_000), ("genome", 500_000), ("end", 1_000_000)])
+@pytest.mark.parametrize("kind,n", [("single", 1_000_000), ("genome", 500_000), ("genome_mix", 500_000), ("end", 1_000_000)])
 def test_full_size_exact_against_compiled_reference(kind, n):
     """BASELINE configs[1..3] at their full sizes, EXACT: the unmodified reference (oracle/_ref/libdynprog_ref.so,
     all host threads) solves the same problems as the GPU and every output field must be equal -- scores, counts,
-    intron boundaries, introntype, npairs, dynprogindex; the Pair records are compared on the first 100 000."""
+    intron boundaries, introntype, splice-site probabilities (rtol 1e-6), npairs, dynprogindex; the Pair records are
+    compared on the first 100 000.  genome_mix is config 3 with its stated mix: finalp and halfp both ways and a
+    10 % subset re-solved with use_probabilities_p and score_threshold = first-pass finalscore - 11 (stage3.c:5833)."""
     import bench
     if not os.path.exists(os.path.join(bench.ROOT, "oracle", "_ref", "libdynprog_ref.so")):
         pytest.skip("compiled reference not built")
-    w, probs = bench.make_workload(0, n, kind)
+    mix = kind == "genome_mix"
+    w, probs = bench.make_workload(0, n, "genome" if mix else kind, genome_mix=mix)
     ref = api.RefOracle()
     ref.init()
     ref.setup(w.make_setup())
+    hook = ref.splice_prob if mix else None        # finalp / probability mode need the MaxEnt hook
+    ref.setup(w.make_setup(splice_prob=hook))
     lib = api.CudaLib()
     lib.init()
-    lib.setup(w.make_setup())
+    lib.setup(w.make_setup(splice_prob=hook))
     lib.open(0)
+    if mix:
+        probs = api.arm_probability_mode(probs, lib)
+        assert (probs["use_probabilities_p"] == 1).sum() > n // 20 and probs["finalp"].sum() > n // 3
     try:
         got, _, _ = lib.solve(probs, want_pairs=False)
         want, _ = ref.solve_mt(probs, os.cpu_count() or 1)

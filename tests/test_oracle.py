@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from gmap_gsnap_b200 import api
-from util import GOLDEN_SETS, Golden, mixed_problems
+from conftest import has_ref
+from util import GOLDEN_SETS, SPLICING_IIT_MODES, Golden, long_nogaps_ends, mixed_problems, splicing_iit_hooks
 
 
 @pytest.fixture(scope="module")
@@ -116,6 +117,44 @@ def test_known_splice_sites(workload, prob_hook):
         assert not api.compare(*want, *got)
         if not novel:
             assert want[0]["null_list"].sum() > 0
+
+
+def test_long_nogaps_ends(workload, ref, port, emul):
+    """QUERYEND_NOGAPS ends are not clipped to maxlength (dynprog.c:5179): 16 384+ columns need more than one
+    traceback op; beyond 38 ops the problem is refused, never truncated."""
+    probs = long_nogaps_ends(workload)
+    want = ref.solve(probs)
+    assert (want[0]["npairs"] >= 16383).all()
+    assert not api.compare(*want, *port.solve(probs))
+    assert not api.compare(*want, *emul.solve(probs))
+    probs["length1"][0] = probs["length2"][0] = 38 * 16383 + 1
+    with pytest.raises(RuntimeError):
+        emul.solve(probs[:1])
+
+
+@pytest.mark.parametrize("intron_level,novel", SPLICING_IIT_MODES)
+def test_splicing_iit_modes_match_compiled_reference(workload, intron_level, novel):
+    """Every flavour of splicing_iit != NULL in bridge_intron_gap: splice-site level (dynprog.c:3377-3458) and intron
+    level (3460-3542), novel splicing allowed or not -- the latter with an intron-level IIT is the scan constrained
+    to the given introns (3552-3696).  Compiled reference == restatement == device routines on the CPU; a tenth of
+    the problems ask for use_probabilities_p (ignored by the constrained scan)."""
+    if not has_ref():
+        pytest.skip("compiled reference not built")
+    known, intron = splicing_iit_hooks(known_mod=(3 if novel else 17) if intron_level else 3, intron_mod=3)
+    r = api.RefOracle()
+    r.init()
+    s = workload.make_setup(splice_prob=r.splice_prob, splice_known=known, novelsplicingp=novel,
+                            splice_intron=intron, intron_level=intron_level)
+    o, e = api.PortOracle(), api.EmulLib()
+    o.init(); e.init()
+    r.setup(s); o.setup(s); e.setup(s)
+    probs = workload.genome_gaps(400, seed=41 + 2 * intron_level + novel, finalp_mode=2, prob_mode_pm=100, long_frac=0.02, long_hi=300)
+    probs = api.arm_probability_mode(probs, o)
+    want = r.solve(probs)
+    assert not api.compare(*want, *o.solve(probs))
+    assert not api.compare(*want, *e.solve(probs))
+    nulls = int(want[0]["null_list"].sum())
+    assert len(probs) - nulls > 20 and (novel or nulls > 0), nulls
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])

@@ -59,3 +59,36 @@ def mixed_problems(w, n_each, seed, **kw):
     allp = np.concatenate(sets)
     rng = np.random.default_rng(seed)
     return allp[rng.permutation(len(allp))]
+
+
+def splicing_iit_hooks(known_mod=3, intron_mod=2):
+    """Deterministic stand-ins for the splicing IIT lookups behind dpc_setup_t.splice_known / splice_intron."""
+    known = api.KNOWN_FN(lambda which, chrnum, pos, sign, user: int((pos * 7 + which + chrnum) % known_mod == 0))
+    intron = api.INTRON_FN(lambda chrnum, pos1, pos2, sign, user: int((pos1 + 3 * pos2 + sign + chrnum) % intron_mod == 0))
+    return known, intron
+
+
+SPLICING_IIT_MODES = [(0, 1), (0, 0), (1, 1), (1, 0)]        # (intron_level, novelsplicingp)
+
+
+def long_nogaps_ends(w, lengths=(16383, 16384, 20000, 40000), seed=5):
+    """QUERYEND_NOGAPS end gaps longer than one traceback op can carry (the reference does not clip these ends,
+    dynprog.c:5179-5186): both ends, both strands, random query (a quarter of the columns match)."""
+    rng = np.random.default_rng(seed)
+    base = w.end_gaps(64, seed=seed)
+    out = []
+    for n in lengths:
+        for kind in (api.END3_GAP, api.END5_GAP):
+            for watson in (0, 1):
+                p = base[(base["kind"] == kind)][:1].copy()
+                p["watsonp"] = watson
+                p["chrpos"], p["genomiclength"] = 1000, 90000
+                off = 30000 if kind == api.END3_GAP else 30000 + n
+                q = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+                w._keep.append(q)
+                p["endalign"] = api.QUERYEND_NOGAPS
+                p["length1"], p["length2"] = n, n + 10
+                p["offset2"] = off
+                p["seq1"] = q.ctypes.data + (n - 1 if kind == api.END5_GAP else 0)
+                out.append(p)
+    return np.concatenate(out)
