@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from gmap_gsnap_b200 import api  # noqa: E402
+from oracle import checkers  # noqa: E402   (the CPU reference: cpu_baseline and --impl reference only)
 
 METRIC = "banded_dp_gcups_single_gap"
 UNIT = "GCUPS"
@@ -109,7 +110,7 @@ WORKLOADS = {
 
 def make_workload(rank, n, kind="single", genome_mix=False):
     """The synthetic inputs of BASELINE configs[1..3].  genome_mix: config 3's stated mix -- finalp and
-    halfp both ways, a 10 % subset marked for the probability-mode second call (arm it with api.arm_probability_mode)."""
+    halfp both ways, a 10 % subset marked for the probability-mode second call (arm it with checkers.arm_probability_mode)."""
     w = api.Workload(GENOME_BASES, seed=0x9E3779B9 + rank, nchr=4)
     if kind == "genome":
         probs = w.genome_gaps(n, extraband=7, seed=0x5EED0003 + 1000 * rank, finalp_mode=2 if genome_mix else 0,
@@ -125,7 +126,7 @@ def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path, all host threads (gmap -t N shape, gmap.c:2254-2276)."""
     if rank != 0:
         return
-    ref = api.RefOracle()
+    ref = checkers.RefOracle()
     ref.init()
     cores = os.cpu_count() or 1
     sample = min(N_PROBLEMS, max(20000, 40000 * cores))
@@ -299,7 +300,7 @@ def main():
         for _ in range(args.warmup + args.steps):
             lib.check(L.dpc_relaunch(lib.ctx), "dpc_relaunch")
             lib.check(L.dpc_sync(lib.ctx), "dpc_sync")
-            t.append(lib.kernel_ms()[2])
+            t.append(lib.kernel_ms())
         print(json.dumps({"kernel_only_ms": t, "problems": n, "cells": int(lib.stats().cells)}), flush=True)
         lib.close()
         return
@@ -314,7 +315,7 @@ def main():
     def step():
         lib.check(L.dpc_relaunch(lib.ctx), "dpc_relaunch")
         lib.check(L.dpc_sync(lib.ctx), "dpc_sync")
-        return lib.kernel_ms()[2]
+        return lib.kernel_ms()
 
     for _ in range(args.warmup):
         step()
@@ -334,6 +335,10 @@ def main():
     r2, pairs, off = lib.solve(probs)             # also sizes the caller-owned output arrays, reused below
     npairs = len(pairs)
     pairs = np.zeros(npairs + 1024, dtype=api.PAIR_DT)
+    # caller-owned output arrays, page-locked once (like a long-lived pair pool): the copy engine writes into them
+    pinned = [pairs, r2, probs, w.last_qbuf]
+    for a in pinned:
+        lib.register(a)
     for _ in range(2):
         assert lib.solve_into(probs, r2, pairs, off) == npairs
     barrier()
@@ -348,6 +353,8 @@ def main():
     for _ in range(args.e2e_steps):
         lib.solve_into(probs, r2, None, off)
     e2e_results_s = (time.perf_counter() - t0) / args.e2e_steps
+    for a in pinned:
+        lib.unregister(a)
     pairs = pairs[:npairs]
     barrier()
     sampler.stop_flag.set()
@@ -396,7 +403,7 @@ def main():
     if args.workload != "single":
         line["metric"] = "banded_dp_gcups_%s_gap" % args.workload
     if rank == 0 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdynprog_ref.so")):
-        ref = api.RefOracle()
+        ref = checkers.RefOracle()
         ref.init()
         ref.setup(w.make_setup())
         cores = os.cpu_count() or 1

@@ -71,9 +71,9 @@ class Setup(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("nproblems", C.c_int64), ("nmatrices", C.c_int64), ("cells", C.c_int64),
-        ("fill_bytes", C.c_int64), ("traceback_bytes", C.c_int64),
+        ("fill_bytes", C.c_int64), ("pipeline_chunks", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-        ("launches", C.c_int32), ("reserved", C.c_int32),
+        ("launches", C.c_int32), ("host_chunks", C.c_int32),
     ]
 
 
@@ -168,6 +168,7 @@ class Workload:
         if used < 0:
             raise RuntimeError("%s: query buffer too small" % fname)
         self._keep.append(qbuf)
+        self.last_qbuf = qbuf          # the contiguous query buffer the problems just generated point into
         return probs
 
     def single_gaps(self, n, extraband=30, **kw):
@@ -285,7 +286,8 @@ class Workload:
 
 # --------------------------------------------------------------------------- solvers
 class _SolverLib:
-    """Common driver for the three libraries that speak dpc_problem_t / dpc_result_t."""
+    """Common driver for libraries that speak dpc_problem_t / dpc_result_t (the product here; the CPU checkers in
+    oracle/checkers.py)."""
 
     prefix = None
 
@@ -315,88 +317,6 @@ def _solve_common(fn, problems, want_pairs=True, pair_cap=None):
     return results, pairs[: pair_off[n]] if want_pairs else pairs, pair_off
 
 
-class PortOracle(_SolverLib):
-    """oracle/liboracle_port.so -- TEST INFRASTRUCTURE (CPU restatement)."""
-
-    def __init__(self, path=None):
-        super().__init__(path or os.path.join(ROOT, "oracle", "liboracle_port.so"))
-        L = self.lib
-        L.port_init.argtypes = [C.c_int] * 6
-        L.port_setup.argtypes = [C.POINTER(Setup)]
-        L.port_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-        L.port_pairdistance.argtypes = [C.c_int] * 3
-
-    def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
-        self.lib.port_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
-
-    def setup(self, setup):
-        self._setup = setup
-        self.lib.port_setup(C.byref(setup))
-
-    def solve(self, problems, want_pairs=True):
-        return _solve_common(self.lib.port_solve, problems, want_pairs)
-
-
-class RefOracle(_SolverLib):
-    """oracle/_ref/libdynprog_ref.so -- the compiled, unmodified reference (TEST INFRASTRUCTURE)."""
-
-    def __init__(self, path=None):
-        super().__init__(path or os.path.join(ROOT, "oracle", "_ref", "libdynprog_ref.so"))
-        L = self.lib
-        L.ref_init.argtypes = [C.c_int] * 6
-        L.ref_setup.argtypes = [C.POINTER(Setup)]
-        L.ref_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-        L.ref_solve_mt.restype = C.c_double
-        L.ref_solve_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
-        L.ref_pairdistance.argtypes = [C.c_int] * 2
-        L.ref_splice_prob.restype = C.c_double
-        self.splice_prob = C.cast(L.ref_splice_prob, PROB_FN)
-
-    def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
-        self.lib.ref_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
-
-    def setup(self, setup):
-        self._setup = setup
-        self.lib.ref_setup(C.byref(setup))
-
-    def solve(self, problems, want_pairs=True):
-        return _solve_common(self.lib.ref_solve, problems, want_pairs)
-
-    def solve_mt(self, problems, nthreads):
-        results = np.zeros(len(problems), dtype=RESULT_DT)
-        secs = self.lib.ref_solve_mt(_ptr(problems), len(problems), _ptr(results), nthreads)
-        return results, secs
-
-
-class EmulLib(_SolverLib):
-    """tests/emul/libdpc_emul.so -- TEST SCAFFOLDING: the device routines compiled single-lane for the CPU."""
-
-    def __init__(self, path=None):
-        super().__init__(path or os.path.join(ROOT, "tests", "emul", "libdpc_emul.so"))
-        L = self.lib
-        L.emul_init.argtypes = [C.c_int] * 6
-        L.emul_setup.argtypes = [C.POINTER(Setup)]
-        L.emul_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-        L.emul_pairdistance.argtypes = [C.c_int] * 3
-        L.emul_set_fill.argtypes = [C.c_int]
-
-    def set_fill(self, force_generic):
-        """0: row-sweep fill + lane-parallel walk on 32 simulated lanes; 1: memory-state fill + serial walk."""
-        self.lib.emul_set_fill(int(force_generic))
-
-    def init(self, mode=0, maxlookback=600, extraquerygap=10, maxpeelback=11, end=10, paired=8):
-        rc = self.lib.emul_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode)
-        if rc != 0:
-            raise RuntimeError("emul_init failed: %d" % rc)
-
-    def setup(self, setup):
-        self._setup = setup
-        self.lib.emul_setup(C.byref(setup))
-
-    def solve(self, problems, want_pairs=True):
-        return _solve_common(self.lib.emul_solve, problems, want_pairs)
-
-
 class CudaLib(_SolverLib):
     """gmap-gsnap_b200/csrc/libdynprog_cuda.so -- THE PRODUCT."""
 
@@ -423,7 +343,13 @@ class CudaLib(_SolverLib):
         L.dpc_set_fill.argtypes = [C.c_int]
         L.dpc_stream.restype = C.c_void_p
         L.dpc_stream.argtypes = [C.c_void_p]
-        L.dpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
+        L.dpc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.dpc_ctx_new_multi.restype = C.c_void_p
+        L.dpc_ctx_new_multi.argtypes = [C.POINTER(C.c_int), C.c_int]
+        L.dpc_host_register.argtypes = [C.c_void_p, C.c_uint64]
+        L.dpc_host_unregister.argtypes = [C.c_void_p]
+        L.dpc_set_path.argtypes = [C.c_int]
+        L.dpc_device_count.restype = C.c_int
         L.dpc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.dpc_pairdistance.argtypes = [C.c_int] * 3
         L.dpc_strerror.restype = C.c_char_p
@@ -512,9 +438,23 @@ class CudaLib(_SolverLib):
         return s
 
     def kernel_ms(self):
-        ms = (C.c_float * 3)()
+        ms = C.c_float()
         self.check(self.lib.dpc_last_kernel_ms(self.ctx, C.byref(ms)), "dpc_last_kernel_ms")
-        return list(ms)
+        return float(ms.value)
+
+    def open_multi(self, devices):
+        arr = (C.c_int * len(devices))(*devices)
+        self.ctx = self.lib.dpc_ctx_new_multi(arr, len(devices))
+        if not self.ctx:
+            raise RuntimeError("dpc_ctx_new_multi(%r) failed: no usable CUDA device (no CPU fallback)" % (devices,))
+        return self
+
+    def register(self, array):
+        """Page-locks a numpy array so that dpc_solve can copy results into it in place."""
+        self.check(self.lib.dpc_host_register(_ptr(array), array.nbytes), "dpc_host_register")
+
+    def unregister(self, array):
+        self.check(self.lib.dpc_host_unregister(_ptr(array)), "dpc_host_unregister")
 
 
 # --------------------------------------------------------------------------- comparison
@@ -586,19 +526,4 @@ def attach(problems, qbuf, offs):
             out["seq1R"][i] = base + offs[i] + int(out["offset1R"][i]) - int(out["offset1"][i])
         else:
             out["seq1"][i] = base + offs[i]
-    return out
-
-
-def arm_probability_mode(problems, solver):
-    """Genome gaps the generator marked use_probabilities_p == 2 become the reference's second call
-    (stage3.c:5833): use_probabilities_p = true with score_threshold = first-pass finalscore + QOPEN + 3*QINDEL
-    (scores.h:7-8) = finalscore - 11.  `solver` is any of the libraries above."""
-    out = problems.copy()
-    sel = np.nonzero(out["use_probabilities_p"] == 2)[0]
-    if len(sel) == 0:
-        return out
-    out["use_probabilities_p"][sel] = 0
-    res, _, _ = solver.solve(out[sel], want_pairs=False)
-    out["use_probabilities_p"][sel] = 1
-    out["score_threshold"][sel] = res["finalscore"] - 11
     return out

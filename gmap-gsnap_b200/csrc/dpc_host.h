@@ -754,18 +754,33 @@ struct Batch {
   }
   int rebuild(int i, const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s, bool stream_dst = false) const {
     const HostProb &h = probs[i];
-    const dpc_problem_t &p = P(i);
+    return rebuild_core(P(i), (const char *)&pool[h.q0], &pool[h.q1], h.L1, h.L2, staged(h), dr, ops, dst, s, stream_dst);
+  }
+  /* lengths as the entry points clip them (5179-5186, 2358-2369): what the device worked on */
+  static void clipped_lengths(const dpc_problem_t &p, int *L1, int *L2) {
+    *L1 = p.length1; *L2 = p.length2;
+    if (p.kind == DPC_END5_GAP || p.kind == DPC_END3_GAP) {
+      if (p.endalign != DPC_QUERYEND_NOGAPS) {
+        if (*L1 > G().maxlength1) *L1 = G().maxlength1;
+        if (*L2 > G().maxlength2) *L2 = G().maxlength2;
+      } else *L1 = *L2 = (*L1 < *L2 ? *L1 : *L2);
+    }
+  }
+  /* q: the query bytes of the problem in forward order (first byte of the span the problem points at); codes2: the
+     junction string as genome codes (splice-junction solvers only); L1c / L2c: clipped lengths; staged: the genome
+     characters the device staged for this problem, or NULL (decode the 2-bit genome here) */
+  static int rebuild_core(const dpc_problem_t &p, const char *q, const uint8_t *codes2, int L1c, int L2c, const char *staged_g,
+                          const DevRes &dr, const uint16_t *ops, dpc_pair_t *dst, Scratch &s, bool stream_dst) {
     const uint32_t *blocks = G().setup.genome_blocks;
-    const char *q = (const char *)&pool[h.q0];
     Out out; out.p = dst; out.n = 0; out.stream = stream_dst;
     const bool nostar = !(dr.status & DPC_ST_STAR);
     switch (p.kind) {
     case DPC_SINGLE_GAP: {
-      const char *ga = staged(h);
+      const char *ga = staged_g;
 #ifdef DPC_PROFILE_REBUILD
       unsigned long long t0 = __rdtsc();
 #endif
-      if (!ga) { char *buf = fit(s.ga, h.L2); gather_genome(p, blocks, p.offset2, h.L2, false, buf); ga = buf; }
+      if (!ga) { char *buf = fit(s.ga, L2c); gather_genome(p, blocks, p.offset2, L2c, false, buf); ga = buf; }
 #ifdef DPC_PROFILE_REBUILD
       unsigned long long t1 = __rdtsc();
 #endif
@@ -778,11 +793,11 @@ struct Batch {
     }
     case DPC_END5_GAP: case DPC_END3_GAP: {
       const bool five = p.kind == DPC_END5_GAP;
-      char *qa = fit(s.qa, h.L1);
-      const char *ga = staged(h);
-      for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
-      if (!ga) { char *buf = fit(s.ga, h.L2); gather_genome(p, blocks, p.offset2, h.L2, five, buf); ga = buf; }
-      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 2); sL.n = 0;
+      char *qa = fit(s.qa, L1c);
+      const char *ga = staged_g;
+      for (int k = 0; k < L1c; k++) qa[k] = five ? q[L1c - 1 - k] : q[k];
+      if (!ga) { char *buf = fit(s.ga, L2c); gather_genome(p, blocks, p.offset2, L2c, five, buf); ga = buf; }
+      Out sL; sL.p = fit(s.sL, L1c + L2c + 2); sL.n = 0;
       replay(sL, ops, dr.nopsL, dr.bestrL, dr.bestcL, qa, ga, p.offset1, p.offset2, five, false, p.dynprogindex, nostar);
       if ((p.endalign == DPC_QUERYEND_GAP || p.endalign == DPC_BEST_LOCAL) && dr.nmatches + 1 < dr.nmismatches) break;   /* 5259 */
       int first = 0;                                                   /* 5265-5268 */
@@ -796,10 +811,10 @@ struct Batch {
          and the gap run that follows it, so the split can only fall before an aligned column. */
       const bool five = p.kind == DPC_END5_SPLICEJUNCTION;
       const int endc = p.length2R;
-      char *qa = fit(s.qa, h.L1), *ga = fit(s.ga, h.L2);
-      for (int k = 0; k < h.L1; k++) qa[k] = five ? q[h.L1 - 1 - k] : q[k];
-      for (int k = 0; k < h.L2; k++) ga[k] = (char)dpc_code_char(pool[h.q1 + (uint32_t)k]);
-      Out sL; sL.p = fit(s.sL, h.L1 + h.L2 + 4); sL.n = 0;
+      char *qa = fit(s.qa, L1c), *ga = fit(s.ga, L2c);
+      for (int k = 0; k < L1c; k++) qa[k] = five ? q[L1c - 1 - k] : q[k];
+      for (int k = 0; k < L2c; k++) ga[k] = (char)dpc_code_char(codes2[k]);
+      Out sL; sL.p = fit(s.sL, L1c + L2c + 4); sL.n = 0;
       std::vector<uint16_t> part;
       const int nops = dr.nopsL;
       int r = dr.bestrL, c = dr.bestcL, k = 0, used = 0;                /* used: columns of run k taken by the first call */
@@ -837,7 +852,7 @@ struct Batch {
       if (!(dr.status & DPC_ST_OK)) break;
       const int L1 = p.length1, L2L = p.length2, L2R = p.length2R, revoffset1 = p.offset1 + L1 - 1;
       char *qb = fit(s.qb, L1);
-      const char *ga = staged(h), *gb = ga ? ga + dpc_gout_span(L2L) : NULL;
+      const char *ga = staged_g, *gb = ga ? ga + dpc_gout_span(L2L) : NULL;
       for (int k = 0; k < L1; k++) qb[k] = q[L1 - 1 - k];
       if (!ga) {
         char *bufa = fit(s.ga, L2L), *bufb = fit(s.gb, L2R);

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -139,6 +140,7 @@ static std::mutex g_mu;
 static uint64_t g_version = 0;
 static int g_force_generic = 0;
 
+#define CK_VOID(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) fprintf(stderr, "libdynprog_cuda: %s failed: %s\n", #call, cudaGetErrorString(e_)); } while (0)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
   fprintf(stderr, "libdynprog_cuda: %s failed at %s:%d: %s\n", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
   return DPC_ERR_CUDA; } } while (0)
@@ -516,14 +518,20 @@ struct Workers {
   }
 };
 
+#include "dpc_pipeline.cuh"
+
 struct dpc_ctx {
   Engine main;                       /* ticket API, dpc_relaunch */
-  std::vector<Engine *> subs;        /* bulk API: one engine per chunk in flight */
+  std::vector<int> devices;          /* bulk API: the devices the chunks are dealt to (main.device first) */
+  std::vector<std::vector<Pipe *> > pipes;     /* bulk API: pipeline slots per device */
+  std::vector<std::vector<Engine *> > engines; /* bulk API: engines for chunks that need the host half, per device */
   Workers *workers;
   int nthreads;
-  std::atomic<int64_t> solve_h2d, solve_d2h, solve_launches, solve_problems;   /* totals of the last dpc_solve */
-  dpc_ctx() : workers(NULL), nthreads(1), solve_h2d(0), solve_d2h(0), solve_launches(0), solve_problems(0) {}
+  std::atomic<int64_t> solve_h2d, solve_d2h, solve_launches, solve_problems, solve_pipe_chunks, solve_host_chunks;   /* totals of the last dpc_solve */
+  dpc_ctx() : workers(NULL), nthreads(1), solve_h2d(0), solve_d2h(0), solve_launches(0), solve_problems(0), solve_pipe_chunks(0), solve_host_chunks(0) {}
 };
+static int g_path = 0;               /* dpc_set_path: 0 auto, 1 host half only, 2 device pipeline or fail, 3 / 4 = 2 with the
+                                        Pair records expanded on the device / by the host */
 
 /* ---- C ABI ---------------------------------------------------------------------------------- */
 extern "C" {
@@ -592,13 +600,44 @@ dpc_ctx_t *dpc_ctx_new(int device) {
   if (t < 1) t = 1;
   if (t > 64) t = 64;
   c->nthreads = t;
+  c->devices.push_back(device);
   return c;
+}
+
+dpc_ctx_t *dpc_ctx_new_multi(const int *devices, int ndevices) {
+  if (!devices || ndevices < 1 || ndevices > MAXDEV) return NULL;
+  for (int i = 0; i < ndevices; i++)
+    for (int k = 0; k < i; k++) if (devices[k] == devices[i]) return NULL;
+  dpc_ctx *c = dpc_ctx_new(devices[0]);
+  if (!c) return NULL;
+  for (int i = 1; i < ndevices; i++) {
+    if (devices[i] < 0 || devices[i] >= dpc_device_count() || ensure_device(devices[i]) != DPC_OK) { dpc_ctx_free(c); return NULL; }
+    c->devices.push_back(devices[i]);
+  }
+  return c;
+}
+
+int dpc_host_register(void *p, uint64_t bytes) {
+  if (!p || !bytes) return DPC_ERR_ARG;
+  if (cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return DPC_ERR_CUDA; }
+  return DPC_OK;
+}
+int dpc_host_unregister(void *p) {
+  if (!p) return DPC_ERR_ARG;
+  if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return DPC_ERR_CUDA; }
+  return DPC_OK;
+}
+int dpc_set_path(int path) {
+  if (path < 0 || path > 4) return DPC_ERR_ARG;
+  g_path = path;
+  return DPC_OK;
 }
 
 void dpc_ctx_free(dpc_ctx_t *c) {
   if (!c) return;
   delete c->workers;
-  for (size_t i = 0; i < c->subs.size(); i++) delete c->subs[i];
+  for (size_t d = 0; d < c->pipes.size(); d++) for (size_t i = 0; i < c->pipes[d].size(); i++) delete c->pipes[d][i];
+  for (size_t d = 0; d < c->engines.size(); d++) for (size_t i = 0; i < c->engines[d].size(); i++) delete c->engines[d][i];
   delete c;
 }
 
@@ -678,148 +717,353 @@ int dpc_pairs(dpc_ctx_t *c, int ticket, dpc_pair_t *out, int cap) {
   return k;
 }
 
-/* Bulk call: the problems are cut into chunks; host threads pack a chunk, queue its copies and kernels on
- * the chunk's own stream, and finalise it when it is back, so packing, PCIe traffic, kernels and Pair
- * rebuild of different chunks overlap.  Results and pairs come out in input order. */
+/* Bulk call.  The problems are cut into chunks; chunk j belongs to device j mod ndevices (dpc_ctx_new_multi).  Per
+ * device ONE driver thread walks its chunks through the device pipeline (dpc_pipeline.cuh) as a state machine over a
+ * handful of pipeline slots: it only queues copies and kernels and polls events, so a dozen chunks are in flight per
+ * device whatever the number of host cores.  The other host threads are workers: they scan chunks ahead of the
+ * driver (does a chunk need a host hook? where do its query bytes lie?), expand the Pair records of the chunks the
+ * driver routes to the host, apply the MaxEnt hook, and serve whole chunks that need the host half (known splice
+ * sites, probability mode, splice-junction solvers) with an Engine, like the ticket API.  Results and pairs come
+ * out in input order; the only ordered step is the running pair offset handed from chunk to chunk. */
 static double now_s() {
   struct timespec t;
   clock_gettime(CLOCK_MONOTONIC, &t);
   return t.tv_sec + 1e-9 * t.tv_nsec;
 }
 
+enum { JS_NEW = 0, JS_WAIT1, JS_WAIT2, JS_CHAIN, JS_WAIT3, JS_WORKER, JS_DONE };
+enum { WK_FINAL = 0, WK_REBUILD, WK_LEGACY_A, WK_LEGACY_B };
+struct SolveJob {
+  int lo, cnt;
+  std::atomic<int> scanned, mine_known, at_known, worker_done;
+  ChunkScan cs;
+  int state, route;
+  bool piped;
+  Pipe *pp;
+  Engine *eng;
+  int64_t mine, at, queued;
+  SolveJob() : lo(0), cnt(0), scanned(0), mine_known(0), at_known(0), worker_done(0), state(JS_NEW), route(0), piped(false),
+               pp(NULL), eng(NULL), mine(0), at(0), queued(0) {}
+};
+
 int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *results,
               dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off) {
   if (!c || n < 0 || (n > 0 && (!problems || !results))) return DPC_ERR_ARG;
-  int rc = ensure_device(c->main.device);
-  if (rc != DPC_OK) return rc;
-  const int device = c->main.device;
-  const int T = c->nthreads;
+  const int ndev = (int)c->devices.size();
+  for (int d = 0; d < ndev; d++) { int rc = ensure_device(c->devices[(size_t)d]); if (rc != DPC_OK) return rc; }
+  if (pair_off && n == 0) pair_off[0] = 0;
+  if (n == 0) return DPC_OK;
+  /* threads: drivers (two per device when the budget of dpc_set_threads allows: queueing a chunk's ~25 copies and
+     launches costs ~0.1 ms of a thread) + workers (at least one) */
+  static const int env_drivers = getenv("DPC_DRIVERS") ? std::max(1, atoi(getenv("DPC_DRIVERS"))) : 0;
+  const int dpd = env_drivers ? env_drivers : (c->nthreads >= 6 * ndev ? 2 : 1);       /* drivers per device */
+  const int ndrv = dpd * ndev;
+  const int nworkers = std::max(1, c->nthreads - ndrv);
+  const int T = ndrv + nworkers;
+  if (c->workers && (int)c->workers->th.size() != T) { delete c->workers; c->workers = NULL; }
   if (!c->workers) c->workers = new Workers(T);
-  int chunk = n / (4 * T) + 1;
+  static const int nslots = getenv("DPC_PIPE_SLOTS") ? std::max(2, atoi(getenv("DPC_PIPE_SLOTS"))) : 12;
+  c->pipes.resize((size_t)ndrv); c->engines.resize((size_t)ndrv);
+  /* chunk size: small enough that the workers' last rebuilds do not trail the GPU by much, large enough that a
+     driver's ~0.1 ms of queueing per chunk stays off the critical path */
+  int chunk = n / (3 * nslots * ndrv) + 1;
   if (chunk < 2048) chunk = 2048;
-  if (chunk > 16384) chunk = 16384;
+  if (chunk > (dpd >= 2 ? 8192 : 16384)) chunk = dpd >= 2 ? 8192 : 16384;
   { static const int forced = getenv("DPC_CHUNK") ? atoi(getenv("DPC_CHUNK")) : 0; if (forced >= 256) chunk = forced; }   /* tuning aid */
   const int nchunks = (n + chunk - 1) / chunk;
-  const int nengines = std::min(nchunks, 4 * T);              /* chunks in flight */
-  while ((int)c->subs.size() < nengines) {
-    Engine *e = new Engine();
-    if (e->open(device) != DPC_OK) { delete e; return DPC_ERR_CUDA; }
-    c->subs.push_back(e);
-  }
   static const bool timing = getenv("DPC_TIMING") != NULL;
-  static const bool stream_pairs = getenv("DPC_NO_STREAM") == NULL;     /* non-temporal stores for the pair records */
-  std::atomic<int> err(0);
-  std::atomic<int64_t> t_pack(0), t_flush(0), t_wait(0), t_fin(0), t_pairs(0), t_stall(0);
-  /* chunk j publishes the end offset of its pair block once every chunk before it has; a chunk's engine is
-   * free again when the chunk's pairs are out */
-  std::vector<std::atomic<int64_t>> chunk_end((size_t)nchunks);
-  std::vector<std::atomic<int>> chunk_done((size_t)nchunks);
-  for (int j = 0; j < nchunks; j++) { chunk_end[(size_t)j].store(-1); chunk_done[(size_t)j].store(0); }
+  static const bool stream_pairs = getenv("DPC_NO_STREAM") == NULL;     /* non-temporal stores for rebuilt pair records */
+  static const double link_depth = getenv("DPC_LINK_DEPTH") ? atof(getenv("DPC_LINK_DEPTH")) : 2.0;
+  static const int env_route = getenv("DPC_ROUTE") ? (!strcmp(getenv("DPC_ROUTE"), "host") ? 1 : !strcmp(getenv("DPC_ROUTE"), "device") ? 0 : -1) : -1;
+  const int forced_route = g_path == 3 ? 0 : g_path == 4 ? 1 : env_route;
+  const bool direct = pairs != NULL && host_pinned(pairs, (size_t)pair_cap * sizeof(dpc_pair_t));
+  const bool hp_pinned = host_pinned(problems, (size_t)n * sizeof(dpc_problem_t));
+  const bool res_pinned = host_pinned(results, (size_t)n * sizeof(dpc_result_t));
+  const int fill_gen = g_force_generic;
+  const int path = g_path;
+
+  std::vector<SolveJob> jobs((size_t)nchunks);
+  for (int j = 0; j < nchunks; j++) { jobs[(size_t)j].lo = j * chunk; jobs[(size_t)j].cnt = std::min(chunk, n - j * chunk); }
+  std::atomic<int> err(0), scan_next(0), drivers_left(ndrv), host_routed(0), rebuild_queued(0);
+  std::atomic<int64_t> t_scan(0), t_work(0), t_legacy(0), d2h_backlog(0);
+  std::mutex qmu, chain_mu;
+  std::deque<std::pair<int, int> > queue;          /* (work kind, chunk) */
+  int chain_next = 0; int64_t chain_total = 0;
+  std::vector<Scratch> scratch((size_t)T);
   const double t0 = now_s();
-  c->solve_h2d = 0; c->solve_d2h = 0; c->solve_launches = 0; c->solve_problems = n;
-  std::atomic<int> next_chunk(0);
-  /* first half of a chunk: pack and queue copies + kernels on the chunk's stream (returns at once) */
-  auto launch = [&](int j) {
-    Engine &e = *c->subs[(size_t)(j % nengines)];
-    const int lo = j * chunk, cnt = std::min(chunk, n - lo);
-    double a0 = timing ? now_s() : 0;
-    if (j >= nengines) while (!chunk_done[(size_t)(j - nengines)].load(std::memory_order_acquire)) std::this_thread::yield();
-    if (err.load()) return;
-    int r = 0;
-    try {
-      e.reset();
-      r = e.batch.add_ext(problems + lo, results + lo, cnt);
-      double a1 = timing ? now_s() : 0;
-      if (r >= 0) r = e.flush();
-      if (timing) { t_pack += (int64_t)((a1 - a0) * 1e9); t_flush += (int64_t)((now_s() - a1) * 1e9); }
-    } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
-    if (r < 0) { int z = 0; err.compare_exchange_strong(z, r); }
-  };
-  /* second half: wait for the device, finalise, take the pair offset from the previous chunk, rebuild the pairs */
-  auto finish = [&](int j) {
-    Engine &e = *c->subs[(size_t)(j % nengines)];
-    const int lo = j * chunk, cnt = std::min(chunk, n - lo);
-    int64_t mine = 0;
-    double a2 = timing ? now_s() : 0, a3 = 0, a4 = 0;
-    if (!err.load()) {
-      int r = 0;
-      try {
-        r = e.wait();
-        if (r >= 0) for (int i = 0; i < cnt; i++) mine += results[lo + i].npairs;
-      } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
-      if (r < 0) { int z = 0; err.compare_exchange_strong(z, r); }
-    }
-    if (timing) a3 = now_s();
-    int64_t at = 0;
-    if (j > 0) {
-      int64_t prev;
-      while ((prev = chunk_end[(size_t)(j - 1)].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
-      at = prev;
-    }
-    chunk_end[(size_t)j].store(at + mine, std::memory_order_release);
-    if (timing) a4 = now_s();
-    if (!err.load() && (pairs || pair_off)) {
-      if (pairs && at + mine > pair_cap) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_NOMEM); }
-      else {
-        try {
-          for (int i = 0; i < cnt; i++) {
-            const int np = results[lo + i].npairs;
-            if (pairs && i + 8 < cnt) e.batch.prefetch_genome(i + 8);
-            if (pair_off) pair_off[lo + i] = at;
-            if (!pairs || np == 0) { at += np; continue; }
-            int k = e.pairs_into(i, pairs + at, stream_pairs);
-            if (k != np) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_STATE); break; }
-            at += k;
-          }
-        } catch (const std::bad_alloc &) { int z = 0; err.compare_exchange_strong(z, DPC_ERR_NOMEM); }
-      }
-    }
-    c->solve_h2d += e.h2d_bytes; c->solve_d2h += e.d2h_bytes; c->solve_launches += e.nlaunch;
-    chunk_done[(size_t)j].store(1, std::memory_order_release);
-    if (timing) {
-      t_wait += (int64_t)((a3 - a2) * 1e9); t_fin += (int64_t)(e.t_finalize * 1e9);
-      t_stall += (int64_t)((a4 - a3) * 1e9); t_pairs += (int64_t)((now_s() - a4) * 1e9);
+  c->solve_h2d = 0; c->solve_d2h = 0; c->solve_launches = 0; c->solve_problems = n; c->solve_pipe_chunks = 0; c->solve_host_chunks = 0;
+  auto fail = [&](int code) { int z = 0; err.compare_exchange_strong(z, code); };
+  auto push = [&](int kind, int j) { std::lock_guard<std::mutex> l(qmu); queue.push_back(std::make_pair(kind, j)); };
+
+  /* hands out the running pair offset in chunk order; host-half chunks get their second half queued here */
+  auto advance_chain = [&]() {
+    std::lock_guard<std::mutex> l(chain_mu);
+    while (chain_next < nchunks && jobs[(size_t)chain_next].mine_known.load(std::memory_order_acquire)) {
+      SolveJob &jb = jobs[(size_t)chain_next];
+      jb.at = chain_total;
+      chain_total += jb.mine;
+      if (pairs && chain_total > pair_cap) fail(DPC_ERR_NOMEM);
+      jb.at_known.store(1, std::memory_order_release);
+      if (!jb.piped && !err.load()) push(WK_LEGACY_B, chain_next);
+      chain_next++;
     }
   };
-  /* Launch tickets and finish tickets are handed out separately, both in chunk order; a thread launches one chunk
-     (two before its first finish, so that every thread keeps two in flight) and then finishes the OLDEST chunk
-     nobody has taken yet -- not necessarily one it launched.  Finishing in order keeps the ordered hand-off of the
-     pair offsets short: chunk j-1 is always in somebody's hands before chunk j is.  (No deadlock: a launch only
-     waits for the engine of chunk l - nengines, whose finish ticket is taken by then because nengines = 4T and a
-     thread is never more than two launches ahead of its finishes.) */
-  std::vector<std::atomic<int>> launched((size_t)nchunks);
-  for (int j = 0; j < nchunks; j++) launched[(size_t)j].store(0);
-  std::atomic<int> next_finish(0);
-  c->workers->run(T, [&](int) {
-    cudaSetDevice(device);
-    auto try_launch = [&]() {
-      const int l = next_chunk.fetch_add(1);
-      if (l < nchunks) { launch(l); launched[(size_t)l].store(1, std::memory_order_release); }
-    };
-    try_launch();
+
+  auto fill_pair_off = [&](const SolveJob &jb, const long long *off) {
+    if (pair_off) for (int i = 0; i < jb.cnt; i++) pair_off[jb.lo + i] = jb.at + off[i];
+  };
+
+  /* ---- worker: queued work first, else scan ahead ---- */
+  auto worker = [&](int w) {
+    Scratch &sc = scratch[(size_t)w];
+    int idle = 0;
     for (;;) {
-      try_launch();
-      const int f = next_finish.fetch_add(1);
-      if (f >= nchunks) break;
-      while (!launched[(size_t)f].load(std::memory_order_acquire)) std::this_thread::yield();
-      finish(f);
+      std::pair<int, int> it(-1, -1);
+      { std::lock_guard<std::mutex> l(qmu); if (!queue.empty()) { it = queue.front(); queue.pop_front(); } }
+      if (it.first >= 0) {
+        idle = 0;
+        SolveJob &jb = jobs[(size_t)it.second];
+        const dpc_problem_t *P = problems + jb.lo;
+        dpc_result_t *R = results + jb.lo;
+        const double a0 = timing ? now_s() : 0;
+        int r = DPC_OK;
+        try {
+          switch (it.first) {
+          case WK_FINAL:
+            pipe_device_route_final(*jb.pp, P, jb.cnt, R, pairs ? pairs + jb.at : NULL, direct, jb.mine);
+            fill_pair_off(jb, jb.pp->h_off.data());
+            jb.worker_done.store(1, std::memory_order_release);
+            break;
+          case WK_REBUILD:
+            if (!err.load()) r = pipe_host_route_final(*jb.pp, P, jb.cnt, R, pairs + jb.at, jb.mine, stream_pairs, sc);
+            fill_pair_off(jb, jb.pp->h_off.data());
+            rebuild_queued -= 1;
+            jb.worker_done.store(1, std::memory_order_release);
+            break;
+          case WK_LEGACY_A: {
+            Engine &e = *jb.eng;
+            if (!err.load()) {
+              e.reset();
+              r = e.batch.add_ext(P, R, jb.cnt);
+              if (r >= 0) r = e.flush();
+              if (r >= 0) r = e.wait();
+              if (r >= 0) for (int i = 0; i < jb.cnt; i++) jb.mine += R[i].npairs;
+              else jb.mine = 0;
+            }
+            jb.mine_known.store(1, std::memory_order_release);
+            if (timing) t_legacy += (int64_t)((now_s() - a0) * 1e9);
+            break;
+          }
+          case WK_LEGACY_B: {
+            Engine &e = *jb.eng;
+            int64_t at = jb.at;
+            for (int i = 0; i < jb.cnt && (pairs || pair_off) && !err.load(); i++) {
+              const int np = R[i].npairs;
+              if (pairs && i + 8 < jb.cnt) e.batch.prefetch_genome(i + 8);
+              if (pair_off) pair_off[jb.lo + i] = at;
+              if (!pairs || np == 0) { at += np; continue; }
+              const int k = e.pairs_into(i, pairs + at, stream_pairs);
+              if (k != np) { r = DPC_ERR_STATE; break; }
+              at += k;
+            }
+            c->solve_h2d += e.h2d_bytes; c->solve_d2h += e.d2h_bytes; c->solve_launches += e.nlaunch; c->solve_host_chunks += 1;
+            jb.worker_done.store(1, std::memory_order_release);
+            break;
+          }
+          }
+        } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
+        if (r < 0) {
+          fail(r);
+          if (it.first == WK_LEGACY_A) { jb.mine = 0; jb.mine_known.store(1, std::memory_order_release); }
+          else jb.worker_done.store(1, std::memory_order_release);
+        }
+        if (timing && it.first != WK_LEGACY_A) t_work += (int64_t)((now_s() - a0) * 1e9);
+        continue;
+      }
+      int sidx = scan_next.load();
+      if (sidx < nchunks) {
+        if (scan_next.compare_exchange_strong(sidx, sidx + 1)) {
+          const double a0 = timing ? now_s() : 0;
+          SolveJob &jb = jobs[(size_t)sidx];
+          jb.cs.eligible = false;
+          if (path != 1) jb.cs = scan_chunk(problems + jb.lo, jb.cnt);
+          jb.scanned.store(1, std::memory_order_release);
+          if (timing) t_scan += (int64_t)((now_s() - a0) * 1e9);
+        }
+        idle = 0;
+        continue;
+      }
+      if (drivers_left.load() == 0) { std::lock_guard<std::mutex> l(qmu); if (queue.empty()) break; else continue; }
+      if (++idle < 64) std::this_thread::yield(); else { struct timespec ts = { 0, 20000 }; nanosleep(&ts, NULL); }
     }
-  });
+  };
+
+  /* ---- driver number dslot: chunks dslot, dslot + ndrv, ... on device dslot mod ndev ---- */
+  auto driver = [&](int dslot) {
+    const int device = c->devices[(size_t)(dslot % ndev)];
+    cudaSetDevice(device);
+    std::vector<Pipe *> &pool = c->pipes[(size_t)dslot];
+    std::vector<Engine *> &engs = c->engines[(size_t)dslot];
+    std::vector<Pipe *> free_pipes;
+    std::vector<Engine *> free_engs;
+    std::vector<int> active, legacy_active;
+    for (size_t i = 0; i < pool.size(); i++) free_pipes.push_back(pool[i]);
+    for (size_t i = 0; i < engs.size(); i++) free_engs.push_back(engs[i]);
+    int next_start = dslot, left = 0;
+    for (int j = dslot; j < nchunks; j += ndrv) left++;
+    int idle = 0;
+    auto job_fail = [&](SolveJob &jb, int code) {
+      fail(code);
+      if (!jb.mine_known.load()) { jb.mine = 0; jb.mine_known.store(1, std::memory_order_release); }
+      jb.state = JS_DONE;
+    };
+    while (left > 0) {
+      bool progressed = false;
+      const bool failing = err.load() != 0;
+      /* 1. start chunks, in order */
+      while (next_start < nchunks && jobs[(size_t)next_start].scanned.load(std::memory_order_acquire)) {
+        SolveJob &jb = jobs[(size_t)next_start];
+        if (failing) {                  /* after an error nothing new is queued; the chain still has to move */
+          jb.mine = 0; jb.piped = true; jb.mine_known.store(1, std::memory_order_release);
+          left--; next_start += ndrv; progressed = true;
+          continue;
+        }
+        if (path >= 2 && !jb.cs.eligible) { jb.piped = true; job_fail(jb, DPC_ERR_STATE); left--; next_start += ndrv; progressed = true; continue; }
+        if (!jb.cs.eligible) {
+          if ((int)legacy_active.size() >= nworkers + 1) break;
+          Engine *e = NULL;
+          if (!free_engs.empty()) { e = free_engs.back(); free_engs.pop_back(); }
+          else {
+            e = new Engine();
+            if (e->open(device) != DPC_OK) { delete e; jb.piped = true; job_fail(jb, DPC_ERR_CUDA); left--; next_start += ndrv; continue; }
+            engs.push_back(e);
+          }
+          jb.eng = e; jb.piped = false;
+          legacy_active.push_back(next_start);
+          push(WK_LEGACY_A, next_start);
+        } else {
+          Pipe *pp = NULL;
+          if (!free_pipes.empty()) { pp = free_pipes.back(); free_pipes.pop_back(); }
+          else if ((int)pool.size() < nslots) {
+            pp = new Pipe();
+            if (pp->open(device) != DPC_OK) { delete pp; jb.piped = true; job_fail(jb, DPC_ERR_CUDA); left--; next_start += ndrv; continue; }
+            pool.push_back(pp);
+          } else break;
+          jb.pp = pp; jb.piped = true;
+          int r = DPC_OK;
+          try { r = pipe_stage1(*pp, problems + jb.lo, jb.cnt, jb.cs, fill_gen, hp_pinned); } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
+          if (r < 0) { free_pipes.push_back(pp); job_fail(jb, r); left--; next_start += ndrv; continue; }
+          jb.state = JS_WAIT1;
+          active.push_back(next_start);
+        }
+        next_start += ndrv;
+        progressed = true;
+      }
+      /* 2. advance the chunks in flight */
+      for (size_t a = 0; a < active.size();) {
+        SolveJob &jb = jobs[(size_t)active[a]];
+        Pipe &pp = *jb.pp;
+        int r = DPC_OK;
+        bool moved = false;
+        try {
+          if (jb.state == JS_WAIT1 || jb.state == JS_WAIT2 || jb.state == JS_WAIT3) {
+            const cudaError_t q = cudaEventQuery(pp.ev);
+            if (q == cudaSuccess) {
+              moved = true;
+              if (jb.state == JS_WAIT1) {
+                r = pipe_stage2(pp, jb.cnt, fill_gen);
+                jb.state = JS_WAIT2;
+              } else if (jb.state == JS_WAIT2) {
+                const PipeCounters &pc = pp.h_pc[0];
+                if (pc.err < 0) r = pc.err;
+                else {
+                  jb.mine = pc.pair_total;
+                  /* Who expands this chunk's traceback ops into Pair records?  The device (16 bytes per record over
+                     PCIe) or a worker (the compact device records over PCIe, then the host half's rebuild).  The link
+                     is the scarce resource: once a few pair blocks are queued on it -- enough to keep it busy until
+                     the next chunk is ready -- the next chunk goes to the workers, unless they are behind too. */
+                  jb.route = 0;
+                  if (pairs && jb.mine > 0) {
+                    const bool link_busy = (double)d2h_backlog.load() >= link_depth * (double)jb.mine * sizeof(dpc_pair_t);
+                    const bool workers_free = rebuild_queued.load() < 2 * nworkers;
+                    jb.route = forced_route >= 0 ? forced_route : (link_busy && workers_free ? 1 : 0);
+                  }
+                  if (jb.route == 0) {
+                    jb.queued = pairs ? jb.mine * (int64_t)sizeof(dpc_pair_t) : 0;
+                    d2h_backlog += jb.queued;
+                    r = pipe_device_route_start(pp, jb.cnt, results + jb.lo, res_pinned, pairs != NULL, jb.mine);
+                  } else {
+                    rebuild_queued += 1;
+                    host_routed += 1;
+                    r = pipe_host_route_start(pp, jb.cnt, results + jb.lo, res_pinned);
+                  }
+                  jb.mine_known.store(1, std::memory_order_release);
+                  jb.state = JS_CHAIN;
+                }
+              } else {
+                d2h_backlog -= jb.queued; jb.queued = 0;
+                push(jb.route == 0 ? WK_FINAL : WK_REBUILD, active[a]);
+                jb.state = JS_WORKER;
+              }
+            } else if (q != cudaErrorNotReady) {
+              fprintf(stderr, "libdynprog_cuda: device pipeline failed: %s\n", cudaGetErrorString(q));
+              r = DPC_ERR_CUDA;
+            }
+          }
+          if (r >= 0 && jb.state == JS_CHAIN && jb.at_known.load(std::memory_order_acquire)) {
+            moved = true;
+            if (err.load()) { jb.state = JS_WAIT3; CK_VOID(cudaEventRecord(pp.ev, pp.stream)); }
+            else if (jb.route == 0) { r = pipe_device_route_copy(pp, pairs ? pairs + jb.at : NULL, direct, jb.mine); jb.state = JS_WAIT3; }
+            else jb.state = JS_WAIT3;          /* the event of the host route was recorded with its copies */
+          }
+          if (jb.state == JS_WORKER && jb.worker_done.load(std::memory_order_acquire)) {
+            moved = true;
+            c->solve_h2d += pp.h2d_bytes; c->solve_d2h += pp.d2h_bytes; c->solve_launches += pp.nlaunch; c->solve_pipe_chunks += 1;
+            jb.state = JS_DONE;
+          }
+        } catch (const std::bad_alloc &) { r = DPC_ERR_NOMEM; }
+        if (r < 0) {
+          d2h_backlog -= jb.queued; jb.queued = 0;
+          cudaStreamSynchronize(pp.stream);
+          job_fail(jb, r);
+        }
+        if (moved) progressed = true;
+        if (jb.state == JS_DONE) {
+          free_pipes.push_back(jb.pp);
+          active[a] = active.back(); active.pop_back();
+          left--;
+        } else a++;
+      }
+      for (size_t a = 0; a < legacy_active.size();) {
+        SolveJob &jb = jobs[(size_t)legacy_active[a]];
+        bool finished = jb.worker_done.load(std::memory_order_acquire) != 0;
+        if (!finished && err.load() && jb.mine_known.load() && jb.at_known.load()) finished = true;    /* second half never queued */
+        if (finished) {
+          free_engs.push_back(jb.eng);
+          legacy_active[a] = legacy_active.back(); legacy_active.pop_back();
+          left--; progressed = true;
+        } else a++;
+      }
+      /* 3. the running pair offset */
+      advance_chain();
+      if (progressed) idle = 0;
+      else if (++idle < 200) { /* spin: events complete within microseconds */ }
+      else std::this_thread::yield();
+    }
+    drivers_left -= 1;
+  };
+
+  c->workers->run(T, [&](int w) { if (w < ndrv) driver(w); else worker(w); });
+  advance_chain();
 #if defined(__SSE2__) && defined(__x86_64__)
   _mm_sfence();
 #endif
   if (err.load()) return err.load();
-  if (pair_off) pair_off[n] = nchunks ? chunk_end[(size_t)nchunks - 1].load() : 0;
-#ifdef DPC_PROFILE_REBUILD
-  {
-    unsigned long long cg = 0, cr = 0;
-    for (size_t i = 0; i < c->subs.size(); i++) { cg += c->subs[i]->scratch.cyc_gather; cr += c->subs[i]->scratch.cyc_replay; c->subs[i]->scratch.cyc_gather = c->subs[i]->scratch.cyc_replay = 0; }
-    fprintf(stderr, "rebuild cycles (thread-sum, tsc): gather %.1f M, replay %.1f M\n", cg / 1e6, cr / 1e6);
-  }
-#endif
+  if (pair_off) pair_off[n] = chain_total;
   if (timing)
-    fprintf(stderr, "dpc_solve n=%d chunks=%d x %d threads=%d engines=%d: %.1f ms | thread-sum pack %.1f flush %.1f wait %.1f (finalize %.1f) stall %.1f pairs %.1f ms\n",
-            n, nchunks, chunk, T, nengines, (now_s() - t0) * 1e3, t_pack / 1e6, t_flush / 1e6, t_wait / 1e6, t_fin / 1e6, t_stall / 1e6, t_pairs / 1e6);
+    fprintf(stderr, "dpc_solve n=%d chunks=%d x %d devices=%d drivers=%d workers=%d slots=%d pinned(in %d res %d pairs %d): %.1f ms | %lld pipeline (%d expanded by the host) + %lld host-half chunks | worker thread-sum scan %.1f expand/hooks %.1f host-half %.1f ms\n",
+            n, nchunks, chunk, ndev, ndrv, nworkers, nslots, (int)hp_pinned, (int)res_pinned, (int)direct, (now_s() - t0) * 1e3,
+            (long long)c->solve_pipe_chunks.load(), host_routed.load(), (long long)c->solve_host_chunks.load(), t_scan / 1e6, t_work / 1e6, t_legacy / 1e6);
   return DPC_OK;
 }
 
@@ -845,10 +1089,10 @@ int dpc_sync(dpc_ctx_t *c) {
   return DPC_OK;
 }
 
-int dpc_last_kernel_ms(dpc_ctx_t *c, float ms[3]) {
+int dpc_last_kernel_ms(dpc_ctx_t *c, float *ms) {
   if (!c || !ms) return DPC_ERR_ARG;
   if (!c->main.flushed) return DPC_ERR_STATE;
-  ms[0] = c->main.ms_total; ms[1] = 0.0f; ms[2] = c->main.ms_total;   /* fill, bridge and traceback are one fused kernel */
+  *ms = c->main.ms_total;
   return DPC_OK;
 }
 
@@ -888,9 +1132,10 @@ int dpc_get_stats(dpc_ctx_t *c, dpc_stats_t *out) {
   if (!c->main.batch.probs.empty()) add_stats(c->main, out);
   else {
     /* after dpc_solve: cells / bytes of the chunks still held by the engines, transfer totals of the whole call */
-    for (size_t i = 0; i < c->subs.size(); i++) add_stats(*c->subs[i], out);
+    for (size_t d = 0; d < c->engines.size(); d++) for (size_t i = 0; i < c->engines[d].size(); i++) add_stats(*c->engines[d][i], out);
     out->nproblems = c->solve_problems;
     out->h2d_bytes = c->solve_h2d; out->d2h_bytes = c->solve_d2h; out->launches = (int32_t)c->solve_launches;
+    out->pipeline_chunks = c->solve_pipe_chunks; out->host_chunks = (int32_t)c->solve_host_chunks;
   }
   return DPC_OK;
 }

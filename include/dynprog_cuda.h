@@ -211,6 +211,10 @@ int dpc_warmup(int device);
 
 /* ---- per-thread batch context (one Dynprog_T triple + stream) ---------- */
 dpc_ctx_t *dpc_ctx_new(int device);
+/* A context whose bulk call (dpc_solve) deals its chunks to several devices of this box -- "shard by read across
+ * the GPUs, gather on the host": chunk j of the problem array runs on devices[j mod ndevices], results and pairs
+ * come back in input order.  The ticket API of such a context runs on devices[0].  NULL when a device is unusable. */
+dpc_ctx_t *dpc_ctx_new_multi(const int *devices, int ndevices);
 void dpc_ctx_free(dpc_ctx_t *ctx);
 
 /* Enqueue.  Sequences are copied at enqueue time.  Returns the ticket (>= 0,
@@ -236,10 +240,20 @@ int dpc_set_threads(dpc_ctx_t *ctx, int nthreads);
 /* Whole batch in one call: add_bulk + flush + wait + results (+ pairs when
  * pairs != NULL; pair_off[i] = index of problem i's first record, pair_off has
  * n+1 entries).  Returns 0 or a negative code; DPC_ERR_NOMEM if pair_cap is too small. */
-/* The batch is cut into chunks that host threads pack, solve on their own streams and finalise
- * concurrently; outputs are in input order.  The problems' sequences must stay valid during the call. */
+/* The batch is cut into chunks that run concurrently on their own streams; outputs are in input order.  The
+ * problems' sequences must stay valid during the call.  A chunk takes the DEVICE PIPELINE -- the problem records
+ * and the query bytes they point to are copied as they are, checks / packing / result finalisation / Pair-record
+ * expansion are kernels, and results and pairs are copied straight into the caller's arrays -- unless it needs a
+ * host hook per problem (known splice sites, use_probabilities_p) or a splice-junction solver; such chunks are
+ * packed, finalised and rebuilt by the host threads.  Fastest when the queries of a chunk lie close together in one
+ * buffer (one copy instead of a gather) and `pairs` is page-locked (dpc_host_register: the copy engine then writes
+ * the records in place; otherwise they pass through a page-locked bounce buffer and a memcpy). */
 int dpc_solve(dpc_ctx_t *ctx, const dpc_problem_t *problems, int n,
               dpc_result_t *results, dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off);
+
+/* Page-locks / releases a caller-owned array (cudaHostRegister) so that dpc_solve can copy into it directly. */
+int dpc_host_register(void *p, uint64_t bytes);
+int dpc_host_unregister(void *p);
 
 /* ---- measurement hooks (bench.py) -------------------------------------- */
 /* After dpc_flush+dpc_wait the batch stays resident in HBM; dpc_relaunch runs
@@ -254,20 +268,24 @@ int dpc_sync(dpc_ctx_t *ctx);
  * (the routine used for bands of 64+ diagonals) instead of the register/shuffle fill.
  * Both are device code; the environment variable DPC_FORCE_GENERIC_FILL=1 does the same. */
 int dpc_set_fill(int force_generic);
-/* Average device time in ms of the last dpc_flush/dpc_relaunch per kernel
- * stage (CUDA events recorded on the context's stream):
- * 0 fill(+bridge), 1 traceback, 2 total.  Returns DPC_OK or an error. */
-int dpc_last_kernel_ms(dpc_ctx_t *ctx, float ms[3]);
-/* Work counters of the current batch: in-band DP cells (SURVEY.md 8d
- * definition), matrices filled, algorithmic HBM bytes of the fill kernel,
- * bytes copied H2D / D2H by the last flush. */
+/* Test hook: which half serves dpc_solve -- 0 per chunk as described above, 1 host half for every chunk, 2 device
+ * pipeline or DPC_ERR_STATE; 3 and 4 are 2 with the Pair records of every chunk expanded by the device / by the host
+ * threads (by default a pipeline chunk takes the host route when the PCIe backlog would outlast the rebuild).
+ * All of them return identical outputs. */
+int dpc_set_path(int path);
+/* Device time in ms of the last dpc_flush / dpc_relaunch (CUDA events recorded on the context's stream around the
+ * kernels; fill, bridge and traceback are one fused kernel per launch class). */
+int dpc_last_kernel_ms(dpc_ctx_t *ctx, float *ms);
+/* Work counters of the current batch (after dpc_solve: of the whole call): in-band DP cells (SURVEY.md 8d
+ * definition), matrices filled, algorithmic HBM bytes of the solve kernels (descriptors, sequences, 2-bit genome in;
+ * result records and staged genome characters out), bytes copied H2D / D2H. */
 typedef struct dpc_stats {
   int64_t nproblems, nmatrices, cells;
-  int64_t fill_bytes;           /* direction words written + inputs read by the fill kernel */
-  int64_t traceback_bytes;      /* direction words read + ops written by the traceback kernel */
+  int64_t fill_bytes;
+  int64_t pipeline_chunks;      /* dpc_solve: chunks that took the device pipeline ... */
   int64_t h2d_bytes, d2h_bytes;
-  int32_t launches;             /* kernel launches of the last flush/relaunch */
-  int32_t reserved;
+  int32_t launches;             /* kernel launches of the last flush / relaunch / solve */
+  int32_t host_chunks;          /* ... and chunks served by the host half */
 } dpc_stats_t;
 int dpc_get_stats(dpc_ctx_t *ctx, dpc_stats_t *out);
 

@@ -29,6 +29,7 @@ def _ensure_built():
 _ensure_built()
 
 from gmap_gsnap_b200 import api  # noqa: E402
+from oracle import checkers  # noqa: E402
 
 
 def has_ref():
@@ -44,22 +45,35 @@ def workload():
 def ref(workload):
     if not has_ref():
         pytest.skip("oracle/_ref/libdynprog_ref.so not built (needs /root/reference)")
-    r = api.RefOracle()
+    r = checkers.RefOracle()
     r.init()
     r.setup(workload.make_setup(splice_prob=r.splice_prob))
     return r
+
+
+_hook_owner = []
 
 
 def splice_prob_hook(workload):
     """MaxEnt probabilities for the hook: the compiled reference when present (its Maxent_hr needs the genome
     blocks registered first), else a deterministic stand-in."""
     if has_ref():
-        r = api.RefOracle()
+        r = checkers.RefOracle()
         r.init()
         r.setup(workload.make_setup())
         workload._keep.append(r)
+        _hook_owner.append(r)
         return r.splice_prob
     return api.PROB_FN(lambda which, pos, chroffset, user: ((pos * 2654435761 + which * 97) % 1000003) / 1000003.0)
+
+
+@pytest.fixture(autouse=True)
+def _reclaim_hook_library():
+    """The MaxEnt hook handed to the other libraries is a raw function of the compiled-reference library, whose genome
+    registration is process-wide: a test that registered another genome there must not leak into the next test."""
+    if _hook_owner:
+        _hook_owner[-1]._claim()
+    yield
 
 
 @pytest.fixture(scope="session")
@@ -69,7 +83,7 @@ def prob_hook(workload):
 
 @pytest.fixture(scope="session")
 def port(workload, prob_hook):
-    o = api.PortOracle()
+    o = checkers.PortOracle()
     o.init()
     o.setup(workload.make_setup(splice_prob=prob_hook))
     return o
@@ -77,7 +91,7 @@ def port(workload, prob_hook):
 
 @pytest.fixture(scope="session")
 def emul(workload, prob_hook):
-    e = api.EmulLib()
+    e = checkers.EmulLib()
     e.init()
     e.setup(workload.make_setup(splice_prob=prob_hook))
     return e

@@ -5,10 +5,12 @@
  * CPU test-suite can check index arithmetic, tie-breaks and boundary rules against the oracle on
  * a machine without a GPU.  libdynprog_cuda never links or loads this file; it has no CPU path.
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <vector>
 #include "../../gmap-gsnap_b200/csrc/dpc_host.h"
 #include "../../gmap-gsnap_b200/csrc/dpc_rows.h"
+#include "../../gmap-gsnap_b200/csrc/dpc_pipe.h"
 
 extern "C" int emul_init(int maxlookback, int extraquerygap, int maxpeelback, int end, int paired, int mode) {
   return dpc::host_init(maxlookback, extraquerygap, maxpeelback, end, paired, mode);
@@ -25,8 +27,88 @@ static int g_no_gout = 0;
 extern "C" int emul_set_fill(int force_generic) { g_force_generic = force_generic & 1; g_no_gout = (force_generic >> 1) & 1; return 0; }
 extern "C" int emul_pairdistance(int type, int c1, int c2) { return dpc::G().P[type & 3][c1 & 127][c2 & 127]; }
 
+static int g_pipe = 0;
+extern "C" int emul_set_path(int pipe) { g_pipe = pipe; return 0; }
+
+/* The DEVICE PIPELINE of dpc_solve (dpc_pipe.h: prepare / finish / expand per problem) run on the CPU: queries
+ * gathered into one pool, descriptors from dpc_prepare_one, results from dpc_finish_one, pairs from dpc_expand_one
+ * with 1 lane (even problems) or 32 round-robin "lanes" (odd problems: every lane's share, one after the other). */
+static int emul_solve_pipe(const dpc_problem_t *problems, int n, dpc_result_t *results,
+                           dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off) {
+  const dpc::Globals &g = dpc::G();
+  static const uint32_t class_bytes[6] = { 6 << 10, 13 << 10, 6 << 10, 13 << 10, 13 << 10, 0 };
+  std::vector<uint8_t> pool;
+  std::vector<dpc_problem_t> hp(problems, problems + n);
+  for (int i = 0; i < n; i++) {          /* gather (the library copies a contiguous range instead when it can) */
+    dpc_problem_t &q = hp[i];
+    const int len = q.kind == DPC_CDNA_GAP ? q.offset1R - q.offset1 + 1 : q.length1;
+    if (len <= 0 || !q.seq1) continue;
+    const char *first = q.seq1 - (q.kind == DPC_END5_GAP ? len - 1 : 0);
+    const size_t at = pool.size();
+    pool.insert(pool.end(), (const uint8_t *)first, (const uint8_t *)first + len);
+    const int64_t delta = (int64_t)at - (int64_t)(uintptr_t)first;
+    q.seq1 = (const char *)(uintptr_t)((uint64_t)(uintptr_t)q.seq1 + (uint64_t)delta);
+    if (q.seq1R) q.seq1R = (const char *)(uintptr_t)((uint64_t)(uintptr_t)q.seq1R + (uint64_t)delta);
+  }
+  pool.resize(pool.size() + 64);
+  PrepEnv env;
+  env.maxlength1 = g.maxlength1; env.maxlength2 = g.maxlength2; env.genome_nbases = g.genome_nbases;
+  env.novelsplicingp = g.setup.novelsplicingp; env.fillmode = g_force_generic ? 1 : 2;
+  for (int k = 0; k < 6; k++) env.class_bytes[k] = class_bytes[k];
+  env.qbase = 0; env.qbytes = pool.size();
+  std::vector<uint16_t> ovfbuf(1 << 22);
+  unsigned int used = 0;
+  OvfArena ovf; ovf.ops = ovfbuf.data(); ovf.used = &used; ovf.cap = (unsigned int)ovfbuf.size();
+  Lanes one; one.lane = 0; one.n = 1;
+  GenericFill gfill; RowFill rfill;
+  std::vector<uint8_t> arena, gout;
+  int64_t out = 0;
+  std::vector<dpc_pair_t> st;
+  for (int i = 0; i < n; i++) {
+    DevProb d; PrepOut o; DevRes dr;
+    if (g.setup.splice_known || problems[i].use_probabilities_p || problems[i].kind > DPC_END3_GAP) return DPC_ERR_STATE;
+    const int rc = dpc_prepare_one(hp[i], env, pool.data(), d, results[i], o);
+    if (rc < 0) { if (getenv("EMUL_DEBUG")) fprintf(stderr, "emul pipe: problem %d kind %d rc %d seq1 %p len %d qbytes %llu\n", i, problems[i].kind, rc, (void *)hp[i].seq1, problems[i].length1, (unsigned long long)env.qbytes); return rc; }
+    if (pair_off) pair_off[i] = out;
+    if (rc == DPC_PREP_HOST) continue;
+    gout.assign((size_t)o.gout + 64, 0xEE);
+    if (o.gout) d.gout = 8;
+    ArenaLayout a;
+    dpc_layout(d, a, env.fillmode);
+    arena.assign(a.total + 64, 0xAB);
+    memset(&dr, 0, sizeof dr);
+    uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
+    if (g_force_generic) dpc_solve_problem<GenericFill, -1, -1>(d, pool.data(), g.setup.genome_blocks, &g.tables, base, a.total, base, &dr, ovf, gout.data(), gfill, one);
+    else dpc_solve_problem<RowFill, -1, -1>(d, pool.data(), g.setup.genome_blocks, &g.tables, base, a.total, base, &dr, ovf, gout.data(), rfill, one);
+    if (dr.status & DPC_ST_OVF_LOST) return DPC_ERR_NOMEM;
+    const uint16_t *ops = (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? ovfbuf.data() + dr.ovf : dr.ops;
+    const uint8_t *staged = (i & 2) ? gout.data() : NULL;       /* also exercise the decode-again path */
+    if (!staged) d.gout = DPC_NO_GOUT;
+    const int np = dpc_expand_one(problems[i], d, dr, ops, pool.data(), staged, g.setup.genome_blocks, &g.tables, NULL, one);
+    if (dpc_finish_one(problems[i], dr, np, results[i])) {
+      const int cL = (int)results[i].left_prob, cR = (int)results[i].right_prob;
+      results[i].left_prob = dpc::Batch::site_prob(problems[i], true, cL, false);
+      results[i].right_prob = dpc::Batch::site_prob(problems[i], false, cR, false);
+    }
+    if (pairs && np) {
+      if (out + np > pair_cap) return DPC_ERR_NOMEM;
+      st.assign((size_t)np + 2, dpc_pair_t());
+      memset(st.data(), 0x5A, st.size() * sizeof(dpc_pair_t));
+      if (i & 1) {
+        for (int l = 0; l < 32; l++) { Lanes ln; ln.lane = l; ln.n = 32; if (dpc_expand_one(problems[i], d, dr, ops, pool.data(), staged, g.setup.genome_blocks, &g.tables, st.data(), ln) != np) return -101; }
+      } else if (dpc_expand_one(problems[i], d, dr, ops, pool.data(), staged, g.setup.genome_blocks, &g.tables, st.data(), one) != np) return -101;
+      if ((unsigned char)st[(size_t)np].comp != 0x5A) return -102;          /* wrote past its block */
+      memcpy(pairs + out, st.data(), (size_t)np * sizeof(dpc_pair_t));
+    }
+    out += np;
+  }
+  if (pair_off) pair_off[n] = out;
+  return 0;
+}
+
 extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *results,
                           dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off) {
+  if (g_pipe) return emul_solve_pipe(problems, n, results, pairs, pair_cap, pair_off);
   dpc::Batch b;
   for (int i = 0; i < n; i++) {
     int t = b.add(problems[i]);

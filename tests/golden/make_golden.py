@@ -14,6 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from gmap_gsnap_b200 import api  # noqa: E402
+from oracle import checkers
 
 
 def edge_cases(w):
@@ -57,7 +58,7 @@ def edge_cases(w):
 
 def main():
     w = api.Workload(300_000, seed=20121, n_frac=0.001, nchr=3)
-    ref = api.RefOracle()
+    ref = checkers.RefOracle()
     ref.init()
     ref.setup(w.make_setup(splice_prob=ref.splice_prob))
     calls = {}
@@ -68,7 +69,7 @@ def main():
         return v
 
     hook = api.PROB_FN(rec)
-    port = api.PortOracle()
+    port = checkers.PortOracle()
     port.init()
     port.setup(w.make_setup(splice_prob=hook))
 
@@ -82,7 +83,7 @@ def main():
     sets["edge"] = edge_cases(w)
     out = {"blocks": w.blocks, "nbases": np.int64(w.nbases)}
     for name, probs in sets.items():
-        probs = api.arm_probability_mode(probs, ref)
+        probs = checkers.arm_probability_mode(probs, ref)
         res, pairs, off = ref.solve(probs)
         bad = api.compare(res, pairs, off, *port.solve(probs))   # also records the hook calls
         assert not bad, (name, bad)

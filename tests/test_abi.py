@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from gmap_gsnap_b200 import api
+from oracle import checkers
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -72,7 +73,7 @@ def test_argument_errors_mirror_the_reference_aborts():
     """The reference abort()s on non-positive matrix sizes (dynprog.c:495-498) and on an unknown Endalign_T
     (5215); the host side of the library (shared with tests/emul) returns an error code instead of solving."""
     w = api.Workload(200_000, seed=9)
-    em = api.EmulLib()
+    em = checkers.EmulLib()
     em.init()
     em.setup(w.make_setup())
 

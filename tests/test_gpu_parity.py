@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from gmap_gsnap_b200 import api
+from oracle import checkers
 from util import GOLDEN_SETS, SPLICING_IIT_MODES, Golden, long_nogaps_ends, mixed_problems, splicing_iit_hooks
 
 pytestmark = pytest.mark.gpu
@@ -17,6 +18,17 @@ RTOL = 1e-6
 @pytest.fixture(scope="module")
 def golden():
     return Golden()
+
+
+@pytest.fixture(scope="module", autouse=True, params=[0, 1], ids=["auto_path", "host_half"])
+def solve_path(request):
+    """dpc_solve serves a chunk with its device pipeline (kernels for packing / finalisation / Pair expansion) or
+    with the host half (hooks, splice-junction solvers).  Every test of this module runs once with the library's own
+    choice per chunk and once with the host half forced; both must match the oracle."""
+    lib = api.CudaLib()
+    lib.lib.dpc_set_path(request.param)
+    yield request.param
+    lib.lib.dpc_set_path(0)
 
 
 @pytest.fixture(scope="module", params=[0, 1], ids=["register_fill", "memory_fill"])
@@ -44,12 +56,12 @@ def test_golden_vectors(golden, name):
 
 
 def test_mixed_batch_matches_oracle(workload, port, cuda, fill_mode):
-    probs = api.arm_probability_mode(mixed_problems(workload, 4000, 101, long_frac=0.03, long_hi=611), port)
+    probs = checkers.arm_probability_mode(mixed_problems(workload, 4000, 101, long_frac=0.03, long_hi=611), port)
     assert not api.compare(*port.solve(probs), *cuda.solve(probs), rtol=RTOL)
 
 
 def test_matches_compiled_reference(workload, ref, cuda):
-    probs = api.arm_probability_mode(mixed_problems(workload, 3000, 202), ref)
+    probs = checkers.arm_probability_mode(mixed_problems(workload, 3000, 202), ref)
     assert not api.compare(*ref.solve(probs), *cuda.solve(probs), rtol=RTOL)
 
 
@@ -68,7 +80,7 @@ def test_end_gaps_all_endalign(workload, port, cuda, fill_mode):
 
 def test_genome_gaps_modes(workload, port, cuda, fill_mode):
     probs = workload.genome_gaps(5000, seed=501, finalp_mode=2, prob_mode_pm=200, long_frac=0.08, long_hi=611, iupac_pm=3)
-    probs = api.arm_probability_mode(probs, port)
+    probs = checkers.arm_probability_mode(probs, port)
     want, got = port.solve(probs), cuda.solve(probs)
     assert not api.compare(*want, *got, rtol=RTOL)
     assert want[0]["null_list"].sum() > 0 and (want[0]["null_list"] == 0).sum() > 0
@@ -96,7 +108,7 @@ def test_known_splice_sites(workload, prob_hook):
     known = api.KNOWN_FN(lambda which, chrnum, pos, sign, user: int((pos * 7 + which) % 11 == 0))
     for novel in (1, 0):
         s = workload.make_setup(splice_prob=prob_hook, splice_known=known, novelsplicingp=novel)
-        o, lib = api.PortOracle(), api.CudaLib()
+        o, lib = checkers.PortOracle(), api.CudaLib()
         o.init(); lib.init()
         o.setup(s); lib.setup(s)
         lib.open(0)
@@ -112,7 +124,7 @@ def test_splicing_iit_modes(workload, ref, intron_level, novel):
     """splicing_iit != NULL in all four flavours (splice-site / intron level x novel splicing allowed or not); the
     last one is the bridge constrained to the given introns, dynprog.c:3552-3696.  Against the compiled reference."""
     known, intron = splicing_iit_hooks(known_mod=(3 if novel else 17) if intron_level else 3, intron_mod=3)
-    r = api.RefOracle()
+    r = checkers.RefOracle()
     r.init()
     s = workload.make_setup(splice_prob=r.splice_prob, splice_known=known, novelsplicingp=novel,
                             splice_intron=intron, intron_level=intron_level)
@@ -123,7 +135,7 @@ def test_splicing_iit_modes(workload, ref, intron_level, novel):
     lib.open(0)
     try:
         probs = workload.genome_gaps(1500, seed=51 + 2 * intron_level + novel, finalp_mode=2, prob_mode_pm=100, long_frac=0.03, long_hi=611)
-        probs = api.arm_probability_mode(probs, r)
+        probs = checkers.arm_probability_mode(probs, r)
         for force in (0, 1):
             lib.lib.dpc_set_fill(force)
             assert not api.compare(*r.solve(probs), *lib.solve(probs), rtol=RTOL)
@@ -206,7 +218,7 @@ def test_full_size_properties(workload, port, cuda):
 
 
 @pytest.mark.parametrize("kind,n", [("single", 1_000_000), ("genome", 500_000), ("genome_mix", 500_000), ("end", 1_000_000)])
-def test_full_size_exact_against_compiled_reference(kind, n):
+def test_full_size_exact_against_compiled_reference(kind, n, solve_path):
     """BASELINE configs[1..3] at their full sizes, EXACT: the unmodified reference (oracle/_ref/libdynprog_ref.so,
     all host threads) solves the same problems as the GPU and every output field must be equal -- scores, counts,
     intron boundaries, introntype, splice-site probabilities (rtol 1e-6), npairs, dynprogindex; the Pair records are
@@ -217,7 +229,7 @@ def test_full_size_exact_against_compiled_reference(kind, n):
         pytest.skip("compiled reference not built")
     mix = kind == "genome_mix"
     w, probs = bench.make_workload(0, n, "genome" if mix else kind, genome_mix=mix)
-    ref = api.RefOracle()
+    ref = checkers.RefOracle()
     ref.init()
     ref.setup(w.make_setup())
     hook = ref.splice_prob if mix else None        # finalp / probability mode need the MaxEnt hook
@@ -227,7 +239,7 @@ def test_full_size_exact_against_compiled_reference(kind, n):
     lib.setup(w.make_setup(splice_prob=hook))
     lib.open(0)
     if mix:
-        probs = api.arm_probability_mode(probs, lib)
+        probs = checkers.arm_probability_mode(probs, lib)
         assert (probs["use_probabilities_p"] == 1).sum() > n // 20 and probs["finalp"].sum() > n // 3
     try:
         got, _, _ = lib.solve(probs, want_pairs=False)
@@ -236,8 +248,16 @@ def test_full_size_exact_against_compiled_reference(kind, n):
         z = np.zeros(1, dtype=np.int64)
         assert not api.compare(want, empty, z, got, empty, z, rtol=RTOL)
         head = probs[:100_000]
-        assert not api.compare(*ref.solve(head), *lib.solve(head), rtol=RTOL)
+        want_head = ref.solve(head)
+        assert not api.compare(*want_head, *lib.solve(head), rtol=RTOL)
+        if solve_path == 0 and not mix:
+            # the two output routes of the device pipeline, each forced for every chunk
+            for path in (3, 4):
+                lib.lib.dpc_set_path(path)
+                assert not api.compare(*want_head, *lib.solve(head), rtol=RTOL)
+            lib.lib.dpc_set_path(0)
     finally:
+        lib.lib.dpc_set_path(solve_path)
         lib.close()
 
 
@@ -250,3 +270,72 @@ def test_splicejunction_solvers(workload, ref, port, cuda, fill_mode):
     assert not api.compare(*port.solve(probs), *got)
     mixed = np.concatenate([probs[:500], workload.end_gaps(500, seed=32), workload.single_gaps(500, seed=33)])
     assert not api.compare(*port.solve(mixed), *cuda.solve(mixed))
+
+
+def test_device_pipeline_is_taken_and_exact(workload, ref, solve_path):
+    """Hook-free batches must actually run the device pipeline (stats), with scattered queries (gathered), with one
+    contiguous query buffer (range copy), with page-locked output arrays (copied in place) and without pair output."""
+    if solve_path != 0:
+        pytest.skip("host half forced")
+    lib = api.CudaLib()
+    lib.init()
+    lib.setup(workload.make_setup())
+    lib.open(0)
+    o = checkers.RefOracle()
+    o.init()
+    o.setup(workload.make_setup())
+    try:
+        mixed = mixed_problems(workload, 3000, 4711, long_frac=0.03, long_hi=611)
+        mixed = mixed[(mixed["use_probabilities_p"] == 0) & (mixed["finalp"] == 0)]
+        want = o.solve(mixed)
+        one = workload.single_gaps(40000, extraband=30, seed=4712, edge_frac_pm=10, lower_case=1, iupac_pm=5)
+        want_one = o.solve(one)
+        for path in (3, 4, 2):                           # pairs expanded on the device / by host threads / per chunk
+            lib.lib.dpc_set_path(path)
+            got = lib.solve(mixed)
+            st = lib.stats()
+            assert st.pipeline_chunks > 0 and st.host_chunks == 0
+            assert not api.compare(*want, *got)
+            assert not api.compare(*want_one, *lib.solve(one))
+        want = want_one
+        # caller-owned, page-locked outputs: the copy engine writes results and pairs in place
+        res = np.zeros(len(one), dtype=api.RESULT_DT)
+        pairs = np.zeros(len(want[1]) + 16, dtype=api.PAIR_DT)
+        off = np.zeros(len(one) + 1, dtype=np.int64)
+        lib.register(pairs); lib.register(res)
+        try:
+            for _ in range(2):
+                pairs[:] = np.zeros(1, dtype=api.PAIR_DT)[0]
+                assert lib.solve_into(one, res, pairs, off) == len(want[1])
+                assert not api.compare(*want, res, pairs[:len(want[1])], off)
+        finally:
+            lib.unregister(pairs); lib.unregister(res)
+        got = lib.solve(one, want_pairs=False)
+        assert (got[0] == want[0]).all() and np.array_equal(got[2], want[2])
+        # a chunk that needs a hook refuses the forced pipeline and is served by the host half otherwise
+        probs = workload.genome_gaps(50, seed=4713, finalp_mode=0)
+        probs["use_probabilities_p"] = 1
+        with pytest.raises(RuntimeError):
+            lib.solve(probs)
+    finally:
+        lib.lib.dpc_set_path(0)
+        lib.close()
+
+
+def test_multi_device_context(workload, ref):
+    """dpc_ctx_new_multi: chunks dealt round-robin to the devices of the box, outputs in input order."""
+    lib = api.CudaLib()
+    ndev = lib.lib.dpc_device_count()
+    if ndev < 2:
+        pytest.skip("one device visible")
+    lib.init()
+    lib.setup(workload.make_setup())
+    lib.open_multi(list(range(min(ndev, 4))))
+    try:
+        probs = np.concatenate([workload.single_gaps(60000, extraband=30, seed=4801), workload.end_gaps(30000, seed=4802)])
+        o = checkers.RefOracle()
+        o.init()
+        o.setup(workload.make_setup())
+        assert not api.compare(*o.solve(probs), *lib.solve(probs))
+    finally:
+        lib.close()

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from gmap_gsnap_b200 import api
+from oracle import checkers
 from conftest import has_ref
 from util import GOLDEN_SETS, SPLICING_IIT_MODES, Golden, long_nogaps_ends, mixed_problems, splicing_iit_hooks
 
@@ -15,7 +16,7 @@ def golden():
 
 @pytest.fixture(scope="module")
 def golden_port(golden):
-    o = api.PortOracle()
+    o = checkers.PortOracle()
     o.init()
     o.setup(golden.setup())
     return o
@@ -23,7 +24,7 @@ def golden_port(golden):
 
 @pytest.fixture(scope="module")
 def golden_emul(golden):
-    e = api.EmulLib()
+    e = checkers.EmulLib()
     e.init()
     e.setup(golden.setup())
     return e
@@ -57,13 +58,13 @@ def test_golden_has_negative_cases(golden):
 
 @pytest.mark.parametrize("seed", [1, 2])
 def test_restatement_matches_compiled_reference(workload, ref, port, seed):
-    probs = api.arm_probability_mode(mixed_problems(workload, 1200, seed, long_frac=0.03, long_hi=611), ref)
+    probs = checkers.arm_probability_mode(mixed_problems(workload, 1200, seed, long_frac=0.03, long_hi=611), ref)
     assert not api.compare(*ref.solve(probs), *port.solve(probs))
 
 
 def test_probability_mode_matches_reference(workload, ref, port, emul):
     probs = workload.genome_gaps(800, seed=5, finalp_mode=2, prob_mode_pm=1000, long_frac=0.0)
-    probs = api.arm_probability_mode(probs, ref)
+    probs = checkers.arm_probability_mode(probs, ref)
     assert (probs["use_probabilities_p"] == 1).all()
     want = ref.solve(probs)
     assert not api.compare(*want, *port.solve(probs))
@@ -72,7 +73,7 @@ def test_probability_mode_matches_reference(workload, ref, port, emul):
 
 @pytest.mark.parametrize("fill", [0, 1], ids=["row_sweep_32_lanes", "memory_fill_1_lane"])
 def test_device_routines_on_cpu_match_oracle(workload, port, emul, fill):
-    probs = api.arm_probability_mode(mixed_problems(workload, 1500, 9, long_frac=0.03, long_hi=611), port)
+    probs = checkers.arm_probability_mode(mixed_problems(workload, 1500, 9, long_frac=0.03, long_hi=611), port)
     emul.set_fill(fill)
     try:
         got = emul.solve(probs)
@@ -109,7 +110,7 @@ def test_known_splice_sites(workload, prob_hook):
     known = api.KNOWN_FN(lambda which, chrnum, pos, sign, user: int((pos * 7 + which) % 11 == 0))
     for novel in (1, 0):
         s = workload.make_setup(splice_prob=prob_hook, splice_known=known, novelsplicingp=novel)
-        o, e = api.PortOracle(), api.EmulLib()
+        o, e = checkers.PortOracle(), checkers.EmulLib()
         o.init(); e.init()
         o.setup(s); e.setup(s)
         probs = workload.genome_gaps(300, seed=31 + novel, finalp_mode=2, long_frac=0.0)
@@ -141,15 +142,15 @@ def test_splicing_iit_modes_match_compiled_reference(workload, intron_level, nov
     if not has_ref():
         pytest.skip("compiled reference not built")
     known, intron = splicing_iit_hooks(known_mod=(3 if novel else 17) if intron_level else 3, intron_mod=3)
-    r = api.RefOracle()
+    r = checkers.RefOracle()
     r.init()
     s = workload.make_setup(splice_prob=r.splice_prob, splice_known=known, novelsplicingp=novel,
                             splice_intron=intron, intron_level=intron_level)
-    o, e = api.PortOracle(), api.EmulLib()
+    o, e = checkers.PortOracle(), checkers.EmulLib()
     o.init(); e.init()
     r.setup(s); o.setup(s); e.setup(s)
     probs = workload.genome_gaps(400, seed=41 + 2 * intron_level + novel, finalp_mode=2, prob_mode_pm=100, long_frac=0.02, long_hi=300)
-    probs = api.arm_probability_mode(probs, o)
+    probs = checkers.arm_probability_mode(probs, o)
     want = r.solve(probs)
     assert not api.compare(*want, *o.solve(probs))
     assert not api.compare(*want, *e.solve(probs))
@@ -161,7 +162,7 @@ def test_splicing_iit_modes_match_compiled_reference(workload, intron_level, nov
 def test_pairdistance_tables(mode):
     """pairdistance_init (dynprog.c:1127-1226) for every Mode_T: product table == restatement table,
     including the 'z' / 'Z' loop-bound quirks."""
-    o, lib = api.PortOracle(), api.CudaLib()
+    o, lib = checkers.PortOracle(), api.CudaLib()
     o.init(mode=mode)
     lib.init(mode=mode)
     for t in range(4):
@@ -236,3 +237,48 @@ def test_rebuild_without_the_staged_genome_stream(workload, port, emul):
     finally:
         emul.set_fill(0)
     assert not api.compare(*port.solve(probs), *got)
+
+
+def _hookless(probs):
+    """Problems the device pipeline takes: no use_probabilities_p (needs the host hook per position)."""
+    return probs[probs["use_probabilities_p"] == 0]
+
+
+@pytest.mark.parametrize("fill", [0, 1], ids=["row_sweep", "memory_fill"])
+def test_device_pipeline_routines_on_cpu(workload, port, emul, golden, golden_port, golden_emul, fill):
+    """dpc_pipe.h -- the per-problem routines of dpc_solve's device pipeline (argument checks and early returns,
+    descriptor packing, result finalisation, Pair-record expansion with 1 and with 32 lanes, staged and re-decoded
+    genome characters) -- compiled for the CPU, against the restatement: mixed batches, every golden set including
+    the 232 edge cases, long NOGAPS ends, band widths around the lane-chunk limits."""
+    try:
+        for e, o, sets in ((emul, port, None), (golden_emul, golden_port, GOLDEN_SETS)):
+            e.setup(e._setup)          # the checkers' state is process-wide: register this pair's genome
+            o.setup(o._setup)
+            e.set_fill(fill)
+            e.set_path(1)
+            if sets is None:
+                probs = _hookless(mixed_problems(workload, 1500, 909, long_frac=0.04, long_hi=611))
+                assert not api.compare(*o.solve(probs), *e.solve(probs))
+                probs = long_nogaps_ends(workload, lengths=(16383, 16384, 20000))
+                assert not api.compare(*o.solve(probs), *e.solve(probs))
+                probs = workload.single_gaps(300, extraband=30, seed=77, edge_frac_pm=100, lower_case=1, iupac_pm=20)
+                probs["extraband"] = np.arange(300) % 70
+                assert not api.compare(*o.solve(probs), *e.solve(probs))
+                probs = workload.end_gaps(3000, seed=78, edge_frac_pm=300, lower_case=1, iupac_pm=20)
+                for ea in range(4):
+                    probs["endalign"][ea::5] = ea
+                assert not api.compare(*o.solve(probs), *e.solve(probs))
+            else:
+                for name in sets:
+                    probs = golden.problems(name)
+                    keep = probs["use_probabilities_p"] == 0
+                    want = golden.expected(name)
+                    got = e.solve(probs[keep])
+                    ref = o.solve(probs[keep])
+                    assert not api.compare(*ref, *got), name
+                    assert (want[0][keep] == got[0]).all() or name == "genome", name
+    finally:
+        emul.set_fill(0)
+        emul.set_path(0)
+        emul.setup(emul._setup)
+        port.setup(port._setup)

@@ -8,6 +8,7 @@ import sys
 import numpy as np
 
 from gmap_gsnap_b200 import api, shard
+from oracle import checkers
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -18,12 +19,13 @@ sys.path.insert(0, os.path.join(%(root)r, "tests"))
 import numpy as np
 import torch.distributed as dist
 from gmap_gsnap_b200 import api, shard
+from oracle import checkers
 from util import mixed_problems
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 w = api.Workload(1_000_000, seed=5, nchr=2)
 probs = mixed_problems(w, 150, 33)            # same seeds on every rank: the same problem array everywhere
-em = api.EmulLib(); em.init()
+em = checkers.EmulLib(); em.init()
 em.setup(w.make_setup(splice_prob=api.PROB_FN(lambda which, pos, chroffset, user: ((pos * 2654435761 + which * 97) %% 1000003) / 1000003.0)))
 out = shard.solve_sharded(em, probs, rank, world, dist)
 if rank == 0:
@@ -55,7 +57,7 @@ def test_two_ranks_gloo_equal_one_process(tmp_path):
     from util import mixed_problems
     w = api.Workload(1_000_000, seed=5, nchr=2)
     probs = mixed_problems(w, 150, 33)
-    em = api.EmulLib()
+    em = checkers.EmulLib()
     em.init()
     em.setup(w.make_setup(splice_prob=api.PROB_FN(lambda which, pos, chroffset, user: ((pos * 2654435761 + which * 97) % 1000003) / 1000003.0)))
     want = em.solve(probs)

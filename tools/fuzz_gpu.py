@@ -5,10 +5,11 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gmap_gsnap_b200 import api
+from oracle import checkers
 
 nseeds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 w = api.Workload(8_000_000, seed=17, n_frac=0.001, nchr=4)
-ref = api.RefOracle(); ref.init(); ref.setup(w.make_setup())
+ref = checkers.RefOracle(); ref.init(); ref.setup(w.make_setup())
 hook = ref.splice_prob
 lib = api.CudaLib(); lib.init(); lib.setup(w.make_setup(splice_prob=hook)); lib.open(0)
 ref.setup(w.make_setup(splice_prob=hook))
@@ -33,7 +34,7 @@ for seed in range(1000, 1000 + nseeds):
     lib.setup(w.make_setup(splice_prob=hook)); ref.setup(w.make_setup(splice_prob=hook))
     probs = np.concatenate(sets)
     probs = probs[rng.permutation(len(probs))]
-    probs = api.arm_probability_mode(probs, ref)
+    probs = checkers.arm_probability_mode(probs, ref)
     bad = api.compare(*ref.solve(probs), *lib.solve(probs), rtol=1e-6)
     bad_total += len(bad)
     print("seed %d: %d problems, extraband %d, mismatches %d %s" % (seed, len(probs), eb, len(bad), bad[:2]), flush=True)
