@@ -1,19 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- banded gap-fill DP throughput (GCUPS, gap-fills/s) of libdynprog_cuda on B200.
 
-Workload (BASELINE.json configs[1]): batched Dynprog_single_gap, 1 M synthetic gap fills of 10-100 bp,
+Headline workload (BASELINE.json configs[1]): batched Dynprog_single_gap, 1 M synthetic gap fills of 10-100 bp,
 band (extraband_single) 30, widebandp, on ONE B200; random genome, queries = genomic windows with 5 %
 substitutions, 3 % deletions, 3 % insertions.  Under torchrun each rank owns one GPU and its own
-1 M problems (sharded by read, no collective on the data path): weak scaling.
+1 M problems (sharded by read, no collective on the data path): weak scaling.  The other two hot-path configs
+(configs[2] genome gaps with their stated finalp / halfp / probability mix, configs[3] end gaps: the 10 M reads x 2
+ends cut 8 ways = 2.5 M problems per GPU) run after the headline and are reported under `other_workloads`.
 
 A step = one pass of the hot path over the batch.
-  value   GCUPS with the batch resident in HBM (kernels only, CUDA events on the library's stream).
-  e2e     GCUPS through the C ABI with HOST buffers: dpc_solve = pack + H2D + kernels + D2H + result
-          finalisation + Pair-record rebuild, wall clock.
-  --impl reference   the reference's own dynprog.c (oracle/_ref, compiled unmodified) on all host cores.
+  value   GCUPS with the batch resident in HBM (solve kernels only, CUDA events on the library's stream).
+  e2e     GCUPS through the C ABI with HOST buffers: dpc_solve = copy-in, prepare / solve / finish / expand kernels,
+          copy-out of results and Pair records (or host expansion of the compact device records), wall clock.
+  --impl reference   the reference's own dynprog.c (oracle/_ref, compiled unmodified) on all host cores, same
+          problems, same config object.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -27,44 +29,70 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from gmap_gsnap_b200 import api  # noqa: E402
-from oracle import checkers  # noqa: E402   (the CPU reference: cpu_baseline and --impl reference only)
+from oracle import checkers  # noqa: E402   (the CPU reference: cpu_baseline, --impl reference and the parity sample only)
 
-METRIC = "banded_dp_gcups_single_gap"
 UNIT = "GCUPS"
-N_PROBLEMS = 1_000_000
 GENOME_BASES = 64_000_000
 EXTRABAND = 30
+OPS_PER_CELL = 20          # SURVEY.md 8(d) / DESIGN.md section 3: integer operations of one 3-state cell update
+
+WORKLOADS = {
+    "single": "Dynprog_single_gap, 1M synthetic 10-100 bp gap fills, band 30, on 1 B200 per rank (BASELINE configs[1])",
+    "genome": "Dynprog_genome_gap, 500K synthetic cDNA/genomic gaps across GT-AG/GC-AG/AT-AC introns 50 bp-20 kb, band 7, 10% long, "
+              "finalp and halfp both ways, 10% re-solved in probability mode (BASELINE configs[2])",
+    "end": "Dynprog_end5_gap/end3_gap, synthetic 250-bp read ends, tails 1-40 + 11 peeled, band 3; 10M reads x 2 ends cut 8 ways "
+           "= 2.5M problems per GPU (BASELINE configs[3])",
+    "gmap": "whole-program GMAP (stage 1-3) on synthetic 2-kb spliced transcripts vs a synthetic genome database, "
+            "gap fills collected from stage 3 into device batches (BASELINE configs[4], bounded sample)",
+}
+DEFAULT_PROBLEMS = {"single": 1_000_000, "genome": 500_000, "end": 2_500_000}
+METRICS = {"single": "banded_dp_gcups_single_gap", "genome": "banded_dp_gcups_genome_gap", "end": "banded_dp_gcups_end_gap"}
+STANDIN_HOOK = api.PROB_FN(lambda which, pos, chroffset, user: ((pos * 2654435761 + which * 97) % 1000003) / 1000003.0)
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
-    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def int32_alu_gops():
-    """Measured throughput of the integer ALU pipe (VIMNMX / LOP3), giga lane-operations per second."""
-    path = os.path.join(ROOT, "profiles", "int32_peak_r1.json")
-    if os.path.exists(path):
-        return float(json.load(open(path))["max_xor_gops"])
-    return 148 * 64 * 1.965          # the same figure from the data sheet: 64 lanes per clock per SM
+def ncu_traffic(workload, n):
+    """DRAM bytes per step of the solve kernels from the committed ncu capture of the same workload and size
+    (profiles/r2_traffic.json, written by tools/ncu_summary.py from the raw CSV next to it)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    t = json.load(open(path)).get(workload)
+    if not t or int(t["problems"]) != int(n):
+        return None, None
+    return float(t["dram_bytes_per_step"]), t["source"]
 
 
-def band_cells(probs):
-    """In-band cells of every matrix, for single gaps: one matrix each."""
-    L1 = probs["length1"].astype(np.int64)
-    L2 = probs["length2"].astype(np.int64)
-    eb = probs["extraband"].astype(np.int64)
+def band_cells(L1, L2, eb):
+    """In-band cells of matrices with widened bands."""
+    L1, L2, eb = (np.asarray(x, dtype=np.int64) for x in (L1, L2, eb))
     rband = np.where(L2 >= L1, L2 - L1 + eb, eb)
     lband = np.where(L2 >= L1, eb, L1 - L2 + eb)
-    total = np.zeros(len(probs), dtype=np.int64)
-    for c in range(1, int(L2.max()) + 1):
+    total = np.zeros(len(L1), dtype=np.int64)
+    for c in range(1, int(L2.max()) + 1 if len(L2) else 1):
         lo = np.maximum(1, c - rband)
         hi = np.minimum(L1, c + lband)
         total += np.where(c <= L2, np.maximum(hi - lo + 1, 0), 0)
     return total
+
+
+def cells_numpy(probs, workload):
+    """In-band cells of a batch in numpy (the reference arm has no device; the CUDA arm cross-checks the library's count)."""
+    L1, L2, eb = probs["length1"], probs["length2"], probs["extraband"]
+    if workload == "single":
+        return int(band_cells(L1, L2, eb).sum())
+    if workload == "genome":
+        ok = L1 > 1
+        return int(band_cells(L1[ok], L2[ok], eb[ok]).sum() + band_cells(L1[ok], probs["length2R"][ok], eb[ok]).sum())
+    filled = (probs["endalign"] != api.QUERYEND_NOGAPS) & (L1 > 0) & (L2 > 0)      # NOGAPS ends fill no matrix
+    return int(band_cells(L1[filled], L2[filled], eb[filled]).sum())
 
 
 class ClockSampler(threading.Thread):
@@ -99,15 +127,6 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-WORKLOADS = {
-    "single": "Dynprog_single_gap, 1M synthetic 10-100 bp gap fills, band 30, on 1 B200 per rank (BASELINE configs[1])",
-    "genome": "Dynprog_genome_gap, synthetic cDNA/genomic gaps across GT-AG/GC-AG/AT-AC introns 50 bp-20 kb, band 7, 10% long (BASELINE configs[2], finalp off)",
-    "end": "Dynprog_end5_gap/end3_gap, synthetic 250-bp read ends, tails 1-40 + 11 peeled, band 3 (BASELINE configs[3])",
-    "gmap": "whole-program GMAP (stage 1-3) on synthetic 2-kb spliced transcripts vs a synthetic genome database, "
-            "gap fills collected from stage 3 into device batches (BASELINE configs[4], bounded sample)",
-}
-
-
 def make_workload(rank, n, kind="single", genome_mix=False):
     """The synthetic inputs of BASELINE configs[1..3].  genome_mix: config 3's stated mix -- finalp and
     halfp both ways, a 10 % subset marked for the probability-mode second call (arm it with checkers.arm_probability_mode)."""
@@ -122,33 +141,63 @@ def make_workload(rank, n, kind="single", genome_mix=False):
     return w, probs
 
 
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path, all host threads (gmap -t N shape, gmap.c:2254-2276)."""
-    if rank != 0:
-        return
+def config_of(workload, n, extraband, cells):
+    """The `config` object: identical for the CUDA arm and for --impl reference."""
+    return {"workload": WORKLOADS[workload], "problems_per_gpu": int(n), "extraband": int(extraband), "genome_bases": GENOME_BASES,
+            "cells_per_gpu": int(cells),
+            "l2": "inputs larger than L2: every step streams all problem records, query bytes and result records through HBM"}
+
+
+class _MtSolver:
+    """solve() facade over RefOracle.solve_mt (results only), for arm_probability_mode."""
+
+    def __init__(self, ref):
+        self.ref = ref
+
+    def solve(self, problems, want_pairs=False):
+        res, _ = self.ref.solve_mt(problems, os.cpu_count() or 1)
+        return res, None, None
+
+
+def reference_for(w, workload):
+    """The compiled reference registered on workload w; genome gaps get its own MaxEnt tables as the hook."""
     ref = checkers.RefOracle()
     ref.init()
-    cores = os.cpu_count() or 1
-    sample = min(N_PROBLEMS, max(20000, 40000 * cores))
-    w, probs = make_workload(0, sample)
     ref.setup(w.make_setup())
-    cells = int(band_cells(probs).sum())
+    if workload == "genome":
+        ref.setup(w.make_setup(splice_prob=ref.splice_prob))
+    return ref
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, all host threads (gmap -t N shape, gmap.c:2254-2276), on the
+    same problems and with the same config object as the CUDA arm."""
+    if rank != 0:
+        return
+    workload = args.workload
+    n = args.problems or DEFAULT_PROBLEMS[workload]
+    w, probs = make_workload(0, n, workload, genome_mix=workload == "genome")
+    ref = reference_for(w, workload)
+    if workload == "genome":
+        probs = checkers.arm_probability_mode(probs, _MtSolver(ref))
+    cores = os.cpu_count() or 1
+    cells = cells_numpy(probs, workload)
     for _ in range(args.warmup):
-        ref.solve_mt(probs[: sample // 4], cores)
+        ref.solve_mt(probs[: max(1000, n // 8)], cores)
     secs = 0.0
     for _ in range(args.steps):
         _, s = ref.solve_mt(probs, cores)
         secs += s
     gcups = cells * args.steps / secs / 1e9
     line = {
-        "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRICS[workload], "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "fills_per_s": sample * args.steps / secs,
-        "config": {"workload": "Dynprog_single_gap, synthetic 10-100 bp gap fills, band 30 (BASELINE configs[1])",
-                   "problems_per_step": sample, "extraband_single": EXTRABAND, "genome_bases": GENOME_BASES},
+        "fills_per_s": n * args.steps / secs,
+        "config": config_of(workload, n, probs["extraband"][0], cells),
         "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": "%d of the 1M single-gap problems per step, unmodified dynprog.c -O3, one Dynprog_T + Pairpool per thread" % sample},
+                         "sample": "all %d problems of the step, unmodified dynprog.c -O3, one Dynprog_T triple + Pairpool per thread, "
+                                   "%d threads (scratch allocation outside the timed region)" % (n, cores)},
         "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -166,7 +215,7 @@ def run_gmap_workload(args, rank, world, local_rank):
         return
     cores = os.cpu_count() or 1
     threads = max(1, cores // max(1, world))
-    n = args.problems if args.problems != N_PROBLEMS else 16000
+    n = args.problems or 16000
     case = g.prepare("/tmp/dpc_gmap_case_%d" % rank, args.genome_bases, 4, n, seed=5 + rank)
     line = {"metric": "gmap_queries_per_s", "unit": "queries/s", "n_gpus": world, "steps": 1, "warmup": 0,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -235,15 +284,154 @@ def run_gmap_workload(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def measure(args, lib, workload, n, rank, world, local_rank, host_threads, barrier, allreduce, sampler, have_ref):
+    """One workload through both measurements (kernels only, end to end) plus the parity sample of this rank's shard.
+    Returns the JSON object (rank 0 prints it; the other ranks contribute through the reductions)."""
+    L = lib.lib
+    mix = workload == "genome"
+    w, probs = make_workload(rank, n, workload, genome_mix=mix)
+    ref = reference_for(w, workload) if have_ref else None
+    hook = (ref.splice_prob if ref is not None else STANDIN_HOOK) if mix else None     # MaxEnt hook = the reference's own tables
+    lib.setup(w.make_setup(splice_prob=hook))
+    if mix:
+        probs = checkers.arm_probability_mode(probs, lib)       # second call of stage3.c:5833: threshold from a first pass
+    lib.load(probs)                                             # leaves the batch resident in HBM on the context's own stream
+    kernel_stats = lib.stats()
+    cells = int(kernel_stats.cells)
+    assert cells == cells_numpy(probs, workload), "cell count mismatch"
+
+    def step():
+        lib.check(L.dpc_relaunch(lib.ctx), "dpc_relaunch")
+        lib.check(L.dpc_sync(lib.ctx), "dpc_sync")
+        return lib.kernel_ms()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    ms = [step() for _ in range(args.steps)]
+    barrier()
+    dev_ms = allreduce(float(sum(ms)), "MAX")
+    total_cells = allreduce(float(cells), "SUM")
+    total_fills = allreduce(float(n), "SUM")
+    launches = kernel_stats.launches * args.steps
+
+    # end to end through the C ABI with host buffers (results + Pair records); the caller-owned arrays are page-locked
+    # once (like a long-lived pair pool), so the copy engine reads the problems and writes results / records in place
+    lib.check(L.dpc_reset(lib.ctx), "dpc_reset")
+    res, pairs, off = lib.solve(probs)                 # also sizes the output arrays, reused below
+    npairs = len(pairs)
+    pairs = np.zeros(npairs + 1024, dtype=api.PAIR_DT)
+    r2 = np.zeros(n, dtype=api.RESULT_DT)
+    pinned = [pairs, r2, probs, w.last_qbuf]
+    for a in pinned:
+        lib.register(a)
+    for _ in range(2):
+        assert lib.solve_into(probs, r2, pairs, off) == npairs
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        lib.solve_into(probs, r2, pairs, off)
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    st = lib.stats()
+    # the same call without Pair records (scores, end points, intron boundaries, counts only): what a caller pays
+    # that compares candidates by score first
+    lib.solve_into(probs, r2, None, off)
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        lib.solve_into(probs, r2, None, off)
+    e2e_results_s = (time.perf_counter() - t0) / args.e2e_steps
+    for a in pinned:
+        lib.unregister(a)
+    barrier()
+    if sampler is not None:
+        sampler.stop_flag.set()
+        sampler.join()
+    e2e_s = allreduce(e2e_s, "MAX")
+    e2e_results_s = allreduce(e2e_results_s, "MAX")
+    same = True
+    for f in api.RESULT_FIELDS:
+        same = same and bool((r2[f] == res[f]).all())
+    assert same, "dpc_solve is not repeatable"
+
+    # parity: every rank compares a strided sample of ITS OWN shard with the compiled reference (all fields, Pair records)
+    parity_ok, sample_n, stride = 0.0, 0, max(1, n // 50_000)
+    if have_ref:
+        sample = probs[::stride]
+        sample_n = len(sample)
+        bad = api.compare(*ref.solve(sample), *lib.solve(sample), rtol=1e-6)
+        if bad:
+            raise AssertionError("rank %d: results differ from the compiled reference: %s" % (rank, bad[:3]))
+        parity_ok = 1.0
+    parity_ranks = int(allreduce(parity_ok, "SUM"))
+
+    hbm_peak, peak_src = peaks()
+    alu_gops, mix_gops = lib.int_peak(local_rank)
+    step_ms = dev_ms / args.steps
+    mean_ms = float(np.mean(ms))
+    gcups = total_cells / (step_ms * 1e-3) / 1e9
+    algo_bytes = float(kernel_stats.fill_bytes)
+    traffic, traffic_src = ncu_traffic(workload, n)
+    line = {
+        "metric": METRICS[workload], "value": gcups, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "fills_per_s": total_fills / (step_ms * 1e-3),
+        "config": config_of(workload, n, probs["extraband"][0], cells),
+        "e2e": {"value": total_cells / e2e_s / 1e9, "unit": UNIT, "fills_per_s": total_fills / e2e_s, "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
+                "host_threads_per_rank": host_threads,
+                "pipeline_chunks": int(st.pipeline_chunks), "host_half_chunks": int(st.host_chunks),
+                "results_only": {"value": total_cells / e2e_results_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_results_s,
+                                 "note": "dpc_solve with pairs == NULL: scores, end points, intron boundaries, counts"},
+                "includes": "dpc_solve from and into page-locked caller arrays: copy-in of problem records + query bytes, prepare / solve / "
+                            "finish / expand kernels, copy-out of results and %d Pair records (expanded on the device or, when the link "
+                            "is backlogged, by host threads from the compact device records)" % npairs},
+        "gpu_launches": int(launches),
+        "parity_checked_ranks": parity_ranks,
+        "parity_sample": ("every rank: %d problems of its own shard (stride %d), all result fields and Pair records equal to the compiled "
+                          "reference" % (sample_n, stride)) if have_ref else "compiled reference not on this box",
+        "roofline": {"bound": "int32_alu", "achieved": cells * OPS_PER_CELL / (mean_ms * 1e-3) / 1e12, "peak": alu_gops / 1e3,
+                     "unit": "T int32 lane-op/s", "frac": cells * OPS_PER_CELL / (mean_ms * 1e-3) / 1e9 / alu_gops,
+                     "ops_per_cell": OPS_PER_CELL,
+                     "peak_source": "measured in this process (dpc_measure_int_peak: independent VIMNMX+LOP3 chains = the integer ALU pipe "
+                                    "the fill saturates, 64 lanes per clock per SM)",
+                     "peak_fill_mix": mix_gops / 1e3,
+                     "frac_of_fill_mix": cells * OPS_PER_CELL / (mean_ms * 1e-3) / 1e9 / mix_gops,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "note": "achieved = in-band cells x 20 integer ops (SURVEY.md 8d; derivation in DESIGN.md section 3) / mean kernel "
+                             "time per step; peak_fill_mix is the same device running the fill's add/max/select mix, where adds may "
+                             "issue on the FMA pipe"},
+        "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (mean_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": algo_bytes / (mean_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": algo_bytes, "traffic": traffic,
+                         "note": "matrices stay in registers and direction planes in shared memory: algorithmic HBM bytes are "
+                                 "descriptors, sequences, result records and staged genome characters only"},
+    }
+    if sampler is not None:
+        line["clocks"] = sampler.summary()
+    if rank == 0 and have_ref and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(n, max(20000, 40000 * cores))
+        _, secs = ref.solve_mt(probs[:sample], cores)
+        scells = cells_numpy(probs[:sample], workload)
+        line["cpu_baseline"] = {"value": scells / secs / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+                                "fills_per_s": sample / secs,
+                                "sample": "first %d of the %d problems, unmodified reference dynprog.c (-O3), %d threads" % (sample, n, cores)}
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--problems", type=int, default=N_PROBLEMS)
+    ap.add_argument("--problems", type=int, default=0, help="problems per GPU (default: the config's size)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="headline workload only")
     ap.add_argument("--workload", default="single", choices=sorted(WORKLOADS), help="single = the headline config; genome / end = the other hot-path configs")
     ap.add_argument("--genome-bases", type=int, default=100_000_000, help="gmap workload: size of the synthetic genome database")
     ap.add_argument("--fibers", type=int, default=16, help="gmap workload: worker loops per worker thread (DPC_FIBERS)")
@@ -281,138 +469,44 @@ def main():
         dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
 
-    w, probs = make_workload(rank, args.problems, args.workload)
+    n = args.problems or DEFAULT_PROBLEMS[args.workload]
     lib = api.CudaLib()
     lib.init()
-    lib.setup(w.make_setup())
+    boot = api.Workload(1_000_000, seed=1, nchr=1)        # a context needs a registered genome; measure() registers its own
+    lib.setup(boot.make_setup())
     lib.open(local_rank)
-    L = lib.lib
-    n = len(probs)
-    # the ranks of one box share its host cores: split them (packing / Pair rebuild threads of dpc_solve)
+    # the ranks of one box share its host cores: split them (driver + worker threads of dpc_solve)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     host_threads = max(1, (os.cpu_count() or 1) // max(1, local_world))
-    lib.check(L.dpc_set_threads(lib.ctx, min(64, host_threads)), "dpc_set_threads")
+    lib.check(lib.lib.dpc_set_threads(lib.ctx, min(64, host_threads)), "dpc_set_threads")
 
-    # results for the sanity checks (bulk call), then the whole batch resident in HBM on the context's own stream
     if args.kernel_only:
+        w, probs = make_workload(rank, n, args.workload, genome_mix=False)
+        lib.setup(w.make_setup())
         lib.load(probs)
         t = []
         for _ in range(args.warmup + args.steps):
-            lib.check(L.dpc_relaunch(lib.ctx), "dpc_relaunch")
-            lib.check(L.dpc_sync(lib.ctx), "dpc_sync")
+            lib.check(lib.lib.dpc_relaunch(lib.ctx), "dpc_relaunch")
+            lib.check(lib.lib.dpc_sync(lib.ctx), "dpc_sync")
             t.append(lib.kernel_ms())
         print(json.dumps({"kernel_only_ms": t, "problems": n, "cells": int(lib.stats().cells)}), flush=True)
         lib.close()
         return
-    res, _, _ = lib.solve(probs, want_pairs=False)
-    lib.load(probs)
-    stats = lib.stats()
-    cells = int(stats.cells)
-    if args.workload == "single":
-        assert cells == int(band_cells(probs).sum()), "cell count mismatch"
-        assert (res["null_list"] == 0).all()
 
-    def step():
-        lib.check(L.dpc_relaunch(lib.ctx), "dpc_relaunch")
-        lib.check(L.dpc_sync(lib.ctx), "dpc_sync")
-        return lib.kernel_ms()
-
-    for _ in range(args.warmup):
-        step()
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdynprog_ref.so"))
     sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    ms = [step() for _ in range(args.steps)]
-    barrier()
-    dev_ms = allreduce(float(sum(ms)), "MAX")
-    total_cells = allreduce(float(cells), "SUM")
-    total_fills = allreduce(float(n), "SUM")
-    launches = stats.launches * args.steps
-
-    # end to end through the C ABI with host buffers (results + Pair records)
-    kernel_stats = lib.stats()
-    lib.check(L.dpc_reset(lib.ctx), "dpc_reset")
-    r2, pairs, off = lib.solve(probs)             # also sizes the caller-owned output arrays, reused below
-    npairs = len(pairs)
-    pairs = np.zeros(npairs + 1024, dtype=api.PAIR_DT)
-    # caller-owned output arrays, page-locked once (like a long-lived pair pool): the copy engine writes into them
-    pinned = [pairs, r2, probs, w.last_qbuf]
-    for a in pinned:
-        lib.register(a)
-    for _ in range(2):
-        assert lib.solve_into(probs, r2, pairs, off) == npairs
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        lib.solve_into(probs, r2, pairs, off)
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    # the same call without Pair records (scores, end points, intron boundaries, counts only): what a caller pays
-    # that compares candidates by score first, and what the Pair rebuild costs on the host
-    lib.solve_into(probs, r2, None, off)
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        lib.solve_into(probs, r2, None, off)
-    e2e_results_s = (time.perf_counter() - t0) / args.e2e_steps
-    for a in pinned:
-        lib.unregister(a)
-    pairs = pairs[:npairs]
-    barrier()
-    sampler.stop_flag.set()
-    sampler.join()
-    e2e_s = allreduce(e2e_s, "MAX")
-    e2e_results_s = allreduce(e2e_results_s, "MAX")
-    st = lib.stats()
-    assert (r2 == res).all()
-
-    hbm_peak, peak_src, sm_max = peaks()
-    step_ms = dev_ms / args.steps
-    gcups = total_cells / (step_ms * 1e-3) / 1e9
-    algo_bytes = float(kernel_stats.fill_bytes)
-    line = {
-        "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
-        "fills_per_s": total_fills / (step_ms * 1e-3),
-        "config": {"workload": WORKLOADS[args.workload],
-                   "problems_per_gpu": n, "extraband": int(probs["extraband"][0]), "genome_bases": GENOME_BASES,
-                   "cells_per_gpu": cells, "l2": "inputs larger than L2 (descriptors + sequences + results = %.0f MB per step)" % (algo_bytes / 1e6)},
-        "e2e": {"value": total_cells / e2e_s / 1e9, "unit": UNIT, "fills_per_s": total_fills / e2e_s, "ms_per_step": 1e3 * e2e_s,
-                "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
-                "host_threads_per_rank": host_threads,
-                "results_only": {"value": total_cells / e2e_results_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_results_s,
-                                 "note": "dpc_solve with pairs == NULL: everything but the Pair-record rebuild"},
-                "includes": "dpc_solve: pack, H2D, kernels, D2H, result finalisation, Pair-record rebuild (%d records)" % len(pairs)},
-        "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms[len(ms) // 2] * 1e-3) / 1e9 if rank == 0 else None,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9 / hbm_peak,
-                     "traffic": 620.4e6 if (args.workload == "single" and n == 1_000_000) else None,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the step's two launches, "
-                                       "profiles/r1_final_single_gap_ncu_full.csv (bytes per step)",
-                     "peak_source": peak_src,
-                     "note": "fused fill+traceback keeps matrices and direction nibbles in shared memory; algorithmic HBM bytes are "
-                             "descriptors, sequences and result records only, so the kernel is integer-ALU/latency bound (see alu_roofline)"},
-        "alu_roofline": {"achieved_gcups_per_gpu": cells / (float(np.mean(ms)) * 1e-3) / 1e9,
-                         "peak_gcups": int32_alu_gops() / 25,
-                         "note": "peak = measured integer-ALU-pipe throughput (tools/int_peak.cu on this pool's B200: 18.5 T "
-                                 "VIMNMX+LOP3 lane-ops/s = 63.7 per clock per SM, profiles/int32_peak_r1.json) / 25 ALU ops per cell (DESIGN.md)"},
-    }
-    line["roofline"]["achieved"] = algo_bytes / (float(np.mean(ms)) * 1e-3) / 1e9
-    line["alu_roofline"]["frac"] = line["alu_roofline"]["achieved_gcups_per_gpu"] / line["alu_roofline"]["peak_gcups"]
-
-    if args.workload != "single":
-        line["metric"] = "banded_dp_gcups_%s_gap" % args.workload
-    if rank == 0 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdynprog_ref.so")):
-        ref = checkers.RefOracle()
-        ref.init()
-        ref.setup(w.make_setup())
-        cores = os.cpu_count() or 1
-        sample = min(n, max(20000, 40000 * cores))
-        _, secs = ref.solve_mt(probs[:sample], cores)
-        scells = int(band_cells(probs[:sample]).sum()) if args.workload == "single" else int(round(cells * sample / n))
-        line["cpu_baseline"] = {"value": scells / secs / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
-                                "fills_per_s": sample / secs,
-                                "sample": "first %d of the %d problems, unmodified reference dynprog.c (-O3), %d threads" % (sample, n, cores)}
+    line = measure(args, lib, args.workload, n, rank, world, local_rank, host_threads, barrier, allreduce, sampler, have_ref)
+    if args.workload == "single" and not args.no_other_workloads:
+        # BASELINE configs[2] and configs[3] in the same record: fewer timed steps, same measurements
+        short = argparse.Namespace(**vars(args))
+        short.steps, short.e2e_steps = max(3, args.steps // 3), 3
+        others = {}
+        for wl in ("genome", "end"):
+            o = measure(short, lib, wl, DEFAULT_PROBLEMS[wl], rank, world, local_rank, host_threads, barrier, allreduce, None, have_ref)
+            keep = ("metric", "value", "unit", "ms_per_step", "steps", "fills_per_s", "config", "e2e", "gpu_launches", "parity_checked_ranks",
+                    "roofline", "cpu_baseline")
+            others[wl] = {k: o[k] for k in keep if k in o}
+        line["other_workloads"] = others
     lib.close()
     if rank == 0:
         print(json.dumps(line), flush=True)

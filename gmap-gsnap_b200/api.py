@@ -350,6 +350,7 @@ class CudaLib(_SolverLib):
         L.dpc_host_unregister.argtypes = [C.c_void_p]
         L.dpc_set_path.argtypes = [C.c_int]
         L.dpc_device_count.restype = C.c_int
+        L.dpc_measure_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.dpc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.dpc_pairdistance.argtypes = [C.c_int] * 3
         L.dpc_strerror.restype = C.c_char_p
@@ -441,6 +442,12 @@ class CudaLib(_SolverLib):
         ms = C.c_float()
         self.check(self.lib.dpc_last_kernel_ms(self.ctx, C.byref(ms)), "dpc_last_kernel_ms")
         return float(ms.value)
+
+    def int_peak(self, device=0):
+        """(ALU-pipe, fill-mix) giga lane-operations per second measured on `device` right now."""
+        a, m = C.c_double(), C.c_double()
+        self.check(self.lib.dpc_measure_int_peak(device, C.byref(a), C.byref(m)), "dpc_measure_int_peak")
+        return float(a.value), float(m.value)
 
     def open_multi(self, devices):
         arr = (C.c_int * len(devices))(*devices)

@@ -533,6 +533,38 @@ struct dpc_ctx {
 static int g_path = 0;               /* dpc_set_path: 0 auto, 1 host half only, 2 device pipeline or fail, 3 / 4 = 2 with the
                                         Pair records expanded on the device / by the host */
 
+/* ---- calibration of the roofline denominators (SURVEY.md 8d asks for a measured INT32 peak, not an assumed one) ---- */
+#define PEAK_ITER 4096
+template <int MODE> __global__ void __launch_bounds__(256) dpc_int_peak_kernel(int *out, int a, int b) {
+  int x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 8
+  for (int i = 0; i < PEAK_ITER; i++) {
+    if (MODE == 0) {          /* VIMNMX + LOP3: both on the integer ALU pipe (the pipe the fill saturates) */
+      x0 = max(x0, a) ^ b; x1 = max(x1, a) ^ b; x2 = max(x2, a) ^ b; x3 = max(x3, a) ^ b;
+      x4 = max(x4, a) ^ b; x5 = max(x5, a) ^ b; x6 = max(x6, a) ^ b; x7 = max(x7, a) ^ b;
+    } else {                  /* the fill's mix -- add, max, compare/select -- where the adds may go to the FMA pipe as IMAD */
+      x0 = max(x0 + a, x1); x1 = x1 > x2 ? x1 + b : x2; x2 = max(x2 + a, x3); x3 = x3 > x4 ? x3 + b : x4;
+      x4 = max(x4 + a, x5); x5 = x5 > x6 ? x5 + b : x6; x6 = max(x6 + a, x7); x7 = x7 > x0 ? x7 + b : x0;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
+template <int MODE> static int int_peak_run(int *d, int grid, double *gops) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int w = 0; w < 3; w++) dpc_int_peak_kernel<MODE><<<grid, 256>>>(d, 3, 5);
+  CK(cudaEventRecord(e0));
+  const int reps = 20;
+  for (int r = 0; r < reps; r++) dpc_int_peak_kernel<MODE><<<grid, 256>>>(d, 3, 5);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *gops = (double)grid * 256 * PEAK_ITER * 16.0 * reps / (ms * 1e-3) / 1e9;      /* 8 chains x 2 lane-operations per step */
+  return DPC_OK;
+}
+
 /* ---- C ABI ---------------------------------------------------------------------------------- */
 extern "C" {
 
@@ -1087,6 +1119,20 @@ int dpc_sync(dpc_ctx_t *c) {
   CK(cudaStreamSynchronize(e.stream));
   if (e.flushed && !e.batch.dprobs.empty()) CK(cudaEventElapsedTime(&e.ms_total, e.ev0, e.ev1));
   return DPC_OK;
+}
+
+int dpc_measure_int_peak(int device, double *alu_gops, double *mix_gops) {
+  if (!alu_gops || !mix_gops || device < 0 || device >= dpc_device_count()) return DPC_ERR_ARG;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  const int grid = p.multiProcessorCount * 8;
+  int *d = NULL;
+  CK(cudaMalloc(&d, (size_t)grid * 256 * sizeof(int)));
+  int rc = int_peak_run<0>(d, grid, alu_gops);
+  if (rc == DPC_OK) rc = int_peak_run<1>(d, grid, mix_gops);
+  cudaFree(d);
+  return rc;
 }
 
 int dpc_last_kernel_ms(dpc_ctx_t *c, float *ms) {

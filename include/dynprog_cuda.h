@@ -273,6 +273,10 @@ int dpc_set_fill(int force_generic);
  * threads (by default a pipeline chunk takes the host route when the PCIe backlog would outlast the rebuild).
  * All of them return identical outputs. */
 int dpc_set_path(int path);
+/* Calibration of the roofline denominators on `device`: giga lane-operations per second of the integer ALU pipe
+ * (independent VIMNMX + LOP3 chains: the pipe the fill saturates) and of the fill's add / max / select mix (adds may
+ * issue on the FMA pipe).  Runs for a few milliseconds. */
+int dpc_measure_int_peak(int device, double *alu_gops, double *mix_gops);
 /* Device time in ms of the last dpc_flush / dpc_relaunch (CUDA events recorded on the context's stream around the
  * kernels; fill, bridge and traceback are one fused kernel per launch class). */
 int dpc_last_kernel_ms(dpc_ctx_t *ctx, float *ms);
