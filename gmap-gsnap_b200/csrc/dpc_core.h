@@ -412,6 +412,71 @@ struct Bridge { int have, finalscore, rL, cL, rR, cR, introntype; };
  * (3331-3373) and intron_score for every (leftdi & rightdi) value are tabulated once, so one candidate costs two
  * byte loads, an AND and a table load instead of two compare chains and a switch.  Candidates are in band by
  * construction (their column ranges are clipped to the band, 3545-3549), so the nogap band is read directly. */
+/* the tables of the bridge: dinucleotide code of every column (3331-3373) and intron_score for every
+ * (leftdi & rightdi) value, so that one candidate costs two byte loads, an AND and a table load */
+DPC_HD void dpc_bridge_tables(const Mat &mL, const Mat &mR, const DevProb &p, uint8_t *ldi, uint8_t *rdi, int8_t *itab, const Lanes &ln) {
+  const int L2L = mL.L2, L2R = mR.L2, finalp = (p.flags & DPC_F_FINALP) != 0;
+  const uint8_t *gL = mL.colch, *gR = mR.colch;
+  int it;
+  for (int c = ln.lane; c < L2L; c += ln.n) ldi[c] = (uint8_t)dpc_leftdi(gL[c], gL[c + 1]);
+  for (int c = ln.lane; c < L2R; c += ln.n) rdi[c] = (uint8_t)dpc_rightdi(gR[c + 1], gR[c]);
+  for (int t = ln.lane; t < 64; t += ln.n) itab[t] = (int8_t)dpc_intron_score(&it, t, t, p.cdna_direction, p.reward, finalp);
+  DPC_SYNC();
+}
+
+/* from the winning candidate (scan-order key) to the reference's outputs: bestrL/cL/rR/cR, finalscore, introntype */
+DPC_HD void dpc_bridge_finish(Bridge &br, Best best, double bestprob, int probkey, const Mat &mL, const Mat &mR, const DevProb &p,
+                              const uint8_t *lknown, const uint8_t *rknown, const uint8_t *introns, const Lanes &ln) {
+  const int L1 = mL.L1, L2L = mL.L2, L2R = mR.L2, eb = p.extraband;
+  const int rbandL = L2L - L1 + eb, lbandL = eb, lbandR = eb;
+  const int finalp = (p.flags & DPC_F_FINALP) != 0, halfp = (p.flags & DPC_F_HALFP) != 0;
+  const int probmode = (p.flags & DPC_F_PROBMODE) != 0;
+  const uint8_t *gL = mL.colch, *gR = mR.colch;
+  int it;
+  (void)L2R; (void)bestprob;
+  if (probmode) {
+#ifdef __CUDACC__
+    for (int o = 16; o > 0; o >>= 1) {
+      double q = __shfl_xor_sync(0xffffffffu, bestprob, o); int k = __shfl_xor_sync(0xffffffffu, probkey, o);
+      if (q > bestprob || (q == bestprob && k < probkey)) { bestprob = q; probkey = k; }
+    }
+#endif
+    best.key = probkey;
+    br.have = probkey != 0x7fffffff;
+  } else {
+    dpc_warp_best(best, 0, ln);
+    br.have = best.key != 0x7fffffff;
+  }
+  br.introntype = 0;
+  if (!br.have) {
+    br.finalscore = (probmode || introns) ? DPC_BRIDGE_FLOOR : (halfp ? DPC_BRIDGE_FLOOR - DPC_BRIDGE_FLOOR / 2 : DPC_BRIDGE_FLOOR);
+    br.rL = br.cL = br.rR = br.cR = 0;
+    return;
+  }
+  {
+    int rL = best.key >> 13, j = best.key & 8191, rR = L1 - rL;
+    int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
+    int cloR = rR - lbandR < 1 ? 1 : rR - lbandR;
+    int nL = chighL - cloL + 1;
+    if (nL < 0) nL = 0;
+    int left = j < nL, cL = left ? cloL + j : rL, cR = left ? rR : cloR + (j - nL);
+    int sI = dpc_intron_score(&it, dpc_leftdi(gL[cL], gL[cL + 1]), dpc_rightdi(gR[cR + 1], gR[cR]), p.cdna_direction, p.reward, finalp);
+    br.rL = rL; br.cL = cL; br.rR = rR; br.cR = cR;
+    if (introns) {                                                      /* 3694-3695 */
+      br.finalscore = best.score;
+      br.introntype = 0;
+    } else if (probmode) {                                                     /* 4055-4080: -1 on both sides */
+      int sL = dpc_nscore(mL, rL, cL) + (lknown && lknown[cL] ? 20 : 0) - (dpc_dirN(mL, rL, cL) > 0 ? 1 : 0);
+      int sR = dpc_nscore(mR, rR, cR) + (rknown && rknown[cR] ? 20 : 0) - (dpc_dirN(mR, rR, cR) > 0 ? 1 : 0);
+      br.finalscore = halfp ? sL + sI + sR - sI / 2 : sL + sI + sR;
+      br.introntype = -1;                                               /* *introntype left untouched, 4071 */
+    } else {
+      br.finalscore = halfp ? best.score - sI / 2 : best.score;        /* 3823-3827 */
+      br.introntype = it;
+    }
+  }
+}
+
 DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const DevProb &p,
                               const uint8_t *lknown, const uint8_t *rknown, const double *lp, const double *rp,
                               const uint8_t *introns, uint8_t *ldi, uint8_t *rdi, int8_t *itab, const Lanes &ln) {
@@ -423,10 +488,7 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
   Best best; best.score = DPC_BRIDGE_FLOOR; best.key = 0x7fffffff;
   double bestprob = 0.0; int probkey = 0x7fffffff;
   int it;
-  for (int c = ln.lane; c < L2L; c += ln.n) ldi[c] = (uint8_t)dpc_leftdi(gL[c], gL[c + 1]);
-  for (int c = ln.lane; c < L2R; c += ln.n) rdi[c] = (uint8_t)dpc_rightdi(gR[c + 1], gR[c]);
-  for (int t = ln.lane; t < 64; t += ln.n) itab[t] = (int8_t)dpc_intron_score(&it, t, t, p.cdna_direction, p.reward, finalp);
-  DPC_SYNC();
+  dpc_bridge_tables(mL, mR, p, ldi, rdi, itab, ln);
   const bool fast = mL.planes && mR.planes && mL.cpl == 1 && mR.cpl == 1 && !lknown && !rknown && !probmode;
   if (introns) {
     /* novelsplicingp == false with an intron-level IIT, 3552-3696: only (cL, cR) pairs that are given introns (the
@@ -538,47 +600,7 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
       else if (dpc_better(s, key, best, 0)) { best.score = s; best.key = key; }
     }
   }
-  if (probmode) {
-#ifdef __CUDACC__
-    for (int o = 16; o > 0; o >>= 1) {
-      double q = __shfl_xor_sync(0xffffffffu, bestprob, o); int k = __shfl_xor_sync(0xffffffffu, probkey, o);
-      if (q > bestprob || (q == bestprob && k < probkey)) { bestprob = q; probkey = k; }
-    }
-#endif
-    best.key = probkey;
-    br.have = probkey != 0x7fffffff;
-  } else {
-    dpc_warp_best(best, 0, ln);
-    br.have = best.key != 0x7fffffff;
-  }
-  br.introntype = 0;
-  if (!br.have) {
-    br.finalscore = (probmode || introns) ? DPC_BRIDGE_FLOOR : (halfp ? DPC_BRIDGE_FLOOR - DPC_BRIDGE_FLOOR / 2 : DPC_BRIDGE_FLOOR);
-    br.rL = br.cL = br.rR = br.cR = 0;
-    return;
-  }
-  {
-    int rL = best.key >> 13, j = best.key & 8191, rR = L1 - rL;
-    int cloL = rL - lbandL < 1 ? 1 : rL - lbandL, chighL = rL + rbandL > L2L - 1 ? L2L - 1 : rL + rbandL;
-    int cloR = rR - lbandR < 1 ? 1 : rR - lbandR;
-    int nL = chighL - cloL + 1;
-    if (nL < 0) nL = 0;
-    int left = j < nL, cL = left ? cloL + j : rL, cR = left ? rR : cloR + (j - nL);
-    int sI = dpc_intron_score(&it, dpc_leftdi(gL[cL], gL[cL + 1]), dpc_rightdi(gR[cR + 1], gR[cR]), p.cdna_direction, p.reward, finalp);
-    br.rL = rL; br.cL = cL; br.rR = rR; br.cR = cR;
-    if (introns) {                                                      /* 3694-3695 */
-      br.finalscore = best.score;
-      br.introntype = 0;
-    } else if (probmode) {                                                     /* 4055-4080: -1 on both sides */
-      int sL = dpc_nscore(mL, rL, cL) + (lknown && lknown[cL] ? 20 : 0) - (dpc_dirN(mL, rL, cL) > 0 ? 1 : 0);
-      int sR = dpc_nscore(mR, rR, cR) + (rknown && rknown[cR] ? 20 : 0) - (dpc_dirN(mR, rR, cR) > 0 ? 1 : 0);
-      br.finalscore = halfp ? sL + sI + sR - sI / 2 : sL + sI + sR;
-      br.introntype = -1;                                               /* *introntype left untouched, 4071 */
-    } else {
-      br.finalscore = halfp ? best.score - sI / 2 : best.score;        /* 3823-3827 */
-      br.introntype = it;
-    }
-  }
+  dpc_bridge_finish(br, best, bestprob, probkey, mL, mR, p, lknown, rknown, introns, ln);
 }
 
 /* bridge_cdna_gap, 3066-3146: rows = genome, the gap is in the cDNA. */
@@ -623,6 +645,7 @@ DPC_HD void dpc_bridge_cdna(Bridge &br, const Mat &mL, const Mat &mR, const DevP
 struct MatDims { int rows, cols, lband, rband, W, wstride, planes, cpl; };
 struct ArenaLayout {
   int nmat;
+  int fused;                             /* genome gap whose bridge runs inside the R sweep (no stored R band) */
   MatDims d[2];
   /* two regions: `small` (characters, profiles, bridge tables: read on the fill's critical path, always in shared
    * memory when the problem runs in the shared-memory class) and `bulk` (direction bits, nogap bands, op strings,
@@ -652,13 +675,20 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
     d.planes = fillmode == 2 && d.W <= 32 * DPC_MAX_CPL;
     if (fillmode == 2 && !d.planes) need_state = 1;
     if (d.rows > maxrows) maxrows = d.rows;
+  }
+  /* genome gap, the common case (bands of at most 32 diagonals, integer mode, no known sites): the intron bridge
+     runs inside the sweep of the R matrix against the stored band of L, so R's band is never stored */
+  a.fused = p.kind == 1 && a.d[0].planes && a.d[1].planes && a.d[0].cpl == 1 && a.d[1].cpl == 1 &&
+            !(p.flags & (DPC_F_PROBMODE | DPC_F_KNOWN | DPC_F_INTRONS));
+  for (int i = 0; i < a.nmat; i++) {
+    const MatDims &d = a.d[i];
     a.rowch[i] = so; so = dpc_al(so + (uint32_t)d.rows + 2, 4);
     a.colch[i] = so; so = dpc_al(so + (uint32_t)d.cols + 2, 4);
     a.di[i] = so;
     if (p.kind == 1) so = dpc_al(so + (uint32_t)d.cols + 2, 4);         /* dinucleotide code per column (intron bridge) */
     a.dir[i] = bo;
     if (d.planes) bo += (uint32_t)d.rows * (uint32_t)d.cpl * 16; else bo += (uint32_t)d.rows * (uint32_t)d.wstride * 4;
-    if (a.nmat == 2) { a.nband[i] = bo; bo = dpc_al(bo + (uint32_t)d.rows * (uint32_t)d.W * 2, 16); } else a.nband[i] = 0;
+    if (a.nmat == 2 && !(a.fused && i == 1)) { a.nband[i] = bo; bo = dpc_al(bo + (uint32_t)d.rows * (uint32_t)d.W * 2, 16); } else a.nband[i] = 0;
     a.ops[i] = bo; bo = dpc_al(bo + 2 * (uint32_t)(d.rows + d.cols + 2), 16);
   }
   a.state = bo;
@@ -677,7 +707,7 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *small, ui
   m.rowch = small + a.rowch[i]; m.colch = small + a.colch[i];
   m.planes = d.planes; m.cpl = d.cpl; m.cplsh = d.cpl == 1 ? 0 : d.cpl == 2 ? 1 : 2;
   m.dir = (uint32_t *)(bulk + a.dir[i]);
-  m.nband = a.nmat == 2 ? (int16_t *)(bulk + a.nband[i]) : (int16_t *)0;
+  m.nband = (a.nmat == 2 && !(a.fused && i == 1)) ? (int16_t *)(bulk + a.nband[i]) : (int16_t *)0;
 }
 
 /* ---- one problem ------------------------------------------------------------------------------ */
@@ -823,10 +853,19 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       }
       DPC_SYNC();
       EndSearch es; es.mode = 0; es.eb = 0; es.best.score = 0; es.best.key = 0;
-      fill.pair(m0, m1, st, score, es, ln);
       Bridge br;
       int ok;
-      if (!cdna) {
+      if (!cdna && a.fused) {
+        /* both sweeps and the bridge in one pass (no stored R band) */
+        uint8_t *ldi = arena + a.di[0], *rdi = arena + a.di[1];
+        int8_t *itab = (int8_t *)(arena + a.itab);
+        dpc_bridge_tables(m0, m1, p, ldi, rdi, itab, ln);
+        Best best; best.score = DPC_BRIDGE_FLOOR; best.key = 0x7fffffff;
+        fill.pair_bridge(m0, m1, score, p, ldi, rdi, itab, best, ln);
+        dpc_bridge_finish(br, best, 0.0, 0x7fffffff, m0, m1, p, (const uint8_t *)0, (const uint8_t *)0, (const uint8_t *)0, ln);
+        ok = br.have && br.finalscore >= 0;                               /* 4083-4101 */
+      } else if (!cdna) {
+        fill.pair(m0, m1, st, score, es, ln);
         const uint8_t *aux = pool + p.aux, *lknown = 0, *rknown = 0;
         const double *lp = 0, *rp = 0;
         const uint8_t *introns = 0;
@@ -837,6 +876,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         ok = br.have && br.finalscore >= 0;                               /* 4083-4101 */
         if (ok && !(p.flags & (DPC_F_NOVEL | DPC_F_INTRONS)) && (p.flags & DPC_F_KNOWN) && (!lknown[br.cL] || !rknown[br.cR])) ok = 0;
       } else {
+        fill.pair(m0, m1, st, score, es, ln);
         dpc_bridge_cdna(br, m0, m1, p, ln);
         ok = br.have;
       }
@@ -873,6 +913,8 @@ struct GenericFill {
     dpc_fill_generic(mA, st, score, es, ln);
     dpc_fill_generic(mB, st, score, es, ln);
   }
+  DPC_HDM void pair_bridge(const Mat &, const Mat &, const int8_t *, const DevProb &, const uint8_t *, const uint8_t *, const int8_t *,
+                           Best &, const Lanes &) const {}      /* never asked for: fused layouts need the row sweep */
   DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {
     return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);
   }

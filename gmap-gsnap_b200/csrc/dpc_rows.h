@@ -51,6 +51,7 @@ template <int CPL> struct RowState {
   vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL];
   vec::VM kok[CPL], ebok[CPL];
   vec::VI bs, bk;
+  uint32_t b0;                    /* plane 0 (the nogap state did not come from nogap) of the row just swept, first diagonal set */
   int rowq;                       /* score-table row of the NEXT matrix row's character (loaded one row ahead) */
 };
 
@@ -150,6 +151,7 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
     /* directions: four ballots, one 16-byte store */
     const uint32_t b0 = vballot(p1[j]), b1 = vballot(p2[j]), b2 = vballot(h), b3 = vballot(pv[j]);
     store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
+    if (j == 0) s.b0 = b0;
     if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), s.kok[j]);
     if (EP) {
       const VI x = s.cm1[j] + r;
@@ -212,6 +214,73 @@ DPC_VFN void dpc_fill_rows2(const Mat &mA, const Mat &mB, const int8_t *score, E
   for (int r = 1; r <= mA.L1; r++) {
     dpc_rows_step<CPL, LATE, false, true, QROWS>(a, mA, score, r);
     dpc_rows_step<CPL, !LATE, false, true, QROWS>(b, mB, score, r);
+  }
+  vec::sync();
+}
+
+/* Genome gap, common case (ArenaLayout::fused): L is swept first and keeps its nogap band; then R is swept and the
+ * intron bridge (bridge_intron_gap, default mode, dynprog.c:3698-3827) is evaluated row by row inside that sweep --
+ * row rR of R against row rL = length1 - rR of the stored L band -- so R's band never exists in memory and the bridge
+ * has no pass of its own.  Lane = diagonal on both sides: one left-scan and one right-scan candidate per lane and
+ * row pair.  The reference walks rL upwards and keeps the first best; here rL comes downwards, so every candidate
+ * carries its scan-order key rL * 8192 + position and ties go to the smaller key.  mL runs with LATE, mR with !LATE. */
+template <bool LATE>
+DPC_VFN void dpc_fill_rows_bridge(const Mat &mL, const Mat &mR, const int8_t *score, const DevProb &p,
+                                  const uint8_t *ldi, const uint8_t *rdi, const int8_t *itab, Best &best) {
+  using namespace vec;
+  EndSearch none; none.mode = 0; none.eb = 0; none.best.score = 0; none.best.key = 0;
+  dpc_fill_rows<1, LATE, false, true, true>(mL, score, none);
+  RowState<1> s;
+  dpc_rows_init<1, true>(s, mR, none);
+  const int L1 = mL.L1, L2L = mL.L2, L2R = mR.L2, eb = p.extraband, gap = p.gap;
+  const int rbandL = L2L - L1 + eb, lbandL = eb, lbandR = eb;      /* 3545-3549 */
+  const VI lane = lane_index();
+  const VI kL = vmin(lane, mL.W - 1);
+  /* lanes that own a diagonal of the band: c <= r + rband, and c >= r - lband holds for every lane */
+  const VM inL = lane < mL.W, inR = lane < mR.W;
+  /* Per lane the candidates come in DESCENDING scan order -- rL downwards, right scan before left scan -- so "the
+     first best in scan order" is "the last one that is at least as good": one >= per candidate, no key compare.
+     A lane remembers where its best came from as rL * 2 + (1 for the right scan); the scan-order key is made
+     from that once, at the end. */
+  VI bs = splat(best.score), bw = splat(-1);
+  for (int rR = 1; rR < L1; rR++) {            /* row length1 of either matrix is never looked at (3700, 5013) */
+    const int rL = L1 - rR;
+    /* the stored row of L first, so that its latency hides behind the sweep of R's row */
+    const int16_t *rowL = mL.nband + (rL - 1) * mL.W;
+    const VI vL = load_i16(rowL, kL);
+    const int dL = rowL[mL.lband];                                /* (rL, rL) */
+    const uint32_t hL = mL.dir[(rL - 1) * 4];
+    const int diR = rdi[rR], diL = ldi[rL];
+    dpc_rows_step<1, !LATE, false, false, true>(s, mR, score, rR);
+    const VI vR = vmax(s.Np[0], -32768);
+    const int dR = extract(vR, mR.lband);                         /* (rR, rR) */
+    const uint32_t hR = s.b0;
+    const VI cL = lane + (rL - mL.lband), cR = lane + (rR - mR.lband);
+    /* 1 <= c <= length2 - 1 and c < rightoffset - leftoffset - (the other side's column): one unsigned compare */
+    const int upL = (L2L - 1 < gap - rR - 1 ? L2L - 1 : gap - rR - 1), upR = (L2R - 1 < gap - rL - 1 ? L2R - 1 : gap - rL - 1);
+    {   /* right scan (3768-3816): cR over the band of row rR, cL = rL; -1 when R's cell was entered through a gap */
+      const VM ok = vand(inR, vlt_u(cR - 1, upR < 0 ? 0 : upR));
+      const VI di = load_u8(rdi, vsel(ok, cR, 0)) & diL;
+      const VI sc = vR - ((splat((int)hR) >> lane) & 1) + load_i8(itab, di) + dL;
+      const VM take = vand(ok, sc >= bs);
+      bs = vsel(take, sc, bs); bw = vsel(take, rL * 2 + 1, bw);
+    }
+    {   /* left scan (3700-3766): cL over the band of row rL, cR = rR */
+      const VM ok = vand(inL, vlt_u(cL - 1, upL < 0 ? 0 : upL));
+      const VI di = load_u8(ldi, vsel(ok, cL, 0)) & diR;
+      const VI sc = vL - ((splat((int)hL) >> lane) & 1) + load_i8(itab, di) + dR;
+      const VM take = vand(ok, sc >= bs);
+      bs = vsel(take, sc, bs); bw = vsel(take, rL * 2, bw);
+    }
+  }
+  {
+    /* the key of each lane's best: rL * 8192 + position in the row pair's scan (left scan first) */
+    const VI rL = bw >> 1, rR = L1 - rL;
+    const VI cloL = vmax(rL - lbandL, 1), chighL = vmin(rL + rbandL, L2L - 1), cloR = vmax(rR - lbandR, 1);
+    const VI nL = vmax(chighL - cloL + 1, 0);
+    const VI cL = lane + (rL - mL.lband), cR = lane + (rR - mR.lband);
+    const VI key = vsel((bw & 1) != 0, rL * 8192 + nL + (cR - cloR), rL * 8192 + (cL - cloL));
+    reduce_better(bs, vsel(bw < 0, best.key, key), 0, &best.score, &best.key);
   }
   vec::sync();
 }
@@ -331,6 +400,15 @@ struct RowFillT {
     }
     (*this)(mA, st, score, es, ln);
     (*this)(mB, st, score, es, ln);
+  }
+  /* genome gap with ArenaLayout::fused: both sweeps and the intron bridge; leaves the winning candidate in `best` */
+  DPC_HDM void pair_bridge(const Mat &mL, const Mat &mR, const int8_t *score, const DevProb &p,
+                           const uint8_t *ldi, const uint8_t *rdi, const int8_t *itab, Best &best, const Lanes &ln) const {
+    (void)ln;
+    if (KG == 1 || KG == -1) {
+      if (mL.late) dpc_fill_rows_bridge<true>(mL, mR, score, p, ldi, rdi, itab, best);
+      else dpc_fill_rows_bridge<false>(mL, mR, score, p, ldi, rdi, itab, best);
+    }
   }
   DPC_HDM int walk(const Mat &m, int r, int c, int revp, int cdna_direction, uint16_t *ops, const Lanes &ln) const {
     if (MAXCPL > 2 && !m.planes) return dpc_walk_serial(m, r, c, revp, cdna_direction, ops, ln);

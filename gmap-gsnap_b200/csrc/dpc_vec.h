@@ -44,6 +44,7 @@ DPC_V uint32_t vballot(VM m) { return __ballot_sync(0xffffffffu, m); }
 DPC_V VI load_u8(const uint8_t *base, VI idx) { return base[idx]; }
 DPC_V VI load_i8(const int8_t *base, VI idx) { return base[idx]; }
 DPC_V VI load_u32(const uint32_t *base, VI idx) { return (int)base[idx]; }
+DPC_V VI load_i16(const int16_t *base, VI idx) { return base[idx]; }
 DPC_V void store_i32(int32_t *base, VI idx, VI val, VM m) { if (m) base[idx] = val; }
 DPC_V void store_i16(int16_t *base, VI idx, VI val, VM m) { if (m) base[idx] = (int16_t)val; }
 /* lane 0 stores four consecutive words */
@@ -118,6 +119,7 @@ DPC_V uint32_t vballot(const VM &m) { uint32_t b = 0; DPC_VLOOP if (m.v[l]) b |=
 DPC_V VI load_u8(const uint8_t *base, const VI &idx) { VI r; DPC_VLOOP r.v[l] = base[idx.v[l]]; return r; }
 DPC_V VI load_i8(const int8_t *base, const VI &idx) { VI r; DPC_VLOOP r.v[l] = base[idx.v[l]]; return r; }
 DPC_V VI load_u32(const uint32_t *base, const VI &idx) { VI r; DPC_VLOOP r.v[l] = (int)base[idx.v[l]]; return r; }
+DPC_V VI load_i16(const int16_t *base, const VI &idx) { VI r; DPC_VLOOP r.v[l] = base[idx.v[l]]; return r; }
 DPC_V void store_i32(int32_t *base, const VI &idx, const VI &val, const VM &m) { DPC_VLOOP if (m.v[l]) base[idx.v[l]] = val.v[l]; }
 DPC_V void store_i16(int16_t *base, const VI &idx, const VI &val, const VM &m) { DPC_VLOOP if (m.v[l]) base[idx.v[l]] = (int16_t)val.v[l]; }
 DPC_V void store4_lane0(uint32_t *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d; }

@@ -50,6 +50,9 @@ struct KernelArgs {
 #ifndef DPC_MIN_BLOCKS_NARROW
 #define DPC_MIN_BLOCKS_NARROW 4
 #endif
+#ifndef DPC_MIN_BLOCKS_GENOME
+#define DPC_MIN_BLOCKS_GENOME 3
+#endif
 /* Launch variants (one kernel instantiation each, so that each carries only its own code and address spaces):
  *   V_NARROW  arenas in shared memory, bulk region in the arena, bands of at most 64 diagonals (RowFillT<2>)
  *   V_WIDE    arenas in shared memory, bulk region in the arena, any band
@@ -59,7 +62,7 @@ struct KernelArgs {
  * (test hook; not instantiated for V_NARROW). */
 enum { V_NARROW = 0, V_WIDE = 1, V_SPILL = 2, V_HBM = 3, NVARIANT = 4 };
 template <int V, int KG, bool GEN>
-__global__ void __launch_bounds__(256, (KG == 0 ? (V == V_NARROW ? DPC_MIN_BLOCKS_NARROW : DPC_MIN_BLOCKS_1M) : 2)) dpc_solve_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(256, (KG == 0 ? (V == V_NARROW ? DPC_MIN_BLOCKS_NARROW : DPC_MIN_BLOCKS_1M) : (KG == 1 && (V == V_NARROW || V == V_SPILL) ? DPC_MIN_BLOCKS_GENOME : 2))) dpc_solve_kernel(const KernelArgs a) {
   constexpr bool SMEM = V != V_HBM;
   constexpr int BULK = (V == V_NARROW || V == V_WIDE) ? 1 : 0;
   extern __shared__ __align__(16) uint8_t smem[];
