@@ -736,8 +736,8 @@ DPC_HD void dpc_emit_ops(DevRes *res, const uint16_t *opsL, int nL, const uint16
 
 /* Solves problem `p` with the fill routine `FILL` (generic here; the CUDA build also has the
  * register/shuffle fill for narrow bands).  `arena` must hold dpc_layout(p).total bytes. */
-/* KG selects what is compiled in: 0 the one-matrix solvers (single gap, end gaps), 1 genome gap, 2 cDNA gap,
- * -1 everything (the CPU simulation).  The CUDA build instantiates one kernel per group so that each carries only
+/* KG selects what is compiled in: 0 single gap, 1 genome gap, 2 cDNA gap, 3 end gaps (and the splice-junction
+ * solvers, which run as end gaps), -1 everything (the CPU simulation).  The CUDA build instantiates one kernel per group so that each carries only
  * its own code and register needs. */
 /* BULK says where the bulk region lives: 1 in the warp's arena right after the small region, 0 in the problem's HBM
  * scratch, -1 decided per problem (the CPU simulation).  The CUDA build makes it a launch property, so that every
@@ -758,7 +758,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
   const int8_t *score = &tb->score[p.type][0][0];
   const uint16_t *opsL = 0, *opsR = 0;
 
-  if ((KG == 0 || KG == -1) && (p.kind == 3 || p.kind == 4) && p.endalign == 2) {
+  if ((KG == 3 || KG == -1) && (p.kind == 3 || p.kind == 4) && p.endalign == 2) {
     /* QUERYEND_NOGAPS: find_best_endpoint_to_queryend_nogaps 2358-2369 + traceback_nogaps 2815-2872 */
     int n = p.L1 < p.L2 ? p.L1 : p.L2, nm = 0, nmm = 0, star = 0, five = p.kind == 3;
     for (int i = ln.lane; i < n; i += ln.n) {
@@ -788,9 +788,10 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
     Mat m0, m1;
     uint8_t *bulk = BULK == 1 ? arena + a.small : BULK == 0 ? scratch : (a.total <= arena_bytes ? arena + a.small : scratch);
     int32_t *st = (int32_t *)(bulk + a.state);
-    if (KG == 0 || (KG == -1 && (p.kind == 0 || p.kind == 3 || p.kind == 4))) {
+    if (KG == 0 || KG == 3 || (KG == -1 && (p.kind == 0 || p.kind == 3 || p.kind == 4))) {
       /* Dynprog_single_gap 4450-4572, Dynprog_end5_gap 5094-5284, Dynprog_end3_gap 5556-5741 */
-      const int five = p.kind == 3;
+      const int kind = KG == 0 ? 0 : p.kind;              /* the single-gap kernel carries no end-gap code */
+      const int five = kind == 3;
       dpc_make_mat(m0, a, 0, arena, bulk, p, five ? !late : late, 1);
       for (int i = ln.lane; i < p.L1; i += ln.n) {
         int q = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
@@ -809,7 +810,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       if (ln.lane == 0) m0.colch[p.L2] = 7;                               /* sentinel one past the last column */
       DPC_SYNC();
       EndSearch es; es.eb = p.extraband;
-      if (p.kind == 0) { es.mode = 3; es.best.score = -2147483647; es.best.key = 0; }
+      if (kind == 0) { es.mode = 3; es.best.score = -2147483647; es.best.key = 0; }
       else if (p.endalign == 1) { es.mode = 2; es.best.score = DPC_NEG; es.best.key = p.L1 * (p.L2 + 1); }
       else { es.mode = 1; es.best.score = 0; es.best.key = 0; }
       fill(m0, st, score, es, ln);                                      /* leaves es.best reduced over the lanes */

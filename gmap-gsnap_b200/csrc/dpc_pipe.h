@@ -34,7 +34,7 @@ struct PrepEnv {
 };
 
 struct PrepOut {
-  int cls;                         /* launch class * 3 + kind group */
+  int cls;                         /* launch class * DPC_NKG + kind group */
   int bucket;                      /* work bucket inside the class, 0 = most work */
   uint64_t scratch;                /* HBM scratch bytes */
   uint32_t gout;                   /* bytes of the staged genome characters */
@@ -42,6 +42,8 @@ struct PrepOut {
 };
 
 #define DPC_NBUCKET 64
+#define DPC_NKG 4                  /* kind groups = kernel instantiations: single gap, genome gap, cDNA gap, end gaps */
+DPC_HB int dpc_kind_group(int kind) { return kind == DPC_GENOME_GAP ? 1 : kind == DPC_CDNA_GAP ? 2 : kind == DPC_SINGLE_GAP ? 0 : 3; }
 #define DPC_PREP_HOST 0
 #define DPC_PREP_DEVICE 1
 
@@ -83,8 +85,7 @@ DPC_HB void dpc_classify(const DevProb &d, int fillmode, const uint32_t *class_b
     if (wb > DPC_NBUCKET - 1) wb = DPC_NBUCKET - 1;
     bucket = DPC_NBUCKET - 1 - wb;
   }
-  const int kg = d.kind == DPC_GENOME_GAP ? 1 : d.kind == DPC_CDNA_GAP ? 2 : 0;
-  o.cls = k * 3 + kg;
+  o.cls = k * DPC_NKG + dpc_kind_group(d.kind);
   o.bucket = bucket;
 }
 

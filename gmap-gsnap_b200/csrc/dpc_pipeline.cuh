@@ -17,11 +17,11 @@
 
 #include "dpc_pipe.h"
 
-#define PIPE_NBIN (NCLASS * 3 * DPC_NBUCKET)
+#define PIPE_NBIN (NCLASS * DPC_NKG * DPC_NBUCKET)
 struct PipeCounters {
   unsigned int bin[PIPE_NBIN];            /* histogram of (class, kind group, bucket) */
-  unsigned int class_count[NCLASS * 3], class_off[NCLASS * 3];
-  unsigned int work[NCLASS * 3];          /* work-claim counters of the solve launches */
+  unsigned int class_count[NCLASS * DPC_NKG], class_off[NCLASS * DPC_NKG];
+  unsigned int work[NCLASS * DPC_NKG];          /* work-claim counters of the solve launches */
   unsigned long long scratch_total, ovf_total;
   long long pair_total;
   unsigned int gout_total, npatch, ovf_used, ndevice;
@@ -73,11 +73,11 @@ __global__ void __launch_bounds__(256) dpc_prepare_kernel(const dpc_problem_t *h
 /* single block: bin offsets, class extents, scatter into the launch lists */
 __global__ void __launch_bounds__(1024) dpc_sort_kernel(const uint32_t *bin_of, int n, uint32_t *list, PipeCounters *pc) {
   __shared__ unsigned int cur[PIPE_NBIN];
-  __shared__ unsigned int ctot[NCLASS * 3];
+  __shared__ unsigned int ctot[NCLASS * DPC_NKG];
   /* per class: exclusive scan of its buckets (one thread per class; 64 buckets each), then the class offsets */
   for (int b = threadIdx.x; b < PIPE_NBIN; b += blockDim.x) cur[b] = pc->bin[b];
   __syncthreads();
-  if (threadIdx.x < NCLASS * 3) {
+  if (threadIdx.x < NCLASS * DPC_NKG) {
     unsigned int at = 0;
     for (int q = 0; q < DPC_NBUCKET; q++) { const unsigned int v = cur[threadIdx.x * DPC_NBUCKET + q]; cur[threadIdx.x * DPC_NBUCKET + q] = at; at += v; }
     ctot[threadIdx.x] = at;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(1024) dpc_sort_kernel(const uint32_t *bin_of, 
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int at = 0;
-    for (int k = 0; k < NCLASS * 3; k++) { pc->class_off[k] = at; pc->class_count[k] = ctot[k]; const unsigned int v = ctot[k]; ctot[k] = at; at += v; }
+    for (int k = 0; k < NCLASS * DPC_NKG; k++) { pc->class_off[k] = at; pc->class_count[k] = ctot[k]; const unsigned int v = ctot[k]; ctot[k] = at; at += v; }
     pc->ndevice = at;
   }
   __syncthreads();
@@ -249,7 +249,7 @@ static double pipe_now() {
 
 /* blocks of a solve launch (cached: the occupancy query is a driver call) */
 static int solve_grid(const DeviceState &dv, int variant, int kg, bool gen, size_t smem, int nproblems) {
-  static std::atomic<int> cache[MAXDEV][NVARIANT][3][2][NCLASS];
+  static std::atomic<int> cache[MAXDEV][NVARIANT][DPC_NKG][2][NCLASS];
   int cls = 0;
   for (int k = 0; k < NCLASS; k++) if ((size_t)8 * k_class_bytes[k] == smem && k_class_variant[k] == variant) cls = k;
   const int dev = (int)(&dv - g_dev);
@@ -352,17 +352,18 @@ static int pipe_stage2(Pipe &pp, int n, int fill_gen) {
   if ((rc = pp.d_scratch.need((size_t)pc.scratch_total + 16)) || (rc = pp.d_gout.need((size_t)pc.gout_total + 64)) ||
       (rc = pp.d_ovf.need(ovf_cap)))
     return rc;
-  for (int k = 0; k < NCLASS * 3; k++) {
+  for (int k = 0; k < NCLASS * DPC_NKG; k++) {
     if (!pc.class_count[k]) continue;
     KernelArgs a;
     a.probs = pp.d_probs.p; a.list = pp.d_list.p + pc.class_off[k]; a.n = (int)pc.class_count[k];
     a.pool = pp.d_q.p; a.blocks = dv.d_blocks; a.tables = dv.d_tables; a.res = pp.d_dres.p;
     a.ovf.ops = pp.d_ovf.p; a.ovf.used = &pp.d_pc.p->ovf_used; a.ovf.cap = (unsigned int)ovf_cap;
-    a.scratch = pp.d_scratch.p; a.gout = pp.d_gout.p; a.arena_bytes = k_class_bytes[k / 3]; a.counter = &pp.d_pc.p->work[k];
-    const int variant = k_class_variant[k / 3];
+    a.scratch = pp.d_scratch.p; a.gout = pp.d_gout.p; a.arena_bytes = k_class_bytes[k / DPC_NKG]; a.counter = &pp.d_pc.p->work[k];
+    a.claim = claim_of(pc.bin + k * DPC_NBUCKET, DPC_NBUCKET);
+    const int variant = k_class_variant[k / DPC_NKG];
     const size_t smem = variant != V_HBM ? (size_t)8 * a.arena_bytes : 0;
-    const int grid = solve_grid(dv, variant, k % 3, fill_gen != 0, smem, a.n);
-    kernel_of(variant, k % 3, fill_gen != 0)<<<grid, 256, smem, pp.stream>>>(a);
+    const int grid = solve_grid(dv, variant, k % DPC_NKG, fill_gen != 0, smem, a.n);
+    kernel_of(variant, k % DPC_NKG, fill_gen != 0, a.claim)<<<grid, 256, smem, pp.stream>>>(a);
     pp.nlaunch++;
   }
   dpc_finish_kernel<<<(n + 255) / 256, 256, 0, pp.stream>>>(pp.d_hp.p, n, pp.d_bin.p, pp.d_probs.p, pp.d_dres.p, pp.d_ovf.p, pp.d_q.p, pp.d_gout.p,

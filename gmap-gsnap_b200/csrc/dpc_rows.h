@@ -154,8 +154,13 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
     if (j == 0) s.b0 = b0;
     if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), s.kok[j]);
     if (EP) {
+      /* find_best_endpoint (2235-2290) scans rows upwards and columns upwards; a lane meets the cells of its
+         diagonals in that order, so "first best" is a strict comparison and, with jump_late_p, "last best" a >=.
+         Ties between lanes are settled by the scan-order key in dpc_rows_finish. */
       const VI x = s.cm1[j] + r;
-      keep_better(s.bs, s.bk, Nn[j], x + (r * (L2 + 1) + 1), vand(vlt_u(x, L2), s.ebok[j]), LATE);
+      const VM take = vand(vand(vlt_u(x, L2), s.ebok[j]), LATE ? (Nn[j] >= s.bs) : (Nn[j] > s.bs));
+      s.bs = vsel(take, Nn[j], s.bs);
+      s.bk = vsel(take, x + (r * (L2 + 1) + 1), s.bk);
     }
     s.Np[j] = Nn[j];
     s.G1p[j] = G1n;
@@ -362,14 +367,14 @@ DPC_VFN int dpc_walk_planes(const Mat &m, int r0, int c0, int revp, int cdna_dir
 template <int MAXCPL, int KG>
 struct RowFillT {
   enum { fillmode = 2, maxcpl = MAXCPL };
-  /* KG (kind group of the kernel: 0 one-matrix solvers, 1 genome gap, 2 cDNA gap, -1 any) prunes the variants a
-     kernel cannot meet, which halves the code of the one-matrix kernels */
+  /* KG (kind group of the kernel: 0 single gap, 1 genome gap, 2 cDNA gap, 3 end gaps, -1 any) prunes the variants a
+     kernel cannot meet: the single-gap kernel carries one loop per (diagonals per lane, jump_late_p) and nothing else */
   template <int CPL, bool LATE>
   DPC_HDM void go(const Mat &m, const int8_t *score, EndSearch &es) const {
     if ((KG == 2 || KG == -1) && !m.query_rows) dpc_fill_rows<CPL, LATE, false, true, false>(m, score, es);          /* cDNA gap */
     else if ((KG == 1 || KG == -1) && m.nband) dpc_fill_rows<CPL, LATE, false, true, true>(m, score, es);            /* genome gap */
     else if (KG == 1 || KG == 2) return;
-    else if (es.mode == 1) dpc_fill_rows<CPL, LATE, true, false, true>(m, score, es);       /* end gap, best end point */
+    else if (KG != 0 && es.mode == 1) dpc_fill_rows<CPL, LATE, true, false, true>(m, score, es);       /* end gap, best end point */
     else dpc_fill_rows<CPL, LATE, false, false, true>(m, score, es);                        /* single gap, end to query end */
   }
   DPC_HDM void operator()(const Mat &m, int32_t *st, const int8_t *score, EndSearch &es, const Lanes &ln) const {

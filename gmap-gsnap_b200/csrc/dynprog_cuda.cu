@@ -22,6 +22,7 @@
 
 #include "dpc_host.h"
 #include "dpc_rows.h"
+#include "dpc_pipe.h"
 
 using namespace dpc;
 
@@ -39,7 +40,16 @@ struct KernelArgs {
   uint8_t *gout;               /* staged genome characters, returned to the host with the results */
   uint32_t arena_bytes;        /* per-warp shared-memory arena (SMEM == true) */
   unsigned int *counter;       /* dynamic work distribution */
+  int claim;                   /* work items per claim: 4 for launches of light problems (end gaps), else 1 */
 };
+/* light = fewer than this many lane-rows per problem on average (an end gap: ~30; a band-30 single gap: ~110) */
+#define DPC_LIGHT_WORK 64
+/* from a class's histogram over the work buckets (bucket b holds problems of about (63 - b) * 8 lane-rows) */
+template <class COUNT> static int claim_of(const COUNT *bucket_count, int nbucket) {
+  uint64_t n = 0, work = 0;
+  for (int b = 0; b < nbucket; b++) { n += (uint64_t)bucket_count[b]; work += (uint64_t)bucket_count[b] * (uint64_t)(nbucket - 1 - b) * 8u; }
+  return (n > 0 && work < (uint64_t)DPC_LIGHT_WORK * n) ? 4 : 1;
+}
 
 /* resident blocks per SM the compiler must leave room for: the one-matrix kernels fit DPC_MIN_BLOCKS_1M x 256
  * threads (3 -> 80 registers); their narrow-band instantiation (1 or 2 diagonals per lane only) is asked for
@@ -58,11 +68,11 @@ struct KernelArgs {
  *   V_WIDE    arenas in shared memory, bulk region in the arena, any band
  *   V_SPILL   small region in shared memory, bulk region (direction planes, nogap bands, ops) in HBM scratch
  *   V_HBM     everything in HBM scratch
- * KG: kind group (0 one-matrix solvers, 1 genome gap, 2 cDNA gap); GEN: every matrix through the memory-state fill
+ * KG: kind group (0 single gap, 1 genome gap, 2 cDNA gap, 3 end gaps); GEN: every matrix through the memory-state fill
  * (test hook; not instantiated for V_NARROW). */
 enum { V_NARROW = 0, V_WIDE = 1, V_SPILL = 2, V_HBM = 3, NVARIANT = 4 };
-template <int V, int KG, bool GEN>
-__global__ void __launch_bounds__(256, (KG == 0 ? (V == V_NARROW ? DPC_MIN_BLOCKS_NARROW : DPC_MIN_BLOCKS_1M) : (KG == 1 && (V == V_NARROW || V == V_SPILL) ? DPC_MIN_BLOCKS_GENOME : 2))) dpc_solve_kernel(const KernelArgs a) {
+template <int V, int KG, bool GEN, int CLAIM>
+__global__ void __launch_bounds__(256, ((KG == 0 || KG == 3) ? (V == V_NARROW ? DPC_MIN_BLOCKS_NARROW : DPC_MIN_BLOCKS_1M) : (KG == 1 && (V == V_NARROW || V == V_SPILL) ? DPC_MIN_BLOCKS_GENOME : 2))) dpc_solve_kernel(const KernelArgs a) {
   constexpr bool SMEM = V != V_HBM;
   constexpr int BULK = (V == V_NARROW || V == V_WIDE) ? 1 : 0;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -75,21 +85,27 @@ __global__ void __launch_bounds__(256, (KG == 0 ? (V == V_NARROW ? DPC_MIN_BLOCK
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   Lanes ln; ln.lane = threadIdx.x & 31; ln.n = 32;
-  /* work items are claimed one ahead, so the next problem's descriptor is already on its way
-     from HBM while the current problem is being solved (the list is ordered by work, not by address) */
+  /* work items are claimed CLAIM at a time and one claim ahead, so neither the atomic nor the next problem's
+     descriptor is waited for (the list is ordered by work, not by address: adjacent items are alike) */
   int nxt = 0;
-  if (ln.lane == 0) nxt = (int)atomicAdd(a.counter, 1u);
+  if (ln.lane == 0) nxt = (int)atomicAdd(a.counter, (unsigned int)CLAIM);
   nxt = __shfl_sync(0xffffffffu, nxt, 0);
   for (;;) {
-    const int i = nxt;
+    const int base = nxt;
+    if (base >= a.n) break;
+    if (ln.lane == 0) nxt = (int)atomicAdd(a.counter, (unsigned int)CLAIM);
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    for (int u = 0; u < CLAIM; u++) {
+    const int i = base + u;
     if (i >= a.n) break;
     const uint32_t pi = a.list[i];
-    if (ln.lane == 0) nxt = (int)atomicAdd(a.counter, 1u);
-    nxt = __shfl_sync(0xffffffffu, nxt, 0);
-    if (nxt < a.n) {
-      const uint32_t pn = a.list[nxt];
-      const char *d = (const char *)&a.probs[pn];
-      if (ln.lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + 64 * ln.lane));
+    {
+      const int j = u + 1 < CLAIM ? i + 1 : nxt;       /* the item after this one */
+      if (j < a.n) {
+        const uint32_t pn = a.list[j];
+        const char *d = (const char *)&a.probs[pn];
+        if (ln.lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + 64 * ln.lane));
+      }
     }
     const DevProb p = a.probs[pi];
     uint8_t *scratch = a.scratch + (((uint64_t)p.scratch_hi << 32) | p.scratch_lo);
@@ -106,25 +122,32 @@ __global__ void __launch_bounds__(256, (KG == 0 ? (V == V_NARROW ? DPC_MIN_BLOCK
       dpc_solve_problem<RowFillT<DPC_MAX_CPL, KG>, KG, BULK>(p, a.pool, a.blocks, &s_tables, arena, arena_bytes, scratch, &a.res[pi], a.ovf, a.gout, fill, ln);
     }
     __syncwarp();
+    }
   }
 }
 
 typedef void (*kernel_fn)(const KernelArgs);
 /* [variant][kind group][generic]; the generic test hook runs the narrow class in the V_WIDE instantiation */
-static kernel_fn kernel_of(int v, int kg, bool gen) {
-  static const kernel_fn tab[NVARIANT][3][2] = {
-    { { dpc_solve_kernel<V_NARROW, 0, false>, dpc_solve_kernel<V_WIDE, 0, true> },
-      { dpc_solve_kernel<V_NARROW, 1, false>, dpc_solve_kernel<V_WIDE, 1, true> },
-      { dpc_solve_kernel<V_NARROW, 2, false>, dpc_solve_kernel<V_WIDE, 2, true> } },
-    { { dpc_solve_kernel<V_WIDE, 0, false>, dpc_solve_kernel<V_WIDE, 0, true> },
-      { dpc_solve_kernel<V_WIDE, 1, false>, dpc_solve_kernel<V_WIDE, 1, true> },
-      { dpc_solve_kernel<V_WIDE, 2, false>, dpc_solve_kernel<V_WIDE, 2, true> } },
-    { { dpc_solve_kernel<V_SPILL, 0, false>, dpc_solve_kernel<V_SPILL, 0, true> },
-      { dpc_solve_kernel<V_SPILL, 1, false>, dpc_solve_kernel<V_SPILL, 1, true> },
-      { dpc_solve_kernel<V_SPILL, 2, false>, dpc_solve_kernel<V_SPILL, 2, true> } },
-    { { dpc_solve_kernel<V_HBM, 0, false>, dpc_solve_kernel<V_HBM, 0, true> },
-      { dpc_solve_kernel<V_HBM, 1, false>, dpc_solve_kernel<V_HBM, 1, true> },
-      { dpc_solve_kernel<V_HBM, 2, false>, dpc_solve_kernel<V_HBM, 2, true> } } };
+static kernel_fn kernel_of(int v, int kg, bool gen, int claim = 1) {
+  /* launches of light one-matrix problems (end gaps) claim four work items at a time */
+  if (v == V_NARROW && kg == 3 && !gen && claim > 1) return dpc_solve_kernel<V_NARROW, 3, false, 4>;
+  static const kernel_fn tab[NVARIANT][DPC_NKG][2] = {
+    { { dpc_solve_kernel<V_NARROW, 0, false, 1>, dpc_solve_kernel<V_WIDE, 0, true, 1> },
+      { dpc_solve_kernel<V_NARROW, 1, false, 1>, dpc_solve_kernel<V_WIDE, 1, true, 1> },
+      { dpc_solve_kernel<V_NARROW, 2, false, 1>, dpc_solve_kernel<V_WIDE, 2, true, 1> },
+      { dpc_solve_kernel<V_NARROW, 3, false, 1>, dpc_solve_kernel<V_WIDE, 3, true, 1> } },
+    { { dpc_solve_kernel<V_WIDE, 0, false, 1>, dpc_solve_kernel<V_WIDE, 0, true, 1> },
+      { dpc_solve_kernel<V_WIDE, 1, false, 1>, dpc_solve_kernel<V_WIDE, 1, true, 1> },
+      { dpc_solve_kernel<V_WIDE, 2, false, 1>, dpc_solve_kernel<V_WIDE, 2, true, 1> },
+      { dpc_solve_kernel<V_WIDE, 3, false, 1>, dpc_solve_kernel<V_WIDE, 3, true, 1> } },
+    { { dpc_solve_kernel<V_SPILL, 0, false, 1>, dpc_solve_kernel<V_SPILL, 0, true, 1> },
+      { dpc_solve_kernel<V_SPILL, 1, false, 1>, dpc_solve_kernel<V_SPILL, 1, true, 1> },
+      { dpc_solve_kernel<V_SPILL, 2, false, 1>, dpc_solve_kernel<V_SPILL, 2, true, 1> },
+      { dpc_solve_kernel<V_SPILL, 3, false, 1>, dpc_solve_kernel<V_SPILL, 3, true, 1> } },
+    { { dpc_solve_kernel<V_HBM, 0, false, 1>, dpc_solve_kernel<V_HBM, 0, true, 1> },
+      { dpc_solve_kernel<V_HBM, 1, false, 1>, dpc_solve_kernel<V_HBM, 1, true, 1> },
+      { dpc_solve_kernel<V_HBM, 2, false, 1>, dpc_solve_kernel<V_HBM, 2, true, 1> },
+      { dpc_solve_kernel<V_HBM, 3, false, 1>, dpc_solve_kernel<V_HBM, 3, true, 1> } } };
   return tab[v][kg][gen ? 1 : 0];
 }
 
@@ -179,10 +202,11 @@ static int ensure_device(int dev) {
   CK(cudaMalloc(&d.d_tables, sizeof(DevTables)));
   CK(cudaMemcpy(d.d_tables, &g.tables, sizeof(DevTables), cudaMemcpyHostToDevice));
   for (int v = 0; v < V_HBM; v++)
-    for (int kg = 0; kg < 3; kg++)
+    for (int kg = 0; kg < DPC_NKG; kg++)
       for (int gen = 0; gen < 2; gen++)
-        CK(cudaFuncSetAttribute((const void *)kernel_of(v, kg, gen != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                d.max_smem - (int)sizeof(DevTables) - 1024));
+        for (int claim = 1; claim <= 4; claim += 3)
+          CK(cudaFuncSetAttribute((const void *)kernel_of(v, kg, gen != 0, claim), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  d.max_smem - (int)sizeof(DevTables) - 1024));
   d.version = g_version;
   d.ready = true;
   return DPC_OK;
@@ -218,6 +242,7 @@ struct ClassLaunch {
   int wpb;
   size_t list_off;
   int n;
+  int claim;
 };
 
 /* Launch classes.  Two shared-memory arena sizes: 6 KB per warp leaves most of the 228 KB to L1 (descriptors,
@@ -309,10 +334,11 @@ struct Engine {
       a.pool = d_pool.p; a.blocks = d.d_blocks; a.tables = d.d_tables; a.res = d_res.p;
       a.ovf.ops = d_ovf.p; a.ovf.used = d_counters.p; a.ovf.cap = (unsigned int)ovf_cap;
       a.scratch = d_scratch.p; a.gout = d_gout.p; a.arena_bytes = L.arena_bytes; a.counter = d_counters.p + 1 + k;
+      a.claim = L.claim;
       const int threads = L.wpb * 32;
       const size_t smem = L.variant != V_HBM ? (size_t)L.wpb * L.arena_bytes : 0;
       int per_sm = 1;
-      const kernel_fn fn = kernel_of(L.variant, L.kg, fill_gen != 0);
+      const kernel_fn fn = kernel_of(L.variant, L.kg, fill_gen != 0, L.claim);
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, threads, smem));
       if (per_sm < 1) per_sm = 1;
       int grid = (L.n + L.wpb - 1) / L.wpb;
@@ -349,7 +375,7 @@ struct Engine {
     /* class (shared-memory arena or HBM only) and a work bucket per problem: within a class the list is ordered
        by descending work so that the long problems start first and the tail of the launch is made of short ones */
     cls.resize(n);
-    size_t count[NCLASS * 3 * NBUCKET] = { 0 };
+    size_t count[NCLASS * DPC_NKG * NBUCKET] = { 0 };
     uint64_t scratch_total = 0, ovf_worst = 0;
     for (size_t i = 0; i < n; i++) {
       DevProb &p = b.dprobs[i];
@@ -381,29 +407,29 @@ struct Engine {
         static const bool nosort = getenv("DPC_NO_SORT") != NULL;
         if (nosort) bucket = 0;
       }
-      const int kg = p.kind == DPC_GENOME_GAP ? 1 : p.kind == DPC_CDNA_GAP ? 2 : 0;
-      cls[i] = (uint16_t)((k * 3 + kg) * NBUCKET + bucket);
+      cls[i] = (uint16_t)((k * DPC_NKG + dpc_kind_group(p.kind)) * NBUCKET + bucket);
       count[cls[i]]++;
     }
     list.clear();
     list.grow(n);
-    size_t off[NCLASS * 3 * NBUCKET], at = 0;
-    for (int k = 0; k < NCLASS * 3 * NBUCKET; k++) { off[k] = at; at += count[k]; }
+    size_t off[NCLASS * DPC_NKG * NBUCKET], at = 0;
+    for (int k = 0; k < NCLASS * DPC_NKG * NBUCKET; k++) { off[k] = at; at += count[k]; }
     {
-      size_t cur[NCLASS * 3 * NBUCKET];
-      for (int k = 0; k < NCLASS * 3 * NBUCKET; k++) cur[k] = off[k];
+      size_t cur[NCLASS * DPC_NKG * NBUCKET];
+      for (int k = 0; k < NCLASS * DPC_NKG * NBUCKET; k++) cur[k] = off[k];
       for (size_t i = 0; i < n; i++) list[cur[cls[i]]++] = (uint32_t)i;
     }
-    for (int k = 0; k < NCLASS * 3; k++) {       /* one launch per (arena class, kind group) that has work */
+    for (int k = 0; k < NCLASS * DPC_NKG; k++) {       /* one launch per (arena class, kind group) that has work */
       size_t cnt = 0;
       for (int q = 0; q < NBUCKET; q++) cnt += count[k * NBUCKET + q];
       if (!cnt) continue;
       ClassLaunch L;
-      L.variant = k_class_variant[k / 3];
-      L.kg = k % 3;
-      L.arena_bytes = k_class_bytes[k / 3];
+      L.variant = k_class_variant[k / DPC_NKG];
+      L.kg = k % DPC_NKG;
+      L.arena_bytes = k_class_bytes[k / DPC_NKG];
       L.wpb = 8;
       L.list_off = off[k * NBUCKET]; L.n = (int)cnt;
+      L.claim = claim_of(count + k * NBUCKET, NBUCKET);
       launches.push_back(L);
     }
     /* ops overflow arena: problems whose worst case exceeds the inline slots (bounded) */
@@ -413,13 +439,13 @@ struct Engine {
     b.pool_align(16);
     int rc;
     if ((rc = d_probs.need(n)) || (rc = d_pool.need(b.pool.size())) || (rc = d_res.need(n)) ||
-        (rc = d_list.need(n)) || (rc = d_ovf.need(ovf_cap)) || (rc = d_counters.need(NCLASS * 3 + 2)) ||
+        (rc = d_list.need(n)) || (rc = d_ovf.need(ovf_cap)) || (rc = d_counters.need(NCLASS * DPC_NKG + 2)) ||
         (rc = d_scratch.need((size_t)scratch_total + 16)) || (rc = d_gout.need((size_t)b.gout_total + 64)))
       return rc;
     h_gout.clear(); h_gout.grow((size_t)b.gout_total + 64);
     b.gout_host = NULL;
     h_res.clear(); h_res.grow(n);
-    h_counters.clear(); h_counters.grow(NCLASS * 3 + 2);
+    h_counters.clear(); h_counters.grow(NCLASS * DPC_NKG + 2);
     CK(cudaMemcpyAsync(d_probs.p, b.dprobs.data(), n * sizeof(DevProb), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_pool.p, b.pool.data(), b.pool.size(), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_list.p, list.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
