@@ -417,7 +417,7 @@ struct Bridge { int have, finalscore, rL, cL, rR, cR, introntype; };
 DPC_HD void dpc_bridge_tables(const Mat &mL, const Mat &mR, const DevProb &p, uint8_t *ldi, uint8_t *rdi, int8_t *itab, const Lanes &ln) {
   const int L2L = mL.L2, L2R = mR.L2, finalp = (p.flags & DPC_F_FINALP) != 0;
   const uint8_t *gL = mL.colch, *gR = mR.colch;
-  int it;
+  int it = 0; (void)it;
   for (int c = ln.lane; c < L2L; c += ln.n) ldi[c] = (uint8_t)dpc_leftdi(gL[c], gL[c + 1]);
   for (int c = ln.lane; c < L2R; c += ln.n) rdi[c] = (uint8_t)dpc_rightdi(gR[c + 1], gR[c]);
   for (int t = ln.lane; t < 64; t += ln.n) itab[t] = (int8_t)dpc_intron_score(&it, t, t, p.cdna_direction, p.reward, finalp);
@@ -432,7 +432,7 @@ DPC_HD void dpc_bridge_finish(Bridge &br, Best best, double bestprob, int probke
   const int finalp = (p.flags & DPC_F_FINALP) != 0, halfp = (p.flags & DPC_F_HALFP) != 0;
   const int probmode = (p.flags & DPC_F_PROBMODE) != 0;
   const uint8_t *gL = mL.colch, *gR = mR.colch;
-  int it;
+  int it = 0; (void)it;
   (void)L2R; (void)bestprob;
   if (probmode) {
 #ifdef __CUDACC__
@@ -487,7 +487,7 @@ DPC_HD void dpc_bridge_intron(Bridge &br, const Mat &mL, const Mat &mR, const De
   const uint8_t *gL = mL.colch, *gR = mR.colch;
   Best best; best.score = DPC_BRIDGE_FLOOR; best.key = 0x7fffffff;
   double bestprob = 0.0; int probkey = 0x7fffffff;
-  int it;
+  int it = 0; (void)it;
   dpc_bridge_tables(mL, mR, p, ldi, rdi, itab, ln);
   const bool fast = mL.planes && mR.planes && mL.cpl == 1 && mR.cpl == 1 && !lknown && !rknown && !probmode;
   if (introns) {

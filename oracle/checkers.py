@@ -45,7 +45,7 @@ class PortOracle(_Checker):
     """oracle/liboracle_port.so -- TEST INFRASTRUCTURE (CPU restatement)."""
 
     def __init__(self, path=None):
-        super().__init__(path or os.path.join(ROOT, "oracle", "liboracle_port.so"))
+        super().__init__(path or os.environ.get("DPC_PORT_LIB") or os.path.join(ROOT, "oracle", "liboracle_port.so"))
         L = self.lib
         L.port_init.argtypes = [C.c_int] * 6
         L.port_setup.argtypes = [C.POINTER(Setup)]
@@ -99,7 +99,7 @@ class EmulLib(_Checker):
     """tests/emul/libdpc_emul.so -- TEST SCAFFOLDING: the device routines compiled single-lane for the CPU."""
 
     def __init__(self, path=None):
-        super().__init__(path or os.path.join(ROOT, "tests", "emul", "libdpc_emul.so"))
+        super().__init__(path or os.environ.get("DPC_EMUL_LIB") or os.path.join(ROOT, "tests", "emul", "libdpc_emul.so"))
         L = self.lib
         L.emul_init.argtypes = [C.c_int] * 6
         L.emul_setup.argtypes = [C.POINTER(Setup)]

@@ -27,6 +27,27 @@ static int g_no_gout = 0;
 extern "C" int emul_set_fill(int force_generic) { g_force_generic = force_generic & 1; g_no_gout = (force_generic >> 1) & 1; return 0; }
 extern "C" int emul_pairdistance(int type, int c1, int c2) { return dpc::G().P[type & 3][c1 & 127][c2 & 127]; }
 
+/* Arena memory for one problem.  Under AddressSanitizer (tools: profiles/r2_sanitizer_host.log) every block has exactly
+ * the size dpc_layout computed, so that a device routine stepping one byte outside its arena, its HBM scratch or its
+ * staged-genome span is reported; otherwise a vector with slack. */
+struct Block {
+  std::vector<uint8_t> v;
+  void *exact;
+  Block() : exact(NULL) {}
+  ~Block() { free(exact); }
+  uint8_t *get(size_t bytes, int fill) {
+#if defined(__SANITIZE_ADDRESS__)
+    free(exact);
+    if (posix_memalign(&exact, 16, bytes ? bytes : 1) != 0) abort();
+    memset(exact, fill, bytes);
+    return (uint8_t *)exact;
+#else
+    v.assign(bytes + 64, (uint8_t)fill);
+    return v.data() + ((16 - ((uintptr_t)v.data() & 15)) & 15);
+#endif
+  }
+};
+
 static int g_pipe = 0;
 extern "C" int emul_set_path(int pipe) { g_pipe = pipe; return 0; }
 
@@ -61,7 +82,7 @@ static int emul_solve_pipe(const dpc_problem_t *problems, int n, dpc_result_t *r
   OvfArena ovf; ovf.ops = ovfbuf.data(); ovf.used = &used; ovf.cap = (unsigned int)ovfbuf.size();
   Lanes one; one.lane = 0; one.n = 1;
   GenericFill gfill; RowFill rfill;
-  std::vector<uint8_t> arena, gout;
+  Block arena, goutb;
   int64_t out = 0;
   std::vector<dpc_pair_t> st;
   for (int i = 0; i < n; i++) {
@@ -71,18 +92,17 @@ static int emul_solve_pipe(const dpc_problem_t *problems, int n, dpc_result_t *r
     if (rc < 0) { if (getenv("EMUL_DEBUG")) fprintf(stderr, "emul pipe: problem %d kind %d rc %d seq1 %p len %d qbytes %llu\n", i, problems[i].kind, rc, (void *)hp[i].seq1, problems[i].length1, (unsigned long long)env.qbytes); return rc; }
     if (pair_off) pair_off[i] = out;
     if (rc == DPC_PREP_HOST) continue;
-    gout.assign((size_t)o.gout + 64, 0xEE);
-    if (o.gout) d.gout = 8;
+    uint8_t *gout = goutb.get((size_t)o.gout, 0xEE);        /* exactly the span dpc_prepare_one asked for */
+    if (o.gout) d.gout = 0;
     ArenaLayout a;
     dpc_layout(d, a, env.fillmode);
-    arena.assign(a.total + 64, 0xAB);
     memset(&dr, 0, sizeof dr);
-    uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
-    if (g_force_generic) dpc_solve_problem<GenericFill, -1, -1>(d, pool.data(), g.setup.genome_blocks, &g.tables, base, a.total, base, &dr, ovf, gout.data(), gfill, one);
-    else dpc_solve_problem<RowFill, -1, -1>(d, pool.data(), g.setup.genome_blocks, &g.tables, base, a.total, base, &dr, ovf, gout.data(), rfill, one);
+    uint8_t *base = arena.get(a.total, 0xAB);
+    if (g_force_generic) dpc_solve_problem<GenericFill, -1, -1>(d, pool.data(), g.setup.genome_blocks, &g.tables, base, a.total, base, &dr, ovf, gout, gfill, one);
+    else dpc_solve_problem<RowFill, -1, -1>(d, pool.data(), g.setup.genome_blocks, &g.tables, base, a.total, base, &dr, ovf, gout, rfill, one);
     if (dr.status & DPC_ST_OVF_LOST) return DPC_ERR_NOMEM;
     const uint16_t *ops = (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? ovfbuf.data() + dr.ovf : dr.ops;
-    const uint8_t *staged = (i & 2) ? gout.data() : NULL;       /* also exercise the decode-again path */
+    const uint8_t *staged = (i & 2) ? gout : NULL;              /* also exercise the decode-again path */
     if (!staged) d.gout = DPC_NO_GOUT;
     const int np = dpc_expand_one(problems[i], d, dr, ops, pool.data(), staged, g.setup.genome_blocks, &g.tables, NULL, one);
     if (dpc_finish_one(problems[i], dr, np, results[i])) {
@@ -121,19 +141,17 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
   Lanes ln; ln.lane = 0; ln.n = 1;
   GenericFill gfill;     /* single lane: memory-state fill + serial walk */
   RowFill rfill;         /* 32 simulated lanes: row-sweep fill + lane-parallel walk (dpc_vec.h host build) */
-  std::vector<uint8_t> arena;
+  Block arena, scratchb;
   std::vector<uint8_t> gout((size_t)b.gout_total + 64, 0xEE);     /* the staged genome characters the device returns */
   b.pool_align(16);
   for (size_t k = 0; k < b.dprobs.size(); k++) {
     ArenaLayout a;
     dpc_layout(b.dprobs[k], a, g_force_generic ? 1 : 2);
-    arena.assign(a.total + 64, 0xAB);
     memset(&dres[k], 0, sizeof(DevRes));
-    uint8_t *base = arena.data() + ((16 - ((uintptr_t)arena.data() & 15)) & 15);
     /* odd problems keep everything in one arena, even ones put the bulk region in a separate "HBM scratch" */
-    std::vector<uint8_t> scratch(a.bulk + 64, 0xCD);
-    uint8_t *sbase = scratch.data() + ((16 - ((uintptr_t)scratch.data() & 15)) & 15);
     const uint32_t arena_bytes = (k & 1) ? a.total : a.small;
+    uint8_t *base = arena.get(arena_bytes, 0xAB);
+    uint8_t *sbase = scratchb.get(a.bulk, 0xCD);
     if (g_force_generic)
       dpc_solve_problem<GenericFill, -1, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), gfill, ln);
     else
