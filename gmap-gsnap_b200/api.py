@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 DPC_UNSET = -2000000001
-SINGLE_GAP, GENOME_GAP, CDNA_GAP, END5_GAP, END3_GAP, END5_SPLICEJUNCTION, END3_SPLICEJUNCTION = range(7)
+SINGLE_GAP, GENOME_GAP, CDNA_GAP, END5_GAP, END3_GAP, END5_SPLICEJUNCTION, END3_SPLICEJUNCTION, MICROEXON_INT = range(8)
 QUERYEND_GAP, QUERYEND_INDELS, QUERYEND_NOGAPS, BEST_LOCAL = range(4)
 KIND_NAMES = ["single_gap", "genome_gap", "cdna_gap", "end5_gap", "end3_gap"]
 
@@ -267,6 +267,85 @@ class Workload:
             pr["watsonp"], pr["jump_late_p"], pr["widebandp"], pr["splicingp"] = int(rng.integers(0, 2)), int(rng.integers(0, 2)), 1, 1
             pr["defect_rate"] = float(rng.choice([0.0, 0.01, 0.05]))
         self._keep.append(qbuf)
+        return probs
+
+    def _set_base(self, pos, ch):
+        """Writes one base (A C G T) into the 3-word genome blocks (high, low, flags per 32 nt, genome.c:9325)."""
+        code = "ACGT".index(ch)
+        w, bit = 3 * (pos >> 5), pos & 31
+        if bit < 16:
+            self.blocks[w + 1] = (int(self.blocks[w + 1]) & ~(3 << (2 * bit))) | (code << (2 * bit))
+        else:
+            self.blocks[w] = (int(self.blocks[w]) & ~(3 << (2 * bit - 32))) | (code << (2 * bit - 32))
+        self.blocks[w + 2] = int(self.blocks[w + 2]) & ~(1 << bit)
+
+    def microexon_problems(self, n, seed=91, span_hi=4000):
+        """Problems for Dynprog_microexon_int (dynprog.c:7127-7429): a query piece = left exon end + microexon + right
+        exon start, against a genomic segment where the three parts are separated by two introns (GT..AG, or CT..AC
+        for the antisense direction).  Most problems get the microexon planted (some with a mismatch in a flank, some
+        with a decoy copy of the middle piece without splice sites); the rest have none.  Plants into the genome:
+        register it again afterwards (the `version` counter tells CudaLib.refresh_genome).  Pure numpy; test workloads."""
+        rng = np.random.default_rng(seed)
+        probs = np.zeros(n, dtype=PROBLEM_DT)
+        qbuf = np.zeros(n * 64 + 4096, dtype=np.uint8)
+        base, at = qbuf.ctypes.data, 0
+        chrlen = self.nbases // self.nchr
+        comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+        for i in range(n):
+            chrn = int(rng.integers(0, self.nchr))
+            glen = int(rng.integers(30000, 60000))
+            chrpos = int(rng.integers(0, chrlen - glen))
+            watson = bool(rng.integers(0, 2))
+            cdna = 1 if rng.random() < 0.5 else -1
+            chroffset = chrn * chrlen
+            a, mid, b = int(rng.integers(4, 16)), int(rng.integers(3, 13)), int(rng.integers(4, 16))
+            span = int(rng.integers(120, span_hi))
+            lo = int(rng.integers(200, glen - span - 200))
+            ro = lo + span
+            i1len = int(rng.integers(20, span - a - b - mid - 30))
+            m0 = lo + a + i1len
+            r0 = ro - b + 1
+
+            def put(s, text):
+                for k, ch in enumerate(text):
+                    gpos = chroffset + chrpos + (s + k if watson else glen - 1 - (s + k))
+                    self._set_base(gpos, ch if watson else comp[ch])
+
+            q = "".join("ACGT"[x] for x in rng.integers(0, 4, a + mid + b))
+            don, acc = ("GT", "AG") if cdna > 0 else ("CT", "AC")
+            planted = rng.random() < 0.8
+            put(lo, q[:a])
+            put(r0, q[a + mid:])
+            if planted:
+                put(lo + a, don); put(m0 - 2, acc); put(m0, q[a:a + mid]); put(m0 + mid, don); put(r0 - 2, acc)
+                if rng.random() < 0.3 and m0 + mid + 40 < r0 - 20:      # a decoy copy of the middle piece further right
+                    put(m0 + mid + 20, q[a:a + mid])
+            ql = list(q)
+            if rng.random() < 0.15:
+                k = int(rng.integers(0, a)); ql[k] = "ACGT"[("ACGT".index(ql[k]) + 1) % 4]
+            if rng.random() < 0.15:
+                k = a + mid + int(rng.integers(0, b)); ql[k] = "ACGT"[("ACGT".index(ql[k]) + 2) % 4]
+            if rng.random() < 0.1:
+                ql[int(rng.integers(0, len(ql)))] = "N"
+            if rng.random() < 0.1:
+                k = int(rng.integers(0, len(ql))); ql[k] = ql[k].lower()
+            L1 = len(ql)
+            qbuf[at:at + L1] = np.frombuffer("".join(ql).encode(), np.uint8)
+            pr = probs[i]
+            pr["kind"] = MICROEXON_INT
+            pr["seq1"] = base + at
+            at += L1 + 1
+            pr["length1"], pr["length2"], pr["length2R"] = L1, L1 + 8, L1 + 8
+            pr["offset1"], pr["offset2"], pr["offset2R"] = int(rng.integers(20, 3000)), lo, ro
+            pr["chroffset"], pr["chrhigh"], pr["chrpos"], pr["genomiclength"] = chroffset, chroffset + chrlen, chrpos, glen
+            pr["chrnum"] = chrn + 1
+            pr["cdna_direction"] = cdna
+            pr["maxpeelback"] = 11
+            pr["dynprogindex"] = int(rng.integers(1, 50)) * (1 if rng.random() < 0.5 else -1)
+            pr["watsonp"], pr["jump_late_p"], pr["widebandp"], pr["splicingp"] = int(watson), int(not watson), 1, 1
+            pr["defect_rate"] = float(rng.choice([0.0, 0.01, 0.05]))
+        self._keep.append(qbuf)
+        self.version = getattr(self, "version", 0) + 1
         return probs
 
     def make_setup(self, splice_prob=None, splice_known=None, novelsplicingp=1, splice_intron=None, intron_level=0):

@@ -121,6 +121,30 @@ DPC_HB int dpc_query_uc(int c) {                   /* UPPERCASE_U2T, complement.
   return c == 'U' ? 'T' : c;
 }
 
+/* One exact-match scan of Dynprog_microexon_int (dynprog.c:7305-7312: BoyerMoore_nt of the query's middle piece over
+ * the intron, boyer-moore.c:384): does pat[0..len) occur at segment position textleft + j, for j in [0, npos)?
+ * The characters come from the 2-bit genome with the semantics of boyer-moore.c:357-381 (Watson as stored, Crick
+ * complemented from the far end; an N never matches).  Hits go to hits[hits_off ..], their number to count[query]. */
+struct ScanQuery {
+  uint32_t gbase, glen;          /* chroffset + chrpos, genomiclength */
+  int32_t textleft, npos;
+  uint32_t pat;                  /* 2 bits per base, base i at bits 2i.. (at most 16 bases) */
+  uint8_t len, watson, pad[2];
+  uint32_t hits_off;
+};
+DPC_HB bool dpc_scan_match(const ScanQuery &q, const uint32_t *blocks, uint64_t nbases, int j) {
+  for (int i = 0; i < q.len; i++) {
+    const int pos = q.textleft + j + i;
+    const uint64_t g = q.watson ? (uint64_t)q.gbase + (uint32_t)pos : (uint64_t)q.gbase + (q.glen - 1) - (uint32_t)pos;
+    if (g >= nbases) return false;
+    int code = dpc_genome_code(blocks, (uint32_t)g);
+    if (code > 3) return false;
+    if (!q.watson) code ^= 3;
+    if (code != (int)((q.pat >> (2 * i)) & 3u)) return false;
+  }
+  return true;
+}
+
 /* ---- one banded matrix ----------------------------------------------------------------- */
 struct Mat {
   int L1, L2;               /* rows, columns */

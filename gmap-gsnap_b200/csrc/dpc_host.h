@@ -18,6 +18,9 @@
 #include <immintrin.h>
 #define DPC_X86_SIMD 1
 #endif
+#include <math.h>
+#include <algorithm>
+#include <functional>
 #include <new>
 #include <vector>
 #include "../../include/dynprog_cuda.h"
@@ -222,11 +225,20 @@ template <class T> struct PBuf {
 };
 
 /* ---- batch ---------------------------------------------------------------------------------- */
+/* Dynprog_microexon_int (dynprog.c:7127-7429) on the host side of the boundary: everything but the exact-match scans */
+struct MicroCand { int cL, cR, mid, textleft, query; };      /* one (cL, cR) pair with splice-site dinucleotides; query = its scan, or -1 */
+struct MicroProb {
+  int problem;                       /* ticket */
+  std::vector<MicroCand> cands;      /* in the reference's loop order */
+  std::vector<dpc_pair_t> pairs;     /* the returned list, head first (filled by finalize_micro) */
+};
+
 struct HostProb {
   uint32_t q0, q1;      /* pool offsets: first byte of the copied span(s) */
   uint32_t aux;         /* pool offset of probability / known-site arrays */
   int32_t dev;          /* index into the device arrays, -1 when resolved on the host (early returns) */
   int32_t L1, L2;       /* lengths after clipping (end gaps) */
+  int32_t micro;        /* index into Batch::micro (Dynprog_microexon_int), else -1 */
   uint32_t gout;        /* offset of the device-staged genome characters in the returned byte stream, or DPC_NO_GOUT */
 };
 
@@ -334,10 +346,14 @@ struct Batch {
      them instead of decoding the 2-bit genome a second time at an unpredictable address per problem */
   uint32_t gout_total;
   const uint8_t *gout_host;
+  /* microexon searches: their scans run on the device next to the solve kernels */
+  std::vector<MicroProb> micro;
+  PBuf<ScanQuery> scans;
+  uint64_t hits_total;
 
-  Batch() : ext(NULL), ext_res(NULL), gout_total(8), gout_host(NULL) {}
+  Batch() : ext(NULL), ext_res(NULL), gout_total(8), gout_host(NULL), hits_total(0) {}
   void clear() { probs.clear(); pool.clear(); dprobs.clear(); dev2host.clear(); own.clear(); own_res.clear(); ext = NULL; ext_res = NULL;
-                 gout_total = 8; gout_host = NULL; }
+                 gout_total = 8; gout_host = NULL; micro.clear(); scans.clear(); hits_total = 0; }
   const dpc_problem_t &P(int i) const { return ext ? ext[i] : own[i]; }
   dpc_result_t &R(int i) { return ext_res ? ext_res[i] : own_res[i]; }
 
@@ -396,6 +412,127 @@ struct Batch {
     return s.splice_prob(which, p.chroffset + pos, p.chroffset, s.user);
   }
 
+  /* Dynprog_microexon_int up to its scans: p-value -> minimum microexon length (7158-7232), the mismatch-bounded
+     ends (7234-7283), the (cL, cR) pairs with splice-site dinucleotides (7289-7312) and one device scan per pair */
+  static void micro_introns(const dpc_problem_t &p, char *i1, char *i2, char *i3, char *i4, char *gapchar, int *type) {
+    if (p.cdna_direction > 0) { *i1 = 'G'; *i2 = 'T'; *i3 = 'A'; *i4 = 'G'; *gapchar = '>'; *type = 0x20; }     /* GTAG_FWD */
+    else { *i1 = 'C'; *i2 = 'T'; *i3 = 'A'; *i4 = 'C'; *gapchar = '<'; *type = 0x04; }                           /* GTAG_REV */
+  }
+  int add_micro(const dpc_problem_t &p, dpc_result_t &r, HostProb &h) {
+    const Globals &g = G();
+    const int L1 = p.length1, lo = p.offset2, ro = p.offset2R;
+    char i1, i2, i3, i4, gapchar; int type;
+    if (p.cdna_direction == 0 || ro - lo <= 0 || L1 <= 0 || p.seq1 == NULL) return DPC_ERR_ARG;     /* abort(), 7192, 7215 */
+    if (g.setup.splice_prob == NULL) return DPC_ERR_STATE;
+    if (!alphabet_ok(p.seq1, L1)) return DPC_ERR_ALPHABET;
+    if (!allstar(p) && !segment_ok(p)) return DPC_ERR_ARG;
+    micro_introns(p, &i1, &i2, &i3, &i4, &gapchar, &type);
+    r.left_prob = r.right_prob = 0.0;
+    r.introntype = type;
+    const double pvalue = p.defect_rate < 0.003 ? 0.01 : p.defect_rate < 0.014 ? 0.001 : 0.0001;
+    int minlen = (int)ceil(-log(1.0 - pow(1.0 - pvalue, 1.0 / (double)(ro - lo))) / log(4));
+    minlen -= 8;
+    if (minlen > 12) { r.introntype = 0; return 0; }                   /* MAX_MICROEXON_LENGTH, 7222-7227 */
+    if (minlen < 3) minlen = 3;
+    int leftbound = 0, rightbound = 0, nmm = 0, i;
+    while (leftbound < L1 - 1 && nmm <= 1) { if ((char)dpc_query_uc(p.seq1[leftbound]) != host_genomic_nt(p, lo + leftbound)) nmm++; leftbound++; }
+    leftbound--;
+    i = L1 - 1; nmm = 0;
+    while (i >= 0 && nmm <= 1) { if ((char)dpc_query_uc(p.seq1[i]) != host_genomic_nt(p, ro - rightbound)) nmm++; rightbound++; i--; }
+    rightbound--;
+    MicroProb mp;
+    mp.problem = (int)probs.size();
+    for (int cL = 1; cL <= leftbound; cL++) {
+      if (!(host_genomic_nt(p, lo + cL) == i1 && host_genomic_nt(p, lo + cL + 1) == i2)) continue;
+      int mincR = L1 - 12 - cL, maxcR = L1 - minlen - cL;
+      if (mincR < 1) mincR = 1;
+      if (maxcR > rightbound) maxcR = rightbound;
+      for (int cR = mincR; cR <= maxcR; cR++) {
+        if (!(host_genomic_nt(p, ro - cR - 1) == i3 && host_genomic_nt(p, ro - cR) == i4)) continue;
+        MicroCand c;
+        c.cL = cL; c.cR = cR; c.mid = L1 - cL - cR; c.textleft = lo + cL + DPC_MICROINTRON; c.query = -1;
+        const int textlen = (ro - cR - DPC_MICROINTRON) - c.textleft;
+        uint32_t pat = 0; bool okay = c.mid >= 1 && c.mid <= 16;
+        for (int k = 0; k < c.mid && okay; k++) {                      /* query_okay, boyer-moore.c:268 */
+          const int ch = dpc_query_uc(p.seq1[cL + k]);
+          const int code = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+          if (code < 0) okay = false; else pat |= (uint32_t)code << (2 * k);
+        }
+        if (okay && textlen - c.mid >= 0) {
+          ScanQuery q;
+          memset(&q, 0, sizeof q);
+          q.gbase = p.chroffset + p.chrpos; q.glen = p.genomiclength; q.textleft = c.textleft; q.npos = textlen - c.mid + 1;
+          q.pat = pat; q.len = (uint8_t)c.mid; q.watson = p.watsonp ? 1 : 0;
+          if (hits_total + (uint64_t)q.npos > (64ull << 20)) return DPC_ERR_NOMEM;
+          q.hits_off = (uint32_t)hits_total; hits_total += (uint64_t)q.npos;
+          c.query = (int)scans.size();
+          scans.push_back(q);
+        }
+        mp.cands.push_back(c);
+      }
+    }
+    if (mp.cands.empty()) { r.introntype = 0; return 0; }              /* no candidate pair: nothing to scan, NULL */
+    h.micro = (int)micro.size();
+    micro.push_back(mp);
+    return 0;
+  }
+  /* ... and after them: flanks of every hit (7327-7330), MaxEnt probabilities through the hook (7336-7372), the best
+     pair, and make_microexon_pairs_double (6941-7053) around the LAST hit looked at (sic, 7401).  hits / count: what
+     the device scan returned (positions j, any order). */
+  void finalize_micro(MicroProb &mp, const uint32_t *hits, const uint32_t *count) {
+    const dpc_problem_t &p = P(mp.problem);
+    dpc_result_t &r = R(mp.problem);
+    const dpc_setup_t &su = G().setup;
+    const int lo = p.offset2, ro = p.offset2R;
+    char i1, i2, i3, i4, gapchar; int type;
+    micro_introns(p, &i1, &i2, &i3, &i4, &gapchar, &type);
+    int bestcL = -1, bestcR = -1, bestmid = 0, candidate = 0;
+    double bestprob = 0.0;
+    std::vector<uint32_t> js;
+    for (size_t k = 0; k < mp.cands.size(); k++) {
+      const MicroCand &c = mp.cands[k];
+      if (c.query < 0) continue;
+      const ScanQuery &q = scans[(size_t)c.query];
+      js.assign(hits + q.hits_off, hits + q.hits_off + count[c.query]);
+      std::sort(js.begin(), js.end(), std::greater<uint32_t>());      /* BoyerMoore_nt pushes its hits: highest position first */
+      for (size_t t = 0; t < js.size(); t++) {
+        candidate = c.textleft + (int)js[t];
+        if (!(host_genomic_nt(p, candidate - 2) == i3 && host_genomic_nt(p, candidate - 1) == i4 &&
+              host_genomic_nt(p, candidate + c.mid) == i1 && host_genomic_nt(p, candidate + c.mid + 1) == i2)) continue;
+        uint32_t s2, s3; int w2, w3;
+        if (p.watsonp) {
+          s2 = p.chrpos + (uint32_t)(candidate - 1) + 1; s3 = p.chrpos + (uint32_t)(candidate + c.mid);
+          if (p.cdna_direction > 0) { w2 = 1; w3 = 0; } else { w2 = 2; w3 = 3; }
+        } else {
+          s2 = p.chrpos + (p.genomiclength - 1) - (uint32_t)(candidate - 1); s3 = p.chrpos + (p.genomiclength - 1) - (uint32_t)(candidate + c.mid) + 1;
+          if (p.cdna_direction > 0) { w2 = 3; w3 = 2; } else { w2 = 0; w3 = 1; }
+        }
+        const double prob2 = su.splice_prob(w2, p.chroffset + s2, p.chroffset, su.user);
+        const double prob3 = su.splice_prob(w3, p.chroffset + s3, p.chroffset, su.user);
+        if (prob2 + prob3 > bestprob) { bestcL = c.cL; bestcR = c.cR; bestmid = c.mid; r.left_prob = prob2; r.right_prob = prob3; bestprob = prob2 + prob3; }
+      }
+    }
+    mp.pairs.clear();
+    if (bestcL < 0 || bestcR < 0) { r.introntype = 0; r.npairs = 0; r.null_list = 1; return; }
+    std::vector<dpc_pair_t> st;
+    Out o;
+    st.resize((size_t)(bestcL + bestmid + bestcR + 2));
+    o.p = st.data(); o.n = 0;
+    const int off1[3] = { p.offset1, p.offset1 + bestcL, p.offset1 + bestcL + bestmid };
+    const int off2[3] = { lo, candidate, ro - bestcR + 1 }, len[3] = { bestcL, bestmid, bestcR };
+    for (int part = 0; part < 3; part++) {
+      if (part > 0) o.push(-1, -1, ' ', gapchar, ' ', 0, 1);           /* gapholder with comp = gapchar, 6979-6982 */
+      for (int k = 0; k < len[part]; k++) {
+        const char c1 = p.seq1[off1[part] - p.offset1 + k], c2 = host_genomic_nt(p, off2[part] + k);
+        const char comp = (char)dpc_query_uc(c1) == c2 ? '*' : G().CONS[c1 & 127][c2 & 127] ? ':' : ' ';
+        o.push(off1[part] + k, off2[part] + k, c1, comp, c2, p.dynprogindex, 0);
+      }
+    }
+    mp.pairs.assign(st.rbegin(), st.rend());                          /* the list comes back as pushed: last pair first */
+    r.npairs = (int32_t)mp.pairs.size(); r.null_list = 0;
+    r.dynprogindex_out = bump(p.dynprogindex);
+  }
+
   /* ticket API: copies the problem */
   int add(const dpc_problem_t &in) {
     if (ext) return DPC_ERR_STATE;
@@ -423,7 +560,7 @@ struct Batch {
     Globals &g = G();
     if (!g.inited || !g.setup_done) return DPC_ERR_STATE;
     HostProb h;
-    h.q0 = h.q1 = h.aux = 0; h.dev = -1; h.L1 = p.length1; h.L2 = p.length2; h.gout = DPC_NO_GOUT;
+    h.q0 = h.q1 = h.aux = 0; h.dev = -1; h.L1 = p.length1; h.L2 = p.length2; h.gout = DPC_NO_GOUT; h.micro = -1;
     result_init(r, p);
     dprobs.reserve(dprobs.size() + 1);
     DevProb &d = dprobs.data()[dprobs.size()];      /* built in place; committed below when it goes to the device */
@@ -612,6 +749,11 @@ struct Batch {
       d.q0 = h.q0 = pool_put(p.seq1, span);
       d.q1 = h.q1 = d.q0 + (uint32_t)(span - 1);
       todev = true;
+      break;
+    }
+    case DPC_MICROEXON_INT: {                                          /* Dynprog_microexon_int, 7127-7429 */
+      int rc = add_micro(p, r, h);
+      if (rc < 0) return rc;
       break;
     }
     default:

@@ -126,6 +126,14 @@ __global__ void __launch_bounds__(256, ((KG == 0 || KG == 3) ? (V == V_NARROW ? 
   }
 }
 
+/* the exact-match scans of Dynprog_microexon_int (one block per scan; dpc_core.h: ScanQuery) */
+__global__ void __launch_bounds__(256) dpc_microexon_scan_kernel(const ScanQuery *queries, const uint32_t *blocks, uint64_t nbases,
+                                                                 uint32_t *hits, unsigned int *count) {
+  const ScanQuery q = queries[blockIdx.x];
+  for (int j = threadIdx.x; j < q.npos; j += blockDim.x)
+    if (dpc_scan_match(q, blocks, nbases, j)) hits[q.hits_off + atomicAdd(&count[blockIdx.x], 1u)] = (uint32_t)j;
+}
+
 typedef void (*kernel_fn)(const KernelArgs);
 /* [variant][kind group][generic]; the generic test hook runs the narrow class in the V_WIDE instantiation */
 static kernel_fn kernel_of(int v, int kg, bool gen, int claim = 1) {
@@ -275,6 +283,11 @@ struct Engine {
   PBuf<uint8_t> h_gout;
   PBuf<unsigned int> h_counters;
   PBuf<uint32_t> list;
+  DBuf<ScanQuery> d_scans;           /* microexon searches */
+  DBuf<uint32_t> d_hits;
+  DBuf<unsigned int> d_hitcount;
+  PBuf<uint32_t> h_hits;
+  PBuf<unsigned int> h_hitcount;
   std::vector<uint16_t> cls;
   std::vector<ClassLaunch> launches;
   Scratch scratch;
@@ -299,6 +312,7 @@ struct Engine {
     CK(cudaEventCreate(&ev1));
     batch.pool.set_alloc(pinned()); batch.dprobs.set_alloc(pinned());
     h_res.set_alloc(pinned()); h_ovf.set_alloc(pinned()); h_gout.set_alloc(pinned()); h_counters.set_alloc(pinned()); list.set_alloc(pinned());
+    h_hits.set_alloc(pinned()); h_hitcount.set_alloc(pinned()); batch.scans.set_alloc(pinned());
     live = true;
     return DPC_OK;
   }
@@ -307,7 +321,7 @@ struct Engine {
     cudaSetDevice(device);
     cudaStreamSynchronize(stream);
     d_probs.release(); d_pool.release(); d_scratch.release(); d_gout.release(); d_res.release(); d_list.release();
-    d_ovf.release(); d_counters.release();
+    d_ovf.release(); d_counters.release(); d_scans.release(); d_hits.release(); d_hitcount.release();
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaStreamDestroy(stream);
     live = false;
   }
@@ -368,6 +382,21 @@ struct Engine {
     const size_t n = b.dprobs.size();
     launches.clear();
     h2d_bytes = d2h_bytes = 0;
+    if (!b.scans.empty()) {
+      /* Dynprog_microexon_int: exact-match scans of the microexon candidates over their introns */
+      const size_t nq = b.scans.size();
+      int rc;
+      if ((rc = d_scans.need(nq)) || (rc = d_hits.need((size_t)b.hits_total + 16)) || (rc = d_hitcount.need(nq))) return rc;
+      h_hits.clear(); h_hits.grow((size_t)b.hits_total + 16);
+      h_hitcount.clear(); h_hitcount.grow(nq);
+      CK(cudaMemcpyAsync(d_scans.p, b.scans.data(), nq * sizeof(ScanQuery), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemsetAsync(d_hitcount.p, 0, nq * sizeof(unsigned int), stream));
+      dpc_microexon_scan_kernel<<<(unsigned int)nq, 256, 0, stream>>>(d_scans.p, d.d_blocks, G().genome_nbases, d_hits.p, d_hitcount.p);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(h_hitcount.data(), d_hitcount.p, nq * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_hits.data(), d_hits.p, (size_t)b.hits_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      h2d_bytes += (int64_t)(nq * sizeof(ScanQuery)); d2h_bytes += (int64_t)(nq * 4 + b.hits_total * 4);
+    }
     if (n == 0) return DPC_OK;
 
     fill_gen = g_force_generic;                       /* one snapshot per batch: layout and kernels must agree */
@@ -468,6 +497,12 @@ struct Engine {
     if (waited) return DPC_OK;
     Batch &b = batch;
     const size_t n = b.dprobs.size();
+    if (!b.micro.empty()) {
+      CK(cudaSetDevice(device));
+      CK(cudaStreamSynchronize(stream));
+      dirty = false;
+      for (size_t k = 0; k < b.micro.size(); k++) b.finalize_micro(b.micro[k], h_hits.data(), h_hitcount.data());
+    }
     if (n > 0) {
       CK(cudaSetDevice(device));
       CK(cudaStreamSynchronize(stream));
@@ -499,6 +534,11 @@ struct Engine {
 
   int pairs_into(int ticket, dpc_pair_t *dst, bool stream_dst = false) {
     const HostProb &h = batch.probs[ticket];
+    if (h.micro >= 0) {
+      const std::vector<dpc_pair_t> &v = batch.micro[(size_t)h.micro].pairs;
+      if (!v.empty()) memcpy(dst, v.data(), v.size() * sizeof(dpc_pair_t));
+      return (int)v.size();
+    }
     if (h.dev < 0) return 0;
     const DevRes &dr = h_res[h.dev];
     return batch.rebuild(ticket, dr, ops_of(dr), dst, scratch, stream_dst);

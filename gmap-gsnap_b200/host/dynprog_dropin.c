@@ -444,6 +444,7 @@ dropin_memo_spans (const dpc_problem_t *p, const char **a, int *na, const char *
   *a = *b = NULL; *na = *nb = 0;
   if (p->seq1 == NULL || p->length1 <= 0 || p->length1 > 4096) return 0;
   if (p->kind == DPC_END5_SPLICEJUNCTION || p->kind == DPC_END3_SPLICEJUNCTION) return 0;   /* every call has its own junction string */
+  if (p->kind == DPC_MICROEXON_INT) return 0;		/* rare, and its answer depends on the whole intron */
   if (p->kind == DPC_END5_GAP) { *a = p->seq1 - (p->length1 - 1); *na = p->length1; }
   else { *a = p->seq1; *na = p->length1; }
   if (p->kind == DPC_CDNA_GAP) {
@@ -560,6 +561,9 @@ dropin_push_pairs (const dpc_pair_t *rec, int n, int dynprogindex, Pairpool_T pa
       pairs = Pairpool_push_gapholder(pairs,pairpool,/*queryjump*/q->querypos,/*genomejump*/q->genomepos,/*knownp*/true);
     } else if (q->gapp) {
       pairs = Pairpool_push_gapholder(pairs,pairpool,/*queryjump*/UNKNOWNJUMP,/*genomejump*/UNKNOWNJUMP,/*knownp*/false);
+      if (q->comp != ' ') {	/* the intron gapholders of a microexon carry their gap character, dynprog.c:6979-6982 */
+	((Pair_T) List_head(pairs))->comp = q->comp;
+      }
     } else {
       pairs = Pairpool_push(pairs,pairpool,q->querypos,q->genomepos,q->cdna,q->comp,q->genome,dynprogindex);
     }
@@ -852,4 +856,37 @@ Dynprog_end3_splicejunction (int *dynprogindex, int *finalscore, int *nmatches, 
 			       sequence1,sequence2,length1,length2,offset1,offset2_anchor,offset2_far,
 			       chroffset,chrhigh,chrpos,genomiclength,cdna_direction,watsonp,jump_late_p,pairpool,
 			       extraband_end,defect_rate,contlength);
+}
+
+
+/* Dynprog_microexon_int, dynprog.c:7127-7429 (called by traverse_genome_gap, stage3.c:5915, when the intron solution
+   is poor): the exact-match scans of the microexon candidates run on the device, the MaxEnt probabilities of the
+   hits come through the hook. */
+List_T
+Dynprog_microexon_int (double *bestprob2, double *bestprob3, int *dynprogindex, int *microintrontype,
+		       char *sequence1, char *sequenceuc1,
+		       char *sequence2L, char *sequenceuc2L,
+		       char *revsequence2R, char *revsequenceuc2R,
+		       int length1, int length2L, int length2R,
+		       int offset1, int offset2L, int revoffset2R, int cdna_direction,
+		       char *queryseq, char *queryuc, char *genomicseg, char *genomicuc,
+		       Genomicpos_T chroffset, Genomicpos_T chrhigh,
+		       Genomicpos_T chrpos, Genomicpos_T genomiclength, bool watsonp,
+		       bool use_genomicseg_p, Pairpool_T pairpool, double defect_rate) {
+  dpc_problem_t p;
+  dpc_result_t r;
+  List_T pairs;
+
+  (void) sequenceuc1; (void) sequence2L; (void) sequenceuc2L; (void) revsequence2R; (void) revsequenceuc2R;
+  (void) queryseq; (void) queryuc; (void) genomicseg; (void) genomicuc; (void) use_genomicseg_p;
+  dropin_common(&p,DPC_MICROEXON_INT,*dynprogindex,chroffset,chrhigh,chrpos,genomiclength,
+		cdna_direction,watsonp,/*jump_late_p*/false,/*extraband*/0,defect_rate);
+  p.seq1 = sequence1;
+  p.length1 = length1; p.length2 = length2L; p.length2R = length2R;
+  p.offset1 = offset1; p.offset2 = offset2L; p.offset2R = revoffset2R;
+  pairs = dropin_solve(&r,&p,pairpool);
+  *bestprob2 = r.left_prob; *bestprob3 = r.right_prob;
+  *microintrontype = r.introntype;
+  *dynprogindex = r.dynprogindex_out;
+  return pairs;
 }

@@ -16,6 +16,7 @@
  *   Dynprog_end3_gap      dynprog.h:148-161      dpc_add(kind=DPC_END3_GAP)
  *   Dynprog_end5_splicejunction dynprog.h:134-146   dpc_add(kind=DPC_END5_SPLICEJUNCTION)   
  *   Dynprog_end3_splicejunction dynprog.h:163-175   dpc_add(kind=DPC_END3_SPLICEJUNCTION)
+ *   Dynprog_microexon_int       dynprog.h:177-191   dpc_add(kind=DPC_MICROEXON_INT)         
  *   (List_T of Pair_T via Pairpool_push)         dpc_pairs (flat dpc_pair_t records,
  *                                                in the order of the returned List_T)
  *
@@ -53,7 +54,7 @@ enum { DPC_MODE_STANDARD = 0, DPC_MODE_CMET_STRANDED = 1, DPC_MODE_CMET_NONSTRAN
 
 /* which solver a problem is for */
 enum { DPC_SINGLE_GAP = 0, DPC_GENOME_GAP = 1, DPC_CDNA_GAP = 2, DPC_END5_GAP = 3, DPC_END3_GAP = 4,
-       DPC_END5_SPLICEJUNCTION = 5, DPC_END3_SPLICEJUNCTION = 6 };
+       DPC_END5_SPLICEJUNCTION = 5, DPC_END3_SPLICEJUNCTION = 6, DPC_MICROEXON_INT = 7 };
 
 /* error codes (negative return values) */
 enum {
@@ -88,6 +89,13 @@ enum {
  * piece of the genome -- seq1R = (rev)sequence2, length2 its length, upper-case A C G T N only; offset2 =
  * (rev)offset2_anchor, offset2R = (rev)offset2_far; length2R = contlength.  endalign is ignored (the reference
  * always runs find_best_endpoint_to_queryend_indels here).
+ *
+ * Dynprog_microexon_int (dynprog.c:7127-7429: a microexon between two introns, found by an exact scan of the
+ * query's middle piece over the intron, BoyerMoore_nt boyer-moore.c:384) uses the GENOME column: seq1 = sequence1,
+ * length1, offset1, offset2 = offset2L, offset2R = revoffset2R, cdna_direction, defect_rate (length2 / length2R
+ * are not looked at, as in the reference).  Results: left_prob / right_prob = *bestprob2 / *bestprob3, introntype =
+ * *microintrontype; the two gapholders of the returned list carry comp '>' or '<' (dynprog.c:6982, 7021).  The scan
+ * runs on the device; the MaxEnt probabilities of the hits come through the splice_prob hook.
  *
  * "rev" pointers follow the reference convention: they point at the LAST
  * character and are indexed with non-positive offsets (dynprog.c:1674).

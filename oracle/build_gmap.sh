@@ -30,7 +30,7 @@ cp gmap "$OUT/gmap_ref"
 
 CC="${CC:-gcc}"
 CFLAGS=(-DHAVE_CONFIG_H -I. -mpopcnt '-DTARGET="x86_64-unknown-linux-gnu"' '-DGMAPDB="/usr/share/gmapdb"' -O3)
-SYMS="Dynprog_init Dynprog_setup Dynprog_term Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap Dynprog_end5_splicejunction Dynprog_end3_splicejunction"
+SYMS="Dynprog_init Dynprog_setup Dynprog_term Dynprog_single_gap Dynprog_cdna_gap Dynprog_genome_gap Dynprog_end5_gap Dynprog_end3_gap Dynprog_end5_splicejunction Dynprog_end3_splicejunction Dynprog_microexon_int"
 # Only the DEFINITIONS of the replaced functions are renamed (<name>_cpu), in a scratch copy of dynprog.c: the
 # reference writes a function's name at the start of a line where it defines it and indented where it calls it.
 # Calls from the unreplaced functions of dynprog.c (Dynprog_end5_known / Dynprog_end3_known call Dynprog_end5_gap /

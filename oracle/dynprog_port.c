@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <ctype.h>
 #include "../include/dynprog_cuda.h"
 
@@ -348,6 +349,90 @@ static void emit(Stack *out, const dpc_pair_t *v, int n, int reversed) {
     const dpc_pair_t *p = &v[reversed ? n - 1 - i : i];
     push(out, p->querypos, p->genomepos, p->cdna, p->comp, p->genome, p->dynprogindex, p->gapp);
   }
+}
+
+/* ---- Dynprog_microexon_int, 7127-7429 (+ make_microexon_pairs_double 6941-7053, BoyerMoore_nt boyer-moore.c:384) ---- */
+static char bm_nt(const dpc_problem_t *p, int pos) {
+  /* boyer-moore.c:357-381: its own get_genomic_nt, without the segment bounds of dynprog.c:415-419 */
+  if (p->watsonp) return genome_char(p->chroffset + p->chrpos + (uint32_t)pos);
+  return compl_nt(genome_char(p->chroffset + p->chrpos + (p->genomiclength - 1) - (uint32_t)pos));
+}
+static void micro_segment(Stack *st, const dpc_problem_t *p, int off1, int off2, int len, int idx) {
+  for (int i = 0; i < len; i++) {
+    char c1 = p->seq1[off1 - p->offset1 + i], c2 = genomic_nt(off2 + i, p);
+    char comp = query_uc(c1) == c2 ? '*' : CONS[c1 & 127][c2 & 127] ? ':' : ' ';
+    push(st, off1 + i, off2 + i, c1, comp, c2, idx, 0);
+  }
+}
+static int solve_microexon(const dpc_problem_t *p, dpc_result_t *res, Stack *out) {
+  const int L1 = p->length1, lo = p->offset2, ro = p->offset2R;
+  const double pvalue = p->defect_rate < 0.003 ? 0.01 : p->defect_rate < 0.014 ? 0.001 : 0.0001;     /* 128-130, 7160-7166 */
+  char i1, i2, i3, i4, gapchar;
+  int bestcL = -1, bestcR = -1, bestmid = 0, candidate = 0;
+  double bestprob = 0.0;
+  res->left_prob = res->right_prob = 0.0;
+  if (p->cdna_direction > 0) { i1 = 'G'; i2 = 'T'; i3 = 'A'; i4 = 'G'; gapchar = '>'; res->introntype = 0x20; }
+  else if (p->cdna_direction < 0) { i1 = 'C'; i2 = 'T'; i3 = 'A'; i4 = 'C'; gapchar = '<'; res->introntype = 0x04; }
+  else return DPC_ERR_ARG;                                                  /* abort(), 7192 */
+  const int span = ro - lo;
+  if (span <= 0 || L1 <= 0) return DPC_ERR_ARG;                             /* abort(), 7215 */
+  int minlen = (int)ceil(-log(1.0 - pow(1.0 - pvalue, 1.0 / (double)span)) / log(4));
+  minlen -= 8;
+  if (minlen > 12) { res->introntype = 0; return 0; }                       /* MAX_MICROEXON_LENGTH, 7222-7227 */
+  if (minlen < 3) minlen = 3;
+  int leftbound = 0, rightbound = 0, nmm = 0, i;
+  while (leftbound < L1 - 1 && nmm <= 1) { if (query_uc(p->seq1[leftbound]) != genomic_nt(lo + leftbound, p)) nmm++; leftbound++; }
+  leftbound--;
+  i = L1 - 1; nmm = 0;
+  while (i >= 0 && nmm <= 1) { if (query_uc(p->seq1[i]) != genomic_nt(ro - rightbound, p)) nmm++; rightbound++; i--; }
+  rightbound--;
+  for (int cL = 1; cL <= leftbound; cL++) {
+    if (!(genomic_nt(lo + cL, p) == i1 && genomic_nt(lo + cL + 1, p) == i2)) continue;
+    int mincR = L1 - 12 - cL, maxcR = L1 - minlen - cL;
+    if (mincR < 1) mincR = 1;
+    if (maxcR > rightbound) maxcR = rightbound;
+    for (int cR = mincR; cR <= maxcR; cR++) {
+      if (!(genomic_nt(ro - cR - 1, p) == i3 && genomic_nt(ro - cR, p) == i4)) continue;
+      const int mid = L1 - cL - cR, textleft = lo + cL + 9, textright = ro - cR - 9, textlen = textright - textleft;
+      int okay = 1;
+      for (int k = 0; k < mid; k++) { char c = query_uc(p->seq1[cL + k]); if (c != 'A' && c != 'C' && c != 'G' && c != 'T') okay = 0; }
+      if (!okay) continue;
+      /* BoyerMoore_nt pushes its hits on a list: they come back highest position first */
+      for (int j = textlen - mid; j >= 0; j--) {
+        int k = 0;
+        while (k < mid && query_uc(p->seq1[cL + k]) == bm_nt(p, textleft + j + k)) k++;
+        if (k < mid) continue;
+        candidate = textleft + j;                                           /* sic: assigned for every hit, 7326 */
+        if (genomic_nt(candidate - 2, p) == i3 && genomic_nt(candidate - 1, p) == i4 &&
+            genomic_nt(candidate + mid, p) == i1 && genomic_nt(candidate + mid + 1, p) == i2) {
+          uint32_t s2, s3; int w2, w3;
+          if (p->watsonp) {
+            s2 = p->chrpos + (uint32_t)(candidate - 1) + 1; s3 = p->chrpos + (uint32_t)(candidate + mid);
+            if (p->cdna_direction > 0) { w2 = 1; w3 = 0; } else { w2 = 2; w3 = 3; }
+          } else {
+            s2 = p->chrpos + (p->genomiclength - 1) - (uint32_t)(candidate - 1); s3 = p->chrpos + (p->genomiclength - 1) - (uint32_t)(candidate + mid) + 1;
+            if (p->cdna_direction > 0) { w2 = 3; w3 = 2; } else { w2 = 0; w3 = 1; }
+          }
+          const double prob2 = g_setup.splice_prob(w2, p->chroffset + s2, p->chroffset, g_setup.user);
+          const double prob3 = g_setup.splice_prob(w3, p->chroffset + s3, p->chroffset, g_setup.user);
+          if (prob2 + prob3 > bestprob) { bestcL = cL; bestcR = cR; bestmid = mid; res->left_prob = prob2; res->right_prob = prob3; bestprob = prob2 + prob3; }
+        }
+      }
+    }
+  }
+  if (bestcL < 0 || bestcR < 0) { res->introntype = 0; return 0; }
+  Stack st = { 0, 0, 0 };
+  /* make_microexon_pairs_double with offset2M = candidate: the LAST hit looked at, not the best one (7401) */
+  micro_segment(&st, p, p->offset1, lo, bestcL, p->dynprogindex);
+  push(&st, -1, -1, ' ', gapchar, ' ', 0, 1);
+  micro_segment(&st, p, p->offset1 + bestcL, candidate, bestmid, p->dynprogindex);
+  push(&st, -1, -1, ' ', gapchar, ' ', 0, 1);
+  micro_segment(&st, p, p->offset1 + bestcL + bestmid, ro - bestcR + 1, bestcR, p->dynprogindex);
+  emit(out, st.v, st.n, 1);                                                 /* the list is returned as pushed: last pair first */
+  res->npairs = st.n; res->null_list = 0;
+  res->dynprogindex_out = bump(p->dynprogindex);
+  free(st.v);
+  return 0;
 }
 
 /* ---- Dynprog_single_gap, 4450-4572 ------------------------------------------ */
@@ -776,6 +861,7 @@ int port_solve(const dpc_problem_t *problems, int n, dpc_result_t *results,
     case DPC_END3_GAP: rc = solve_end(p, &results[i], &out, 0); break;
     case DPC_END5_SPLICEJUNCTION: rc = solve_splicejunction(p, &results[i], &out, 1); break;
     case DPC_END3_SPLICEJUNCTION: rc = solve_splicejunction(p, &results[i], &out, 0); break;
+    case DPC_MICROEXON_INT: rc = solve_microexon(p, &results[i], &out); break;
     default: rc = DPC_ERR_ARG;
     }
     if (rc != 0) { free(out.v); return rc; }

@@ -240,6 +240,17 @@ static List_T call_one(Worker *w, const dpc_problem_t *p, dpc_result_t *r) {
                                         p->cdna_direction, p->watsonp, p->jump_late_p, w->pool,
                                         p->extraband, p->defect_rate, /*contlength*/ p->length2R);
     break;
+  case DPC_MICROEXON_INT: {
+    /* queryseq / queryuc are addressed with absolute query offsets (offset1 + i): rebase the piece */
+    char *uc = uc_fwd(w->uc, p->seq1, len1);
+    lprob = rprob = 0.0;
+    pairs = Dynprog_microexon_int(&lprob, &rprob, &idx, &introntype, (char *)p->seq1, uc, NULL, NULL, NULL, NULL,
+                                  p->length1, p->length2, p->length2R, p->offset1, p->offset2, p->offset2R, p->cdna_direction,
+                                  (char *)p->seq1 - p->offset1, uc - p->offset1, NULL, NULL,
+                                  p->chroffset, p->chrhigh, p->chrpos, p->genomiclength, p->watsonp,
+                                  /*use_genomicseg_p*/ false, w->pool, p->defect_rate);
+    break;
+  }
   default:
     break;
   }

@@ -158,12 +158,28 @@ extern "C" int emul_solve(const dpc_problem_t *problems, int n, dpc_result_t *re
       dpc_solve_problem<RowFill, -1, -1>(b.dprobs[k], b.pool.data(), dpc::G().setup.genome_blocks, &dpc::G().tables, base, arena_bytes, sbase, &dres[k], ovf, gout.data(), rfill, ln);
   }
   b.gout_host = g_no_gout ? NULL : gout.data();     /* NULL: the rebuild decodes the 2-bit genome itself (ticket users without the stream) */
+  if (!b.micro.empty()) {
+    /* Dynprog_microexon_int: the device's exact-match scans, hits written back to front to show that their order is free */
+    std::vector<uint32_t> hits((size_t)b.hits_total + 1), count(b.scans.size(), 0);
+    for (size_t q = 0; q < b.scans.size(); q++)
+      for (int j = b.scans[q].npos - 1; j >= 0; j--)
+        if (dpc_scan_match(b.scans[q], dpc::G().setup.genome_blocks, dpc::G().genome_nbases, j)) hits[b.scans[q].hits_off + count[q]++] = (uint32_t)j;
+    for (size_t k = 0; k < b.micro.size(); k++) b.finalize_micro(b.micro[k], hits.data(), count.data());
+  }
   int64_t out = 0;
   dpc::Scratch sc;
   std::vector<dpc_pair_t> st;
   for (int i = 0; i < n; i++) {
     dpc::HostProb &h = b.probs[i];
     if (pair_off) pair_off[i] = out;
+    if (h.micro >= 0) {
+      const std::vector<dpc_pair_t> &v = b.micro[(size_t)h.micro].pairs;
+      if (pairs && !v.empty()) {
+        if (out + (int64_t)v.size() > pair_cap) return DPC_ERR_NOMEM;
+        memcpy(pairs + out, v.data(), v.size() * sizeof(dpc_pair_t));
+      }
+      out += (int64_t)v.size();
+    }
     if (h.dev >= 0) {
       const DevRes &dr = dres[h.dev];
       const uint16_t *ops = (dr.nopsL + dr.nopsR > DPC_INLINE_OPS) ? ovfbuf.data() + dr.ovf : dr.ops;

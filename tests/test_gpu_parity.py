@@ -339,3 +339,28 @@ def test_multi_device_context(workload, ref):
         assert not api.compare(*o.solve(probs), *lib.solve(probs))
     finally:
         lib.close()
+
+
+def test_microexon_search(solve_path):
+    """Dynprog_microexon_int: exact-match scans on the device, flanks / MaxEnt / pair assembly on
+    the host; against the compiled reference, alone and mixed into a batch of other kinds."""
+    w = api.Workload(6_000_000, seed=29, nchr=3)
+    probs = w.microexon_problems(1500, seed=93, span_hi=30000)
+    r = checkers.RefOracle()
+    r.init()
+    r.setup(w.make_setup())
+    s = w.make_setup(splice_prob=r.splice_prob)
+    r.setup(s)
+    lib = api.CudaLib()
+    lib.init()
+    lib.setup(s)
+    lib.open(0)
+    try:
+        want = r.solve(probs)
+        assert (want[0]["null_list"] == 0).sum() > 700
+        assert not api.compare(*want, *lib.solve(probs), rtol=RTOL)
+        mixed = np.concatenate([probs[:300], w.single_gaps(500, seed=94), w.end_gaps(500, seed=95)])
+        mixed = mixed[np.random.default_rng(5).permutation(len(mixed))]
+        assert not api.compare(*r.solve(mixed), *lib.solve(mixed), rtol=RTOL)
+    finally:
+        lib.close()

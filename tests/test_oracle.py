@@ -282,3 +282,24 @@ def test_device_pipeline_routines_on_cpu(workload, port, emul, golden, golden_po
         emul.set_path(0)
         emul.setup(emul._setup)
         port.setup(port._setup)
+
+
+def test_microexon_search(ref, port, emul):
+    """Dynprog_microexon_int (dynprog.c:7127-7429): compiled reference == restatement == the
+    library's host logic around the (here CPU-run) device scan.  Planted microexons of 3-12 nt with GT..AG / CT..AC
+    introns, decoy copies, flank mismatches, N and lower-case query letters, problems without a microexon."""
+    w = api.Workload(3_000_000, seed=23, nchr=3)
+    probs = w.microexon_problems(600, seed=92)
+    r = checkers.RefOracle()
+    r.init()
+    r.setup(w.make_setup())                                   # Maxent_hr needs the genome registered first
+    s = w.make_setup(splice_prob=r.splice_prob)
+    r.setup(s)
+    o, e = checkers.PortOracle(), checkers.EmulLib()
+    o.init(); e.init()
+    o.setup(s); e.setup(s)
+    want = r.solve(probs)
+    found = int((want[0]["null_list"] == 0).sum())
+    assert 300 < found < 600 and ((want[1]["gapp"] == 1) & ((want[1]["comp"] == b">") | (want[1]["comp"] == b"<"))).sum() == 2 * found
+    assert not api.compare(*want, *o.solve(probs))
+    assert not api.compare(*want, *e.solve(probs))
