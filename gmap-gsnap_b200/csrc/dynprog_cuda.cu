@@ -196,7 +196,13 @@ static int ensure_device(int dev) {
     else if (e && !strcmp(e, "spin")) cudaSetDeviceFlags(cudaDeviceScheduleSpin);
     cudaGetLastError();
   }
-  if (d.ready) { cudaFree(d.d_blocks); cudaFree(d.d_tables); d.ready = false; }
+  if (d.ready) {
+    /* dpc_init / dpc_setup were called again: the genome mirror and the tables are replaced.  Work queued by live
+       contexts must have drained (re-registration while solver calls are in flight is a caller error; waiting for
+       the device at least keeps queued kernels off freed memory). */
+    cudaDeviceSynchronize();
+    cudaFree(d.d_blocks); cudaFree(d.d_tables); d.ready = false;
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   if (prop.major < 10) {
@@ -242,6 +248,8 @@ static void *pinned_alloc(size_t n) {
 }
 static void pinned_release(void *p) { cudaFreeHost(p); }
 static Alloc pinned() { Alloc a = { pinned_alloc, pinned_release }; return a; }
+
+static int solve_grid(const DeviceState &dv, int variant, int kg, bool gen, size_t smem, int nproblems);
 
 struct ClassLaunch {
   int variant;                     /* V_* */
@@ -351,12 +359,8 @@ struct Engine {
       a.claim = L.claim;
       const int threads = L.wpb * 32;
       const size_t smem = L.variant != V_HBM ? (size_t)L.wpb * L.arena_bytes : 0;
-      int per_sm = 1;
       const kernel_fn fn = kernel_of(L.variant, L.kg, fill_gen != 0, L.claim);
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, threads, smem));
-      if (per_sm < 1) per_sm = 1;
-      int grid = (L.n + L.wpb - 1) / L.wpb;
-      if (grid > d.sm_count * per_sm) grid = d.sm_count * per_sm;
+      const int grid = solve_grid(d, L.variant, L.kg, fill_gen != 0, smem, L.n);       /* occupancy query cached per kernel */
       fn<<<grid, threads, smem, stream>>>(a);
       CK(cudaGetLastError());
       nlaunch++;

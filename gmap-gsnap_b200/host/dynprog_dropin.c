@@ -365,6 +365,18 @@ dropin_scheduler (void *data) {
 
 /* Replaces pthread_create for the workers of gmap.c:3920 / gsnap.c: the new OS thread runs `start_routine` (the
    reference's worker_thread) DPC_FIBERS times as fibers.  DPC_FIBERS=1 gives the plain thread back. */
+/* Process-wide glibc malloc policy (INTEGRATION.md section 3 says so prominently): no mmap for large blocks, no
+   trimming, a 256 MB top pad per arena.  Applied once, from the first fibered worker; DPC_MALLOC_TUNING=0 skips it. */
+static void
+dropin_malloc_tuning (void) {
+  const char *m = getenv("DPC_MALLOC_TUNING");
+  if (m == NULL || atoi(m) != 0) {
+    mallopt(M_MMAP_MAX,0);
+    mallopt(M_TRIM_THRESHOLD,INT_MAX);
+    mallopt(M_TOP_PAD,256 << 20);
+  }
+}
+
 int
 Dynprog_cuda_worker_create (pthread_t *thread, const pthread_attr_t *attr, void *(*start_routine) (void *), void *arg) {
   const char *e = getenv("DPC_FIBERS");
@@ -377,14 +389,8 @@ Dynprog_cuda_worker_create (pthread_t *thread, const pthread_attr_t *attr, void 
        tables, diagonals, pair pools); with glibc's defaults every one of them is mapped, faulted in and unmapped
        again under the process-wide mmap lock.  Keep freed memory in the arenas instead (measured on the
        whole-program bench: 9.2 M -> 4.5 M page faults, 29 s -> 8 s of system time).  DPC_MALLOC_TUNING=0 skips it. */
-    static int tuned = 0;
-    const char *m = getenv("DPC_MALLOC_TUNING");
-    if (!tuned && (m == NULL || atoi(m) != 0)) {
-      mallopt(M_MMAP_MAX,0);
-      mallopt(M_TRIM_THRESHOLD,INT_MAX);
-      mallopt(M_TOP_PAD,256 << 20);
-    }
-    tuned = 1;
+    static pthread_once_t tuned = PTHREAD_ONCE_INIT;
+    pthread_once(&tuned,dropin_malloc_tuning);
   }
   s = (dropin_sched_t *) calloc(1,sizeof(*s));
   s->fibers = (dropin_fiber_t *) calloc(nfibers,sizeof(dropin_fiber_t));
@@ -502,7 +508,10 @@ dropin_memo_find (const dpc_problem_t *p, dpc_problem_t *key, uint64_t *hash, in
       break;
     default: lo = p->offset2; hi = p->offset2 + p->length2 - 1; break;
     }
-    if (lo >= 0 && hi >= lo && (Genomicpos_T) hi < p->genomiclength) {
+    /* ... provided the segment itself starts inside the chromosome: otherwise every position reads '*' (415-419),
+       which depends on chroffset + chrpos alone and must stay visible in the key */
+    if (lo >= 0 && hi >= lo && (Genomicpos_T) hi < p->genomiclength &&
+	p->chroffset + p->chrpos >= p->chroffset && p->chroffset + p->chrpos < p->chrhigh) {
       if (!p->watsonp) key->chrpos = p->chrpos + p->genomiclength;
       key->genomiclength = 0;
     }
@@ -533,6 +542,10 @@ dropin_memo_store (dropin_memo_t *e, const dpc_problem_t *p, const dpc_problem_t
      in nindels (counted before end gaps strip leading indel pairs, dynprog.c:5265) */
   any_direction = r->nindels != DPC_UNSET && r->nindels < 9;
   for (i = 0; i < npairs; i++) if (pairs[i].gapp) any_direction = 0;
+  /* an end gap the reference nullified (nmatches + 1 < nmismatches, dynprog.c:5259-5262) returns no pairs, so a
+     genome run that became a gapholder is invisible here: keep such a result for its own direction only */
+  if ((p->kind == DPC_END5_GAP || p->kind == DPC_END3_GAP) && npairs == 0 &&
+      r->nmatches != DPC_UNSET && r->nmatches + 1 < r->nmismatches) any_direction = 0;
   if (!any_direction && key->cdna_direction == 0 && p->cdna_direction != 0) {
     e = &dropin_memo_tab[(hash + (uint64_t) (p->cdna_direction > 0 ? 2 : 1)) % (uint64_t) dropin_memo_n];
   }
