@@ -4,7 +4,8 @@
 usage: ncu_summary.py <workload> <problems> <raw.csv> [<workload> <problems> <raw.csv> ...]
   profiles/r2_<workload>_ncu.csv   one row per launch of the step: the metrics that matter for this kernel
   profiles/r2_traffic.json         DRAM bytes per step per workload (roofline.traffic in bench.py)
-The raw CSV holds the launches of ONE step of `bench.py --kernel-only --workload W --problems N` (solve kernels only).
+The raw CSV holds the solve-kernel launches of `bench.py --kernel-only --workload W` (warm-up passes + one step); the
+rows of the last pass are kept.
 """
 import csv
 import json
@@ -28,6 +29,16 @@ KEEP = [
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
+def last_step(hdr, data):
+    """The capture holds warm-up passes and the timed step: every pass launches the same sequence of (kernel, grid),
+    so the rows of the last pass are the last p rows, p the smallest period of that sequence."""
+    key = [(r[hdr.index("Kernel Name")], r[hdr.index("launch__grid_size")]) for r in data]
+    for p in range(1, len(key) + 1):
+        if len(key) % p == 0 and all(key[i] == key[i % p] for i in range(len(key))):
+            return data[-p:]
+    return data
+
+
 def main():
     out_json = os.path.join(ROOT, "profiles", "r2_traffic.json")
     traffic = json.load(open(out_json)) if os.path.exists(out_json) else {}
@@ -36,6 +47,7 @@ def main():
         workload, problems, path = args[k], int(args[k + 1]), args[k + 2]
         rows = list(csv.reader(open(path)))
         hdr, units, data = rows[0], rows[1], rows[2:]
+        data = last_step(hdr, data)
         cols = [hdr.index(c) for c in KEEP if c in hdr]
         dst = os.path.join(ROOT, "profiles", "r2_%s_ncu.csv" % workload)
         with open(dst, "w", newline="") as f:
