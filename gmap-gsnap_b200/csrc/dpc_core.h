@@ -666,7 +666,11 @@ DPC_HD void dpc_bridge_cdna(Bridge &br, const Mat &mL, const Mat &mR, const DevP
 }
 
 /* ---- arena layout (shared by host sizing and the kernel) --------------------------------- */
-struct MatDims { int rows, cols, lband, rband, W, wstride, planes, cpl; };
+struct MatDims {
+  int rows, cols, lband, rband, W, wstride, planes, cpl;
+  int padL, padR;           /* bytes of valid filler before colch[0] / after the sentinel colch[cols]: the row sweep reads the
+                               column code of EVERY diagonal a lane owns, in or out of the matrix (dpc_rows.h) */
+};
 struct ArenaLayout {
   int nmat;
   int fused;                             /* genome gap whose bridge runs inside the R sweep (no stored R band) */
@@ -699,6 +703,14 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
     d.planes = fillmode == 2 && d.W <= 32 * DPC_MAX_CPL;
     if (fillmode == 2 && !d.planes) need_state = 1;
     if (d.rows > maxrows) maxrows = d.rows;
+    /* row sweep with the query as rows: in row r lane l reads column index r + cpl*(l+1) - lband - 1 (0-based) for the
+       NEXT row, r = 0..rows: from cpl - lband - 1 up to rows + 32*cpl - lband - 1 */
+    d.padL = d.padR = 0;
+    if (d.planes && p.kind != 2) {
+      d.padL = d.lband + 1 - d.cpl > 0 ? d.lband + 1 - d.cpl : 0;
+      const int last = d.rows + 32 * d.cpl - d.lband - 1;
+      d.padR = last > d.cols ? last - d.cols : 0;
+    }
   }
   /* genome gap, the common case (bands of at most 32 diagonals, integer mode, no known sites): the intron bridge
      runs inside the sweep of the R matrix against the stored band of L, so R's band is never stored */
@@ -707,7 +719,7 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
   for (int i = 0; i < a.nmat; i++) {
     const MatDims &d = a.d[i];
     a.rowch[i] = so; so = dpc_al(so + (uint32_t)d.rows + 2, 4);
-    a.colch[i] = so; so = dpc_al(so + (uint32_t)d.cols + 2, 4);
+    a.colch[i] = so + (uint32_t)d.padL; so = dpc_al(so + (uint32_t)(d.padL + d.cols + 2 + d.padR), 4);
     a.di[i] = so;
     if (p.kind == 1) so = dpc_al(so + (uint32_t)d.cols + 2, 4);         /* dinucleotide code per column (intron bridge) */
     a.dir[i] = bo;
@@ -732,6 +744,12 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *small, ui
   m.planes = d.planes; m.cpl = d.cpl; m.cplsh = d.cpl == 1 ? 0 : d.cpl == 2 ? 1 : 2;
   m.dir = (uint32_t *)(bulk + a.dir[i]);
   m.nband = (a.nmat == 2 && !(a.fused && i == 1)) ? (int16_t *)(bulk + a.nband[i]) : (int16_t *)0;
+}
+
+/* filler around the staged columns of matrix i (MatDims::padL / padR): any valid genome code */
+DPC_HD void dpc_stage_pads(const Mat &m, const MatDims &d, const Lanes &ln) {
+  for (int i = ln.lane; i < d.padL; i += ln.n) m.colch[-1 - i] = 7;
+  for (int i = ln.lane; i < d.padR; i += ln.n) m.colch[d.cols + 1 + i] = 7;
 }
 
 /* ---- one problem ------------------------------------------------------------------------------ */
@@ -819,7 +837,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
       dpc_make_mat(m0, a, 0, arena, bulk, p, five ? !late : late, 1);
       for (int i = ln.lane; i < p.L1; i += ln.n) {
         int q = pool[five ? p.q0 + (uint32_t)(p.L1 - 1 - i) : p.q0 + (uint32_t)i];
-        m0.rowch[i] = (uint8_t)q;
+        m0.rowch[i] = (uint8_t)(q & 127);            /* query bytes are < 128 (checked when the problem is accepted) */
       }
       if (p.flags & DPC_F_SEQ2) {
         /* Dynprog_end5/3_splicejunction 5411-5552, 5869-6012: use_genomicseg_p, sequence2 = the splice-junction string */
@@ -832,6 +850,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         }
       }
       if (ln.lane == 0) m0.colch[p.L2] = 7;                               /* sentinel one past the last column */
+      dpc_stage_pads(m0, a.d[0], ln);
       DPC_SYNC();
       EndSearch es; es.eb = p.extraband;
       if (kind == 0) { es.mode = 3; es.best.score = -2147483647; es.best.key = 0; }
@@ -853,7 +872,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         /* Dynprog_genome_gap 4798-5061: L = fwd(query, genome @ offset2L), R = rev(query, genome @ revoffset2R) */
         for (int i = ln.lane; i < p.L1; i += ln.n) {
           int qf = pool[p.q0 + (uint32_t)i], qr = pool[p.q0 + (uint32_t)(p.L1 - 1 - i)];
-          m0.rowch[i] = (uint8_t)qf; m1.rowch[i] = (uint8_t)qr;
+          m0.rowch[i] = (uint8_t)(qf & 127); m1.rowch[i] = (uint8_t)(qr & 127);
         }
         for (int i = ln.lane; i < p.L2; i += ln.n) {
           const int g = dpc_genomic_code(p, blocks, p.off2 + i);
@@ -866,6 +885,7 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
           if (gch) gch[dpc_gout_span(p.L2) + (uint32_t)i] = (uint8_t)dpc_code_char(g);
         }
         if (ln.lane == 0) { m0.colch[p.L2] = 7; m1.colch[p.L2R] = 7; }    /* leftdi[length2L-1] = rightdi[length2R-1] = 0, 3354, 3376 */
+        dpc_stage_pads(m0, a.d[0], ln); dpc_stage_pads(m1, a.d[1], ln);
       } else {
         /* Dynprog_cdna_gap 4577-4793: rows = genome (fwd from offset2 / rev from offset2+length2-1) */
         for (int i = ln.lane; i < p.L2; i += ln.n) {

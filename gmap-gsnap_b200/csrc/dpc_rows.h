@@ -48,17 +48,20 @@
  * NEG-ish operands belong to cells the traceback cannot reach (it follows real-valued chains) and the bridges
  * only read in-band cells.  Everything a reachable cell can observe is exact. */
 template <int CPL> struct RowState {
-  vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], cm1[CPL];
+  vec::VI Np[CPL], G1p[CPL], G2p[CPL], sh[CPL], kE[CPL], okE[CPL], cm1[CPL];
   vec::VM kok[CPL], ebok[CPL];
   vec::VI bs, bk;
+  vec::VP colp;                   /* QROWS: colp[r] = code of the column that enters the lane's last diagonal after row r */
+  vec::VI oU, eU;                 /* open / extend for the gap2 move into the lane's last diagonal: + NEG on lane 31 */
+  vec::VI send;                   /* NEG on lane 31, else 0: what lane 31 hands to lane 0 in the prefix scan must lose */
   uint32_t b0;                    /* plane 0 (the nogap state did not come from nogap) of the row just swept, first diagonal set */
   int rowq;                       /* score-table row of the NEXT matrix row's character (loaded one row ahead) */
 };
 
 /* offset of the score-table row of matrix row r (1-based): query rows index score[q][.], genome rows score[.][g] */
 template <bool QROWS> DPC_VFN int dpc_rows_rowq(const Mat &m, int r) {
-  const int ch = (int)m.rowch[r - 1];
-  return QROWS ? (ch & 127) << 3 : ch;
+  const int ch = (int)m.rowch[r - 1];          /* query rows are staged masked to 7 bits */
+  return QROWS ? ch << 3 : ch;
 }
 
 template <int CPL, bool QROWS>
@@ -68,6 +71,12 @@ DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) 
   const VI lane = lane_index();
   s.bs = splat(es.best.score); s.bk = splat(es.best.key);
   s.rowq = dpc_rows_rowq<QROWS>(m, 1);
+  s.colp = vptr(m.colch, lane * CPL + (CPL - 1 - lband));
+  s.send = vsel(lane == 31, DPC_NEG, 0);
+  /* (r-1, c) of lane 31's last diagonal lies beyond everything the warp owns: NEG, as 1501-1507 force it.  Lane 31
+     reads its own values there (a shuffle that keeps) and pays NEG on the way in -- NEG-ish either way */
+  s.oU = vsel(lane == 31, open + DPC_NEG, open);
+  s.eU = vsel(lane == 31, extend + DPC_NEG, extend);
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
     const VI k = lane * CPL + j;
@@ -75,6 +84,7 @@ DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) 
     /* diagonals past the band (k >= W; they exist because a lane owns CPL of them) get NEG here: their gap1 then
        stays NEG-ish instead of inheriting the real prefix maximum of the band, and with it their nogap value */
     s.kE[j] = vsel(s.kok[j], k * extend, DPC_NEG);
+    s.okE[j] = open - s.kE[j];
     s.ebok[j] = vand(k >= lband - es.eb, k <= lband + es.eb);
     const VI c0 = k - lband;                              /* column of this diagonal in row 0 */
     s.cm1[j] = vsel(s.kok[j], c0 - 1, 1 << 24);           /* c - 1 = r + cm1; diagonals past the band never become valid */
@@ -87,6 +97,7 @@ DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) 
     const VI ch = load_u8(m.colch, vsel(vlt_u(c0, L2), c0, 0));
     s.sh[j] = QROWS ? ch : ((ch & 127) << 3);
   }
+  if (CPL == 1) s.okE[0] = s.okE[0] + s.send;             /* one diagonal per lane: the scan feed is the lane total */
 }
 
 /* one row of one matrix */
@@ -101,8 +112,8 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
   s.rowq = dpc_rows_rowq<QROWS>(m, r + 1);                /* rowch has two bytes of padding past the last row */
   (void)L1;
   /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */
-  const VI upN = shfl_down1(s.Np[0], DPC_NEG), upG2 = shfl_down1(s.G2p[0], DPC_NEG);
-  VI Nn[CPL], G2n[CPL], a2[CPL], li[CPL];
+  const VI upN = shfl_down1_keep(s.Np[0]), upG2 = shfl_down1_keep(s.G2p[0]);
+  VI Nn[CPL], G2n[CPL], sv[CPL], li[CPL];
   VM p1[CPL], p2[CPL], pv[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
@@ -116,38 +127,47 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
     /* gap2, 1532-1542 */
     const VI Nu = j + 1 < CPL ? s.Np[j + 1 < CPL ? j + 1 : j] : upN;
     const VI G2u = j + 1 < CPL ? s.G2p[j + 1 < CPL ? j + 1 : j] : upG2;
-    const VI a = Nu + open;
+    const VI a = j + 1 < CPL ? Nu + open : Nu + s.oU;
     VM ge;
     VI g2m;
     if (LATE) { g2m = vmax_ge(G2u, a, ge); pv[j] = ge; } else { g2m = vmax_ge(a, G2u, ge); pv[j] = vnot(ge); }
-    G2n[j] = g2m + extend;
+    G2n[j] = j + 1 < CPL ? g2m + extend : g2m + s.eU;
     /* gap1 feed: nogap + open - k*extend, running maximum inside the lane */
-    a2[j] = Nn[j] + open;
-    const VI sv = a2[j] - s.kE[j];
-    li[j] = j == 0 ? sv : vmax(li[j > 0 ? j - 1 : 0], sv);
+    sv[j] = Nn[j] + s.okE[j];
+    li[j] = j == 0 ? sv[j] : vmax(li[j > 0 ? j - 1 : 0], sv[j]);
   }
-  /* exclusive prefix maximum of the lane totals (1519-1529 unrolled along the row) */
-  VI t = shfl_up(li[CPL - 1], 1, DPC_NEG + extend);
+  /* exclusive prefix maximum of the lane totals (1519-1529 unrolled along the row).  Lane 0 has nothing to its left:
+     it takes lane 31's total, which nobody needs, pushed down by NEG (the forced NEG cell of 1507-1513) */
+  VI t = shfl_rot1(CPL == 1 ? li[0] : li[CPL - 1] + s.send);
   t = vmax(t, shfl_up_keep(t, 1));
   t = vmax(t, shfl_up_keep(t, 2));
   t = vmax(t, shfl_up_keep(t, 4));
   t = vmax(t, shfl_up_keep(t, 8));
   t = vmax(t, shfl_up_keep(t, 16));
   /* next row's column characters: every diagonal moves one column to the right */
-  {
+  if (QROWS) {
+    /* every lane reads the code that enters its last diagonal; the staged columns carry filler on both sides
+       (MatDims::padL / padR), so no index is clamped */
+#pragma unroll
+    for (int j = 0; j + 1 < CPL; j++) s.sh[j] = s.sh[j + 1];
+    s.sh[CPL - 1] = load_u8p(s.colp, r);
+  } else {
     /* column index entering at the last diagonal: r + 32*CPL - lband - 1 >= 1 because lband < W <= 32*CPL;
        past the matrix the staged sentinel colch[L2] is read (those diagonals are out of the matrix anyway) */
     const int gi = r + 32 * CPL - lband - 1;
     const int chn = (int)m.colch[gi < L2 ? gi : L2];
-    const VI nxt = shfl_down1(s.sh[0], QROWS ? chn : ((chn & 127) << 3));
+    const VI nxt = shfl_down1(s.sh[0], (chn & 127) << 3);
 #pragma unroll
     for (int j = 0; j + 1 < CPL; j++) s.sh[j] = s.sh[j + 1];
     s.sh[CPL - 1] = nxt;
   }
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
-    const VI G1n = (j == 0 ? t : vmax(t, li[j > 0 ? j - 1 : 0])) + s.kE[j];
-    const VM h = LATE ? (G1n >= a2[j]) : (G1n > a2[j]);
+    /* gap1 = k*extend + prefix maximum; it came from gap1 (HORIZ) when that beats nogap + open of the same cell:
+       compared before k*extend is added to both sides */
+    const VI tm = j == 0 ? t : vmax(t, li[j > 0 ? j - 1 : 0]);
+    const VI G1n = tm + s.kE[j];
+    const VM h = LATE ? (tm >= sv[j]) : (tm > sv[j]);
     /* directions: four ballots, one 16-byte store */
     const uint32_t b0 = vballot(p1[j]), b1 = vballot(p2[j]), b2 = vballot(h), b3 = vballot(pv[j]);
     store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);

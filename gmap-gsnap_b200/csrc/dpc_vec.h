@@ -39,6 +39,14 @@ DPC_V VI shfl_down1(VI v, VI fill) {
   int t = __shfl_down_sync(0xffffffffu, v, 1u);
   return (threadIdx.x & 31) == 31 ? fill : t;
 }
+/* value of lane l+1; lane 31 keeps its own */
+DPC_V VI shfl_down1_keep(VI v) { return __shfl_down_sync(0xffffffffu, v, 1u); }
+/* value of lane l-1; lane 0 gets lane 31's */
+DPC_V VI shfl_rot1(VI v) { return __shfl_sync(0xffffffffu, v, (int)((threadIdx.x + 31u) & 31u)); }
+/* a per-lane byte pointer (base + idx), kept in a register across a loop; read at a uniform offset */
+typedef const uint8_t *VP;
+DPC_V VP vptr(const uint8_t *base, VI idx) { return base + idx; }
+DPC_V VI load_u8p(VP p, int off) { return p[off]; }
 DPC_V int shfl_get(VI v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 DPC_V uint32_t vballot(VM m) { return __ballot_sync(0xffffffffu, m); }
 DPC_V VI load_u8(const uint8_t *base, VI idx) { return base[idx]; }
@@ -114,6 +122,11 @@ DPC_V VI shfl_up(const VI &v, int delta, int fill) { return shfl_up(v, delta, sp
 DPC_V VI shfl_up_keep(const VI &v, int delta) { VI r; DPC_VLOOP r.v[l] = l < delta ? v.v[l] : v.v[l - delta]; return r; }
 DPC_V VI shfl_down1(const VI &v, const VI &fill) { VI r; DPC_VLOOP r.v[l] = l == 31 ? fill.v[l] : v.v[l + 1]; return r; }
 DPC_V VI shfl_down1(const VI &v, int fill) { return shfl_down1(v, splat(fill)); }
+DPC_V VI shfl_down1_keep(const VI &v) { VI r; DPC_VLOOP r.v[l] = l == 31 ? v.v[l] : v.v[l + 1]; return r; }
+DPC_V VI shfl_rot1(const VI &v) { VI r; DPC_VLOOP r.v[l] = v.v[(l + 31) & 31]; return r; }
+struct VP { const uint8_t *base; VI idx; };
+DPC_V VP vptr(const uint8_t *base, const VI &idx) { VP p; p.base = base; p.idx = idx; return p; }
+DPC_V VI load_u8p(const VP &p, int off) { VI r; DPC_VLOOP r.v[l] = p.base[p.idx.v[l] + off]; return r; }
 DPC_V int shfl_get(const VI &v, int lane) { return v.v[lane & 31]; }
 DPC_V uint32_t vballot(const VM &m) { uint32_t b = 0; DPC_VLOOP if (m.v[l]) b |= 1u << l; return b; }
 DPC_V VI load_u8(const uint8_t *base, const VI &idx) { VI r; DPC_VLOOP r.v[l] = base[idx.v[l]]; return r; }
