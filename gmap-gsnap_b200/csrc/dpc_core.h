@@ -692,7 +692,10 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
   uint32_t so = 0, bo = 0;
   int maxrows = 0, need_state = fillmode == 1;
   a.nmat = (p.kind == 1 || p.kind == 2) ? 2 : 1;
-  for (int i = 0; i < a.nmat; i++) {
+  /* constant trip counts: with a runtime bound the compiler indexes `a` dynamically and keeps it in local memory */
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    if (i >= a.nmat) break;
     MatDims &d = a.d[i];
     if (p.kind == 2) { d.rows = p.L2; d.cols = i ? p.L1R : p.L1; }
     else { d.rows = p.L1; d.cols = i ? p.L2R : p.L2; }
@@ -716,12 +719,14 @@ DPC_HB void dpc_layout(const DevProb &p, ArenaLayout &a, int fillmode) {
      runs inside the sweep of the R matrix against the stored band of L, so R's band is never stored */
   a.fused = p.kind == 1 && a.d[0].planes && a.d[1].planes && a.d[0].cpl == 1 && a.d[1].cpl == 1 &&
             !(p.flags & (DPC_F_PROBMODE | DPC_F_KNOWN | DPC_F_INTRONS));
-  for (int i = 0; i < a.nmat; i++) {
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    if (i >= a.nmat) break;
     const MatDims &d = a.d[i];
     a.rowch[i] = so; so = dpc_al(so + (uint32_t)d.rows + 2, 4);
     a.colch[i] = so + (uint32_t)d.padL; so = dpc_al(so + (uint32_t)(d.padL + d.cols + 2 + d.padR), 4);
-    a.di[i] = so;
-    if (p.kind == 1) so = dpc_al(so + (uint32_t)d.cols + 2, 4);         /* dinucleotide code per column (intron bridge) */
+    a.di[i] = so + (uint32_t)d.padL;
+    if (p.kind == 1) so = dpc_al(so + (uint32_t)(d.padL + d.cols + 2 + d.padR), 4);   /* dinucleotide code per column (intron bridge), filler like colch */
     a.dir[i] = bo;
     if (d.planes) bo += (uint32_t)d.rows * (uint32_t)d.cpl * 16; else bo += (uint32_t)d.rows * (uint32_t)d.wstride * 4;
     if (a.nmat == 2 && !(a.fused && i == 1)) { a.nband[i] = bo; bo = dpc_al(bo + (uint32_t)d.rows * (uint32_t)d.W * 2, 16); } else a.nband[i] = 0;
@@ -750,6 +755,11 @@ DPC_HD void dpc_make_mat(Mat &m, const ArenaLayout &a, int i, uint8_t *small, ui
 DPC_HD void dpc_stage_pads(const Mat &m, const MatDims &d, const Lanes &ln) {
   for (int i = ln.lane; i < d.padL; i += ln.n) m.colch[-1 - i] = 7;
   for (int i = ln.lane; i < d.padR; i += ln.n) m.colch[d.cols + 1 + i] = 7;
+}
+/* the same around the dinucleotide codes of the intron bridge: everything outside [0, cols) */
+DPC_HD void dpc_stage_dipads(uint8_t *di, const MatDims &d, const Lanes &ln) {
+  for (int i = ln.lane; i < d.padL; i += ln.n) di[-1 - i] = 0;
+  for (int i = ln.lane; i < d.padR + 2; i += ln.n) di[d.cols + i] = 0;
 }
 
 /* ---- one problem ------------------------------------------------------------------------------ */
@@ -904,6 +914,9 @@ DPC_HD void dpc_solve_problem(const DevProb &p, const uint8_t *pool, const uint3
         /* both sweeps and the bridge in one pass (no stored R band) */
         uint8_t *ldi = arena + a.di[0], *rdi = arena + a.di[1];
         int8_t *itab = (int8_t *)(arena + a.itab);
+        /* filler on both sides of the dinucleotide codes (the fused bridge reads one per lane and row, in or out of
+           the matrix): everything outside [0, length2) */
+        dpc_stage_dipads(ldi, a.d[0], ln); dpc_stage_dipads(rdi, a.d[1], ln);
         dpc_bridge_tables(m0, m1, p, ldi, rdi, itab, ln);
         Best best; best.score = DPC_BRIDGE_FLOOR; best.key = 0x7fffffff;
         fill.pair_bridge(m0, m1, score, p, ldi, rdi, itab, best, ln);

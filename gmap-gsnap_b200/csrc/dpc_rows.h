@@ -260,39 +260,45 @@ DPC_VFN void dpc_fill_rows_bridge(const Mat &mL, const Mat &mR, const int8_t *sc
   const int L1 = mL.L1, L2L = mL.L2, L2R = mR.L2, eb = p.extraband, gap = p.gap;
   const int rbandL = L2L - L1 + eb, lbandL = eb, lbandR = eb;      /* 3545-3549 */
   const VI lane = lane_index();
-  const VI kL = vmin(lane, mL.W - 1);
-  /* lanes that own a diagonal of the band: c <= r + rband, and c >= r - lband holds for every lane */
-  const VM inL = lane < mL.W, inR = lane < mR.W;
+  /* lanes that own a diagonal of the band: c <= r + rband, and c >= r - lband holds for every lane.  c - 1 = x + r;
+     a lane without a diagonal gets an x that never passes the range test below */
+  const VI xL = vsel(lane < mL.W, lane - (mL.lband + 1), 1 << 24), xR = vsel(lane < mR.W, lane - (mR.lband + 1), 1 << 24);
+  /* per-lane views that slide one position per row: the dinucleotide codes of column c = lane + r - lband (the
+     arrays carry the same filler as the staged columns, MatDims::padL / padR) and the lane's diagonal of L's band */
+  const VP ldiP = vptr(ldi, lane - mL.lband), rdiP = vptr(rdi, lane - mR.lband);
+  const VPS bandL = vptr16(mL.nband, vmin(lane, mL.W - 1));
   /* Per lane the candidates come in DESCENDING scan order -- rL downwards, right scan before left scan -- so "the
      first best in scan order" is "the last one that is at least as good": one >= per candidate, no key compare.
      A lane remembers where its best came from as rL * 2 + (1 for the right scan); the scan-order key is made
      from that once, at the end. */
   VI bs = splat(best.score), bw = splat(-1);
+  int offL = (L1 - 1) * mL.W;                  /* row rL of L's band starts at (rL - 1) * W */
   for (int rR = 1; rR < L1; rR++) {            /* row length1 of either matrix is never looked at (3700, 5013) */
     const int rL = L1 - rR;
+    offL -= mL.W;
     /* the stored row of L first, so that its latency hides behind the sweep of R's row */
-    const int16_t *rowL = mL.nband + (rL - 1) * mL.W;
-    const VI vL = load_i16(rowL, kL);
-    const int dL = rowL[mL.lband];                                /* (rL, rL) */
+    const VI vL = load_i16p(bandL, offL);
+    const int dL = mL.nband[offL + mL.lband];                     /* (rL, rL) */
     const uint32_t hL = mL.dir[(rL - 1) * 4];
     const int diR = rdi[rR], diL = ldi[rL];
     dpc_rows_step<1, !LATE, false, false, true>(s, mR, score, rR);
     const VI vR = vmax(s.Np[0], -32768);
     const int dR = extract(vR, mR.lband);                         /* (rR, rR) */
     const uint32_t hR = s.b0;
-    const VI cL = lane + (rL - mL.lband), cR = lane + (rR - mR.lband);
     /* 1 <= c <= length2 - 1 and c < rightoffset - leftoffset - (the other side's column): one unsigned compare */
-    const int upL = (L2L - 1 < gap - rR - 1 ? L2L - 1 : gap - rR - 1), upR = (L2R - 1 < gap - rL - 1 ? L2R - 1 : gap - rL - 1);
+    int upL = gap - rR - 1, upR = gap - rL - 1;
+    upL = upL < L2L - 1 ? upL : L2L - 1; upR = upR < L2R - 1 ? upR : L2R - 1;
+    upL = upL < 0 ? 0 : upL; upR = upR < 0 ? 0 : upR;
     {   /* right scan (3768-3816): cR over the band of row rR, cL = rL; -1 when R's cell was entered through a gap */
-      const VM ok = vand(inR, vlt_u(cR - 1, upR < 0 ? 0 : upR));
-      const VI di = load_u8(rdi, vsel(ok, cR, 0)) & diL;
+      const VM ok = vlt_u(xR + rR, upR);
+      const VI di = load_u8p(rdiP, rR) & diL;
       const VI sc = vR - ((splat((int)hR) >> lane) & 1) + load_i8(itab, di) + dL;
       const VM take = vand(ok, sc >= bs);
       bs = vsel(take, sc, bs); bw = vsel(take, rL * 2 + 1, bw);
     }
     {   /* left scan (3700-3766): cL over the band of row rL, cR = rR */
-      const VM ok = vand(inL, vlt_u(cL - 1, upL < 0 ? 0 : upL));
-      const VI di = load_u8(ldi, vsel(ok, cL, 0)) & diR;
+      const VM ok = vlt_u(xL + rL, upL);
+      const VI di = load_u8p(ldiP, rL) & diR;
       const VI sc = vL - ((splat((int)hL) >> lane) & 1) + load_i8(itab, di) + dR;
       const VM take = vand(ok, sc >= bs);
       bs = vsel(take, sc, bs); bw = vsel(take, rL * 2, bw);

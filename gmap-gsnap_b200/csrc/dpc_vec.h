@@ -47,6 +47,9 @@ DPC_V VI shfl_rot1(VI v) { return __shfl_sync(0xffffffffu, v, (int)((threadIdx.x
 typedef const uint8_t *VP;
 DPC_V VP vptr(const uint8_t *base, VI idx) { return base + idx; }
 DPC_V VI load_u8p(VP p, int off) { return p[off]; }
+typedef const int16_t *VPS;
+DPC_V VPS vptr16(const int16_t *base, VI idx) { return base + idx; }
+DPC_V VI load_i16p(VPS p, int off) { return p[off]; }
 DPC_V int shfl_get(VI v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 DPC_V uint32_t vballot(VM m) { return __ballot_sync(0xffffffffu, m); }
 DPC_V VI load_u8(const uint8_t *base, VI idx) { return base[idx]; }
@@ -127,6 +130,9 @@ DPC_V VI shfl_rot1(const VI &v) { VI r; DPC_VLOOP r.v[l] = v.v[(l + 31) & 31]; r
 struct VP { const uint8_t *base; VI idx; };
 DPC_V VP vptr(const uint8_t *base, const VI &idx) { VP p; p.base = base; p.idx = idx; return p; }
 DPC_V VI load_u8p(const VP &p, int off) { VI r; DPC_VLOOP r.v[l] = p.base[p.idx.v[l] + off]; return r; }
+struct VPS { const int16_t *base; VI idx; };
+DPC_V VPS vptr16(const int16_t *base, const VI &idx) { VPS p; p.base = base; p.idx = idx; return p; }
+DPC_V VI load_i16p(const VPS &p, int off) { VI r; DPC_VLOOP r.v[l] = p.base[p.idx.v[l] + off]; return r; }
 DPC_V int shfl_get(const VI &v, int lane) { return v.v[lane & 31]; }
 DPC_V uint32_t vballot(const VM &m) { uint32_t b = 0; DPC_VLOOP if (m.v[l]) b |= 1u << l; return b; }
 DPC_V VI load_u8(const uint8_t *base, const VI &idx) { VI r; DPC_VLOOP r.v[l] = base[idx.v[l]]; return r; }
