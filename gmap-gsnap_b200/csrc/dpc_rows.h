@@ -52,7 +52,7 @@ template <int CPL> struct RowState {
   vec::VM kok[CPL], ebok[CPL];
   vec::VI bs, bk;
   vec::VP colp;                   /* QROWS: colp[r] = code of the column that enters the lane's last diagonal after row r */
-  vec::VI oU, eU;                 /* open / extend for the gap2 move into the lane's last diagonal: + NEG on lane 31 */
+  vec::VI eU;                     /* extend for the gap2 move into the lane's last diagonal: + NEG on lane 31 */
   vec::VI send;                   /* NEG on lane 31, else 0: what lane 31 hands to lane 0 in the prefix scan must lose */
   uint32_t b0;                    /* plane 0 (the nogap state did not come from nogap) of the row just swept, first diagonal set */
   int rowq;                       /* score-table row of the NEXT matrix row's character (loaded one row ahead) */
@@ -74,8 +74,7 @@ DPC_VFN void dpc_rows_init(RowState<CPL> &s, const Mat &m, const EndSearch &es) 
   s.colp = vptr(m.colch, lane * CPL + (CPL - 1 - lband));
   s.send = vsel(lane == 31, DPC_NEG, 0);
   /* (r-1, c) of lane 31's last diagonal lies beyond everything the warp owns: NEG, as 1501-1507 force it.  Lane 31
-     reads its own values there (a shuffle that keeps) and pays NEG on the way in -- NEG-ish either way */
-  s.oU = vsel(lane == 31, open + DPC_NEG, open);
+     reads its own value there (a shuffle that keeps) and pays NEG on the way in -- NEG-ish either way */
   s.eU = vsel(lane == 31, extend + DPC_NEG, extend);
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
@@ -111,8 +110,13 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
   const int8_t *srow = score + s.rowq;
   s.rowq = dpc_rows_rowq<QROWS>(m, r + 1);                /* rowch has two bytes of padding past the last row */
   (void)L1;
-  /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above */
-  const VI upN = shfl_down1_keep(s.Np[0]), upG2 = shfl_down1_keep(s.G2p[0]);
+  /* (r-1, c) of a lane's last diagonal is the first diagonal of the lane above.  That lane evaluates the gap2 move
+     (1532-1542) from its own registers and hands over the maximum -- one shuffle instead of two; its ballot carries
+     the direction bit one lane too high */
+  VM geU;
+  const VI xU = LATE ? vmax_ge(s.G2p[0], s.Np[0] + open, geU) : vmax_ge(s.Np[0] + open, s.G2p[0], geU);
+  const VI upX = shfl_down1_keep(xU);
+  const uint32_t b3U = vballot(LATE ? geU : vnot(geU)) >> 1;
   VI Nn[CPL], G2n[CPL], sv[CPL], li[CPL];
   VM p1[CPL], p2[CPL], pv[CPL];
 #pragma unroll
@@ -125,13 +129,17 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
     else { p1[j] = s.Np[j] != best; p2[j] = vand(p1[j], s.G1p[j] != best); }
     Nn[j] = best + load_i8(srow, s.sh[j]);
     /* gap2, 1532-1542 */
-    const VI Nu = j + 1 < CPL ? s.Np[j + 1 < CPL ? j + 1 : j] : upN;
-    const VI G2u = j + 1 < CPL ? s.G2p[j + 1 < CPL ? j + 1 : j] : upG2;
-    const VI a = j + 1 < CPL ? Nu + open : Nu + s.oU;
-    VM ge;
-    VI g2m;
-    if (LATE) { g2m = vmax_ge(G2u, a, ge); pv[j] = ge; } else { g2m = vmax_ge(a, G2u, ge); pv[j] = vnot(ge); }
-    G2n[j] = j + 1 < CPL ? g2m + extend : g2m + s.eU;
+    if (j + 1 < CPL) {
+      const VI Nu = s.Np[j + 1 < CPL ? j + 1 : j], G2u = s.G2p[j + 1 < CPL ? j + 1 : j];
+      const VI a = Nu + open;
+      VM ge;
+      VI g2m;
+      if (LATE) { g2m = vmax_ge(G2u, a, ge); pv[j] = ge; } else { g2m = vmax_ge(a, G2u, ge); pv[j] = vnot(ge); }
+      G2n[j] = g2m + extend;
+    } else {
+      G2n[j] = upX + s.eU;
+      pv[j] = geU;                                       /* not used: plane 3 of this diagonal is b3U */
+    }
     /* gap1 feed: nogap + open - k*extend, running maximum inside the lane */
     sv[j] = Nn[j] + s.okE[j];
     li[j] = j == 0 ? sv[j] : vmax(li[j > 0 ? j - 1 : 0], sv[j]);
@@ -169,7 +177,7 @@ DPC_VFN void dpc_rows_step(RowState<CPL> &s, const Mat &m, const int8_t *score, 
     const VI G1n = tm + s.kE[j];
     const VM h = LATE ? (tm >= sv[j]) : (tm > sv[j]);
     /* directions: four ballots, one 16-byte store */
-    const uint32_t b0 = vballot(p1[j]), b1 = vballot(p2[j]), b2 = vballot(h), b3 = vballot(pv[j]);
+    const uint32_t b0 = vballot(p1[j]), b1 = vballot(p2[j]), b2 = vballot(h), b3 = j + 1 < CPL ? vballot(pv[j]) : b3U;
     store4_lane0(m.dir + ((r - 1) * CPL + j) * 4, b0, b1, b2, b3);
     if (j == 0) s.b0 = b0;
     if (NBAND) store_i16(m.nband, lane * CPL + ((r - 1) * W + j), vmax(Nn[j], -32768), s.kok[j]);

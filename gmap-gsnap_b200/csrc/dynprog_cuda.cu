@@ -878,9 +878,12 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
   const int nchunks = (n + chunk - 1) / chunk;
   static const bool timing = getenv("DPC_TIMING") != NULL;
   static const bool stream_pairs = getenv("DPC_NO_STREAM") == NULL;     /* non-temporal stores for rebuilt pair records */
-  static const double link_depth = getenv("DPC_LINK_DEPTH") ? atof(getenv("DPC_LINK_DEPTH")) : 2.0;
+  static const double host_depth = getenv("DPC_HOST_DEPTH") ? atof(getenv("DPC_HOST_DEPTH")) : 2.0;
   static const int env_route = getenv("DPC_ROUTE") ? (!strcmp(getenv("DPC_ROUTE"), "host") ? 1 : !strcmp(getenv("DPC_ROUTE"), "device") ? 0 : -1) : -1;
   const int forced_route = g_path == 3 ? 0 : g_path == 4 ? 1 : env_route;
+  /* tuning aid: DPC_ROUTE_MIX=p sends p percent of the chunks through the host route, evenly spread */
+  static const int env_mix = getenv("DPC_ROUTE_MIX") ? atoi(getenv("DPC_ROUTE_MIX")) : -1;
+  std::atomic<int> mix_acc(0);
   const bool direct = pairs != NULL && host_pinned(pairs, (size_t)pair_cap * sizeof(dpc_pair_t));
   const bool hp_pinned = host_pinned(problems, (size_t)n * sizeof(dpc_problem_t));
   const bool res_pinned = host_pinned(results, (size_t)n * sizeof(dpc_result_t));
@@ -1083,15 +1086,21 @@ int dpc_solve(dpc_ctx_t *c, const dpc_problem_t *problems, int n, dpc_result_t *
                 if (pc.err < 0) r = pc.err;
                 else {
                   jb.mine = pc.pair_total;
-                  /* Who expands this chunk's traceback ops into Pair records?  The device (16 bytes per record over
-                     PCIe) or a worker (the compact device records over PCIe, then the host half's rebuild).  The link
-                     is the scarce resource: once a few pair blocks are queued on it -- enough to keep it busy until
-                     the next chunk is ready -- the next chunk goes to the workers, unless they are behind too. */
+                  /* Who expands this chunk's traceback ops into Pair records?  A worker (the compact device records
+                     over PCIe, ~200 B per problem, then the host half's rebuild) or the device (16 bytes per record
+                     over PCIe, ~900 B per problem).  Measured on B200 boxes (profiles/r2_route_mix.txt): the host
+                     route is the faster one whenever the workers keep up, and a MIX of the two is slower than either
+                     alone -- the copy engine writing 1 GB of records into host memory slows the host threads' own
+                     scans and rebuilds by 2-3 x.  So: host route while the workers have at most `host_depth` chunks
+                     each waiting, device route for what they cannot absorb. */
                   jb.route = 0;
                   if (pairs && jb.mine > 0) {
-                    const bool link_busy = (double)d2h_backlog.load() >= link_depth * (double)jb.mine * sizeof(dpc_pair_t);
-                    const bool workers_free = rebuild_queued.load() < 2 * nworkers;
-                    jb.route = forced_route >= 0 ? forced_route : (link_busy && workers_free ? 1 : 0);
+                    const bool workers_free = (double)rebuild_queued.load() < host_depth * (double)nworkers;
+                    jb.route = forced_route >= 0 ? forced_route : (workers_free ? 1 : 0);
+                    if (forced_route < 0 && env_mix >= 0) {
+                      jb.route = 0;
+                      if (mix_acc.fetch_add(env_mix) % 100 + env_mix >= 100) jb.route = 1;
+                    }
                   }
                   if (jb.route == 0) {
                     jb.queued = pairs ? jb.mine * (int64_t)sizeof(dpc_pair_t) : 0;
