@@ -388,8 +388,8 @@ def measure(args, lib, workload, n, rank, world, local_rank, host_threads, barri
                 "results_only": {"value": total_cells / e2e_results_s / 1e9, "unit": UNIT, "ms_per_step": 1e3 * e2e_results_s,
                                  "note": "dpc_solve with pairs == NULL: scores, end points, intron boundaries, counts"},
                 "includes": "dpc_solve from and into page-locked caller arrays: copy-in of problem records + query bytes, prepare / solve / "
-                            "finish / expand kernels, copy-out of results and %d Pair records (expanded on the device or, when the link "
-                            "is backlogged, by host threads from the compact device records)" % npairs},
+                            "finish / expand kernels, copy-out of results and %d Pair records (expanded by host threads from the compact "
+                            "device records while they keep up, by the device otherwise)" % npairs},
         "gpu_launches": int(launches),
         "parity_checked_ranks": parity_ranks,
         "parity_sample": ("every rank: %d problems of its own shard (stride %d), all result fields and Pair records equal to the compiled "
