@@ -40,7 +40,7 @@ SYMS="Dynprog_init Dynprog_setup Dynprog_term Dynprog_single_gap Dynprog_cdna_ga
 SEDARGS=(); for s in $SYMS; do SEDARGS+=(-e "s/^$s (/${s}_cpu (/"); done
 sed "${SEDARGS[@]}" dynprog.c > cuda-dynprog_cpu.c
 for s in $SYMS; do grep -q "^${s}_cpu (" cuda-dynprog_cpu.c; done
-$CC "${CFLAGS[@]}" -w -c cuda-dynprog_cpu.c -o cuda-dynprog_cpu.o
+$CC "${CFLAGS[@]}" -w -ffunction-sections -c cuda-dynprog_cpu.c -o cuda-dynprog_cpu.o
 $CC "${CFLAGS[@]}" -I"$REPO/include" -Wall -c "$REPO/gmap-gsnap_b200/host/dynprog_dropin.c" -o cuda-dynprog_dropin.o
 # the one-line change to gmap.c: hand the user segment's blocks to the library
 sed 's|^    Genome_user_setup(genome_blocks);|    Genome_user_setup(genome_blocks);\n    { extern void Dynprog_cuda_register_blocks (UINT4 *blocks, unsigned int nwords); Dynprog_cuda_register_blocks(genome_blocks,((Sequence_fulllength(usersegment) + 31)/32U)*3 + 4); }|' gmap.c > cuda-gmap.c
@@ -52,7 +52,14 @@ $CC "${CFLAGS[@]}" -DExcept_stack_create=Dynprog_cuda_except_stack_create -DExce
     -c cuda-gmap.c -o cuda-gmap.o
 OBJS=$(ls gmap-*.o | grep -v -e '^gmap-dynprog.o$' -e '^gmap-gmap.o$')
 $CC -O3 -o "$OUT/gmap_cuda" $OBJS cuda-dynprog_cpu.o cuda-dynprog_dropin.o cuda-gmap.o \
-    -L"$REPO/gmap-gsnap_b200/csrc" -ldynprog_cuda -Wl,-rpath,'$ORIGIN/../../gmap-gsnap_b200/csrc' -lz -lm -lpthread
+    -L"$REPO/gmap-gsnap_b200/csrc" -ldynprog_cuda -Wl,-rpath,'$ORIGIN/../../gmap-gsnap_b200/csrc' -Wl,--gc-sections -lz -lm -lpthread
+# link-time proof that no CPU solver is reachable: every function of the renamed dynprog.c sits in its own section and
+# the linker drops what nothing references -- the replaced solver bodies must be gone from the binary
+for s in $SYMS; do
+  case $s in Dynprog_init|Dynprog_setup|Dynprog_term) continue;; esac
+  if nm "$OUT/gmap_cuda" | grep -q " T ${s}_cpu$"; then echo "build_gmap.sh: ${s}_cpu is still reachable in gmap_cuda" >&2; exit 1; fi
+done
+nm "$OUT/gmap_cuda" | grep -c "_cpu$" > /dev/null
 # index-building tools of the reference (for the whole-program bench on a synthetic genome database, BASELINE config 5)
 make -j"$(nproc)" gmapindex iit_store >> make.log 2>&1
 (cd ../util && make -s fa_coords gmap_process gmap_build >> ../src/make.log 2>&1)
