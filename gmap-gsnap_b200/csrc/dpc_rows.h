@@ -1,6 +1,6 @@
 /* dpc_rows.h -- banded Gotoh fill as a ROW sweep, one warp per matrix, and the lane-parallel traceback walk.
  *
- * Lane l of chunk j owns diagonal k = 32 j + l (k = c - r + lband) for the whole matrix.  Going from row r-1
+ * Lane l owns the CPL adjacent diagonals k = CPL*l + j (k = c - r + lband) for the whole matrix.  Going from row r-1
  * to row r along a diagonal is the recurrence's diagonal move, so
  *   nogap[r][c]  needs the lane's OWN three values of the previous row            (no communication),
  *   gap2 [r][c]  needs nogap/gap2 of (r-1, c)   = diagonal k+1 of the previous row (one shuffle down),
@@ -10,7 +10,7 @@
  *                an exclusive prefix maximum over the lanes: five shuffle+max steps per 32 diagonals.
  * Every lane works on every row (no wavefront ramp, no idle half-warp, no per-lane row bookkeeping) and the
  * control flow is uniform.  Direction bits leave the warp as four ballots per owned diagonal (bit planes) -- 4 bits
- * per cell, written by one 16-byte store per row and chunk.
+ * per cell, written by one 16-byte store per row and owned diagonal.
  *
  * Exactness: max is exact, so the prefix maximum yields exactly the reference's gap1 values; the direction
  * of gap1[k+1] is better(gap1[k], nogap[k] + open), which lane k can evaluate by itself (plane 2 therefore
@@ -42,8 +42,12 @@
  *    left of it, so N and gap1 stay "NEG-ish" (NEG plus a bounded number of score/penalty terms, always far
  *    below any real score) for every c <= 0, and gap2 of column 0 is max(N(r-1,0) + open, gap2(r-1,0)) + extend
  *    = open + r*extend exactly as 1477-1488 set it (N(0,0) + open for r = 1, the gap2 chain afterwards);
- *  - diagonals beyond the band (k >= W, they exist because a lane owns CPL of them) get a constant NEG added to
- *    their nogap value every row, which keeps "NEG above the band" (1501-1507) for the cells that read them.
+ *  - diagonals beyond the band (k >= W, they exist because a lane owns CPL of them) take NEG instead of k*extend
+ *    as their gap1 term, so gap1 -- and through it nogap -- stays NEG-ish there: "NEG above the band" (1501-1507)
+ *    for the cells that read them;
+ *  - the ends of the warp: lane 31 has no lane above and lane 0 none to its left.  Lane 31 reads its own value
+ *    through a shuffle that keeps and pays NEG in its copy of `extend` (RowState::eU); lane 0 takes lane 31's scan
+ *    total, which nobody else needs, pushed down by NEG (RowState::send).  No select in the loop.
  * NEG-ish values never win a max against a real one and never tie with one; the direction bits produced from
  * NEG-ish operands belong to cells the traceback cannot reach (it follows real-valued chains) and the bridges
  * only read in-band cells.  Everything a reachable cell can observe is exact. */
