@@ -264,12 +264,14 @@ struct ClassLaunch {
 /* Launch classes.  Two shared-memory arena sizes: 6 KB per warp leaves most of the 228 KB to L1 (descriptors,
  * genome blocks and query bytes are read through it), 13 KB takes what is bigger (the register file allows at most
  * 2-4 blocks of 8 warps per SM, so 13 KB per warp never limits occupancy below that of the two-matrix kernels).  A
- * problem whose bulk region does not fit keeps it in HBM scratch (V_SPILL); a problem whose small region alone does
- * not fit runs entirely from HBM scratch (V_HBM).  Narrow problems (every band <= 64 diagonals) get the narrow
+ * problem whose bulk region does not fit keeps it in HBM scratch (V_SPILL: only the small region -- characters, bridge
+ * tables, under 4 KB at the largest sizes dpc_init accepts -- sits in shared memory, so the 6 KB arena does and the
+ * launch keeps three blocks per SM); a problem whose small region alone does not fit runs entirely from HBM scratch
+ * (V_HBM).  Narrow problems (every band <= 64 diagonals) get the narrow
  * instantiation. */
 #define NCLASS 6
 static const int k_class_variant[NCLASS] = { V_NARROW, V_NARROW, V_WIDE, V_WIDE, V_SPILL, V_HBM };
-static uint32_t k_class_bytes[NCLASS] = { 6 << 10, 13 << 10, 6 << 10, 13 << 10, 13 << 10, 0 };
+static uint32_t k_class_bytes[NCLASS] = { 6 << 10, 13 << 10, 6 << 10, 13 << 10, 6 << 10, 0 };
 #define NBUCKET 64                       /* work buckets for longest-first scheduling */
 #define SCRATCH_BUDGET (16ull << 30)
 

@@ -57,7 +57,7 @@ extern "C" int emul_set_path(int pipe) { g_pipe = pipe; return 0; }
 static int emul_solve_pipe(const dpc_problem_t *problems, int n, dpc_result_t *results,
                            dpc_pair_t *pairs, int64_t pair_cap, int64_t *pair_off) {
   const dpc::Globals &g = dpc::G();
-  static const uint32_t class_bytes[6] = { 6 << 10, 13 << 10, 6 << 10, 13 << 10, 13 << 10, 0 };
+  static const uint32_t class_bytes[6] = { 6 << 10, 13 << 10, 6 << 10, 13 << 10, 6 << 10, 0 };
   std::vector<uint8_t> pool;
   std::vector<dpc_problem_t> hp(problems, problems + n);
   for (int i = 0; i < n; i++) {          /* gather (the library copies a contiguous range instead when it can) */
