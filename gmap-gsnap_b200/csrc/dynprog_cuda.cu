@@ -649,6 +649,8 @@ int dpc_init(int maxlookback, int extraquerygap, int maxpeelback, int extramater
   g_version++;
   const char *kb = getenv("DPC_CLASS0_KB");          /* tuning aid: size of the small shared-memory class */
   if (kb && atoi(kb) >= 1 && atoi(kb) <= 13) k_class_bytes[0] = k_class_bytes[2] = (uint32_t)atoi(kb) << 10;
+  kb = getenv("DPC_CLASS1_KB");                      /* ... and of the big one */
+  if (kb && atoi(kb) >= 1 && atoi(kb) <= 27) k_class_bytes[1] = k_class_bytes[3] = (uint32_t)atoi(kb) << 10;
   const char *e = getenv("DPC_FORCE_GENERIC_FILL");
   g_force_generic = (e && *e && *e != '0') ? 1 : 0;
   return rc;
