@@ -35,4 +35,26 @@ for seed in range(5000, 5000 + nseeds):
     bad_total += len(bad)
     print("seed %d: %d problems, extraband %d, mismatches %d %s" % (seed, len(probs), eb, len(bad), bad[:2]), flush=True)
 print("FUZZ (emulation) %s: %d seeds, %d mismatching fields, %.0f s" % ("OK" if bad_total == 0 else "FAILED", nseeds, bad_total, time.time() - t0))
-sys.exit(1 if bad_total else 0)
+
+# second part: genome gaps under every flavour of splicing IIT (splice-site / intron level x novel splicing or not)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import util  # noqa: E402
+w = api.Workload(4_000_000, seed=11, n_frac=0.0005, nchr=4)
+bad_iit, n_iit, t0 = 0, 0, time.time()
+for seed in range(7000, 7000 + max(1, nseeds // 6)):
+    for intron_level, novel in util.SPLICING_IIT_MODES:
+        rng = np.random.default_rng(seed * 4 + intron_level * 2 + novel)
+        known, intron = util.splicing_iit_hooks(known_mod=int(rng.choice([2, 3, 5, 17])), intron_mod=int(rng.choice([2, 3, 5])))
+        r = checkers.RefOracle(); r.init()
+        s = w.make_setup(splice_prob=r.splice_prob, splice_known=known, novelsplicingp=novel, splice_intron=intron, intron_level=intron_level)
+        e = checkers.EmulLib(); e.init(); r.setup(s); e.setup(s)
+        probs = w.genome_gaps(300, seed=seed, extraband=int(rng.choice([3, 7, 12])), finalp_mode=2, prob_mode_pm=100, long_frac=0.03,
+                              long_hi=int(rng.choice([150, 400])))
+        r.setup(s); e.setup(s)
+        probs = checkers.arm_probability_mode(probs, r)
+        bad = api.compare(*r.solve(probs), *e.solve(probs), rtol=1e-6)
+        bad_iit += len(bad); n_iit += len(probs)
+        if bad:
+            print("seed %d intron_level %d novel %d: %s" % (seed, intron_level, novel, bad[:2]), flush=True)
+print("FUZZ splicing-IIT modes (emulation) %s: %d problems, %d mismatching fields, %.0f s" % ("OK" if bad_iit == 0 else "FAILED", n_iit, bad_iit, time.time() - t0))
+sys.exit(1 if bad_total or bad_iit else 0)
