@@ -1,9 +1,10 @@
+# Scratch job script for `gpurun -- 'bash tools/gpu_job.sh'` (edited per run; outputs under gpurun_out/, which is not tracked).
+# Default content: the round-end sequence -- smoke, GPU parity tests, the bench line of both arms.
 set -x
-mkdir -p gpurun_out/r3i
+mkdir -p gpurun_out/job
 cd $GRAFT_REPO_ROOT
-O=gpurun_out/r3i
-T=/tmp/ncu_r3i
-mkdir -p $T
-timeout 600 ncu --set full --clock-control none -k regex:dpc_solve_kernel -c 40 -f -o $T/full_genome python bench.py --kernel-only --workload genome --steps 1 --warmup 3 > $O/ncu_f_genome.log 2>&1
-ncu -i $T/full_genome.ncu-rep --page raw --csv > $O/raw_genome.csv 2>$O/raw_genome.err
-ls -la $O
+O=gpurun_out/job
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
+timeout 1800 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest.log
+timeout 900 python bench.py --impl reference > $O/bench_ref.log 2> $O/bench_ref.err; echo "ref rc=$?"
+timeout 900 python bench.py > $O/bench.log 2> $O/bench.err; echo "bench rc=$?"
